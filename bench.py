@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: fused view-synthesis (photometric) loss forward+backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): 640x480, batch 16 per GPU, 2 source frames, 4 scales, fp32, synthetic
+Redwood-shaped geometrically consistent triplets.  One step = one forward + backward of the loss
+for one batch.  Metric: warped pixels per second, B*S*N*H*W / t, whole job.  Prints ONE JSON line on rank 0.
+
+  value        device-timed (CUDA events), inputs resident in HBM, L2 flushed between steps
+  e2e          same step through the public API from pinned HOST buffers: H2D of every input, D2H of the
+               losses and all gradients, inside the timed region
+  roofline     dominant kernel (fused_tile_kernel) timed with events around its launch inside libdvsloss.so;
+               achieved = bytes_alg(B,H,W,N,S) / t   (SURVEY 8d figure, 303.9 B per full-res pixel at N=2,S=4)
+  cpu_baseline the oracle port (op-for-op restatement of the reference's PyTorch path) on the host cores, on a
+               bounded sample (batch 2 of the same workload); rank 0, N=1 only
+  --impl reference   times that CPU path alone (all host threads), same metric/config
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "deep-visual-slam_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+H, W, NSRC, NSCALE = 480, 640, 2, 4
+METRIC = "photometric_loss_fwd_bwd_warped_pixels_per_s"
+UNIT = "Gpix/s"
+
+
+def bytes_alg(B, Hh, Ww, N, S):
+    """compulsory fp32 traffic of one forward + one backward pass."""
+    return B * Hh * Ww * (2 * S * 12 * (1 + N) + 12 * sum(4.0 ** -s for s in range(S)))
+
+
+def bytes_floor(B, Hh, Ww, N, S):
+    """Strict single-pass floor: every image once, disparities read once, gradients written once."""
+    return B * Hh * Ww * (12 * (1 + N) + 8 * sum(4.0 ** -s for s in range(S)))
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(B, seed, device):
+    from dvsloss.synthetic import make_problem, pose_matrix
+    p = make_problem(B, H, W, NSRC, NSCALE, seed=seed, consistent=True)
+    Ts = [pose_matrix(a.view(B, 3), t.view(B, 3), inv) for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+    host = dict(target=p["target"], sources=p["sources"], disps=p["disps"], K=p["K"], inv_K=p["inv_K"], Ts=Ts)
+    return host
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_step(host, B_s):
+    """One fwd+bwd of the oracle port on the CPU for the first B_s items (checker code, timed as baseline)."""
+    from oracle import reference_port as port
+    sl = lambda t: t[:B_s].clone()
+    disps = [sl(d).requires_grad_(True) for d in host["disps"]]
+    Ts = [sl(T).requires_grad_(True) for T in host["Ts"]]
+    noise = [torch.randn(B_s, NSRC, H, W) for _ in range(NSCALE)]        # the reference draws it per scale
+    out = port.view_synthesis_loss(disps, sl(host["target"]), [sl(s) for s in host["sources"]], sl(host["K"]),
+                                   sl(host["inv_K"]), Ts, noise)
+    out["loss"].backward()
+    return float(out["loss"].detach())
+
+
+def time_cpu(host, B_s, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    for _ in range(warmup):
+        cpu_port_step(host, B_s)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_port_step(host, B_s)
+    dt = (time.perf_counter() - t0) / steps
+    return B_s * NSCALE * NSRC * H * W / dt / 1e9, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B_s = args.cpu_batch
+    host = make_inputs(B_s, 0, "cpu")
+    val, dt = time_cpu(host, B_s, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    sample = f"batch {B_s} of the {W}x{H}, {NSRC} sources, {NSCALE} scales workload per step, fp32, torch CPU ops"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"photometric loss fwd+bwd {W}x{H} N={NSRC} S={NSCALE} (bounded CPU sample: batch {B_s})"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    from dvsloss import lib, view_synthesis_loss
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    host = make_inputs(B, rank, "cpu")
+
+    pin = lambda t: t.contiguous().pin_memory()
+    h_in = dict(target=pin(host["target"]), sources=[pin(s) for s in host["sources"]],
+                disps=[pin(d) for d in host["disps"]], K=pin(host["K"]), inv_K=pin(host["inv_K"]),
+                Ts=[pin(T) for T in host["Ts"]])
+    d_in = dict(target=h_in["target"].to(dev), sources=[s.to(dev) for s in h_in["sources"]],
+                disps=[d.to(dev).requires_grad_(True) for d in h_in["disps"]], K=h_in["K"].to(dev),
+                inv_K=h_in["inv_K"].to(dev), Ts=[T.to(dev).requires_grad_(True) for T in h_in["Ts"]])
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
+
+    def step():
+        for t in d_in["disps"] + d_in["Ts"]:
+            t.grad = None
+        loss, per_scale = view_synthesis_loss(d_in["disps"], d_in["target"], d_in["sources"], d_in["K"], d_in["inv_K"],
+                                              d_in["Ts"], noise="kernel")
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in evs:
+        flush.zero_()
+        e0.record()
+        step()
+        e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = sum(e0.elapsed_time(e1) for e0, e1 in evs) / 1e3
+    tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev = float(tt.item())
+    pix_step = B * NSCALE * NSRC * H * W
+    value = world * pix_step * args.steps / t_dev / 1e9
+
+    # ---- dominant kernel alone (events recorded by the library around its launch)
+    L = lib()
+    L.dvs_set_profiling(1)
+    tk = []
+    for _ in range(10):
+        flush.zero_()
+        step()
+        ms = C.c_float(0)
+        if L.dvs_last_tile_kernel_ms(C.byref(ms)) == 0:
+            tk.append(ms.value)
+    L.dvs_set_profiling(0)
+    torch.cuda.synchronize()
+    t_kernel = sum(tk) / len(tk) / 1e3 if tk else None
+
+    # ---- end to end from pinned host buffers
+    d_buf = dict(target=torch.empty_like(d_in["target"]), sources=[torch.empty_like(s) for s in d_in["sources"]],
+                 disps=[torch.empty_like(d).requires_grad_(True) for d in d_in["disps"]], K=torch.empty_like(d_in["K"]),
+                 inv_K=torch.empty_like(d_in["inv_K"]), Ts=[torch.empty_like(T).requires_grad_(True) for T in d_in["Ts"]])
+    h_out = dict(loss=torch.empty(1 + NSCALE).pin_memory(), gd=[torch.empty_like(d).pin_memory() for d in h_in["disps"]],
+                 gT=[torch.empty_like(T).pin_memory() for T in h_in["Ts"]])
+    h2d = sum(t.numel() * 4 for t in [h_in["target"], h_in["K"], h_in["inv_K"]] + h_in["sources"] + h_in["disps"] + h_in["Ts"])
+    d2h = sum(t.numel() * 4 for t in [h_out["loss"]] + h_out["gd"] + h_out["gT"])
+
+    def e2e_step():
+        with torch.no_grad():
+            d_buf["target"].copy_(h_in["target"], non_blocking=True)
+            d_buf["K"].copy_(h_in["K"], non_blocking=True)
+            d_buf["inv_K"].copy_(h_in["inv_K"], non_blocking=True)
+            for a, b in zip(d_buf["sources"] + d_buf["disps"] + d_buf["Ts"], h_in["sources"] + h_in["disps"] + h_in["Ts"]):
+                a.copy_(b, non_blocking=True)
+        for t in d_buf["disps"] + d_buf["Ts"]:
+            t.grad = None
+        loss, per_scale = view_synthesis_loss(d_buf["disps"], d_buf["target"], d_buf["sources"], d_buf["K"],
+                                              d_buf["inv_K"], d_buf["Ts"], noise="kernel")
+        loss.backward()
+        with torch.no_grad():
+            h_out["loss"][:1].copy_(loss.detach().view(1), non_blocking=True)
+            h_out["loss"][1:].copy_(per_scale.detach(), non_blocking=True)
+            for a, t in zip(h_out["gd"] + h_out["gT"], d_buf["disps"] + d_buf["Ts"]):
+                a.copy_(t.grad, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * pix_step * args.steps / float(te.item()) / 1e9
+
+    if rank == 0:
+        peak, how = measured_peak_gbs()
+        ba = bytes_alg(B, H, W, NSRC, NSCALE)
+        roof = None
+        if t_kernel:
+            ach = ba / t_kernel / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "kernel": "fused_tile_kernel<2,true>", "kernel_ms": t_kernel * 1e3, "bytes_alg": ba, "peak_source": how,
+                    "frac_step": ba / (t_dev / args.steps) / 1e9 / peak,
+                    "frac_strict_floor": bytes_floor(B, H, W, NSRC, NSCALE) / t_kernel / 1e9 / peak}
+            tr = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the committed ncu capture
+            if os.path.exists(tr):
+                try:
+                    roof["traffic"] = json.load(open(tr)).get("fused_tile_kernel_dram_bytes")
+                except Exception:
+                    pass
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            B_s = args.cpu_batch
+            val, dt = time_cpu(host, B_s, 2, 1)
+            cpu = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "s_per_step": dt,
+                   "sample": f"batch {B_s} of the same workload, 1 warm-up + 2 timed fwd+bwd of oracle/reference_port.py "
+                             f"(op-for-op the reference's eager PyTorch path) on CPU"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"isolated photometric loss fwd+bwd, {W}x{H}, batch {B}/GPU, {NSRC} sources, {NSCALE} scales "
+                                       f"(BASELINE configs[1]); consistent synthetic triplets; automask noise from the in-kernel generator",
+                           "l2": "256 MB buffer written between timed steps (outside the event pairs)", "sharding": f"batch, {world} independent rank(s), no data-path collective"},
+                "clocks": clocks, "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": 5 * args.steps, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="batch per GPU (BASELINE configs[1]: 16)")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

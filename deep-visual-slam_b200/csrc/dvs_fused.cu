@@ -1,0 +1,445 @@
+// Fused view-synthesis loss for sm_100a: kernels + C ABI (include/dvsloss.h).
+//
+// Launch sequence of dvs_photometric_forward (all on the caller's stream, no host sync):
+//   1. mean_partial_kernel   partial sums of the up-sampled disparity per (scale, image)      [reads disp once]
+//   2. fused_tile_kernel     one CTA per 30x30 tile x image, all scales, loss sums (+ unit gradients)
+//   3. finish_kernel         per (scale, image): fixed-order reduction of the per-CTA partials, pose
+//                            gradient dL/dT = K^T dL/dP, smoothness mean-coupling coefficient
+//   4. final_kernel          loss/s and loss
+// dvs_photometric_backward is one elementwise kernel: grad = g_s * (unit - coupling), pose combine.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dvsloss.h"
+#include "dvs_fused_core.cuh"
+#include "dvs_host.h"
+
+namespace dvs {
+
+// ------------------------------------------------------------------------------------------------ 1. disparity mean
+// mean(up-sample(d)) is a fixed linear functional of d: sum_ij rw[i] cw[j] d[i,j] / (H W); for the
+// exact power-of-two pyramids of the reference the weights are the constant (H/h)(W/w).
+__global__ void __launch_bounds__(256) mean_partial_kernel(FusedParams p, float* mean_part) {
+  const int chunk = blockIdx.x, b = blockIdx.y, s = blockIdx.z;
+  const int h = p.dh[s], w = p.dw[s], n = h * w;
+  const float* d = p.disp[s] + (size_t)b * n;
+  const bool exact = (p.H % h == 0) && (p.W % w == 0);
+  const float cw = exact ? (float)((p.H / h) * (p.W / w)) : 0.f;
+  const int per = (n + kMeanBlocks - 1) / kMeanBlocks;
+  const int lo = chunk * per, hi = min(lo + per, n);
+  float acc = 0.f;
+  for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+    float wgt = cw;
+    if (!exact) {
+      int i = e / w, j = e - i * w;
+      wgt = up_weight(i, h, p.H) * up_weight(j, w, p.W);
+    }
+    acc = fmaf(wgt, d[e], acc);
+  }
+  __shared__ float red[8];
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    mean_part[(s * p.B + b) * kMeanBlocks + chunk] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 2. fused tile kernel
+template <int NS, bool GRAD>
+__global__ void __launch_bounds__(NT, (NS <= 2 ? 2 : 1)) fused_tile_kernel(const __grid_constant__ FusedParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x;
+  const Tile t = make_tile(p, blockIdx.x);
+  ThreadState<NS> st;
+
+  phase_consts<NS>(p, t, sm, tid);
+  phase_load<NS>(p, t, sm, tid);
+  __syncthreads();
+  phase_identity<NS>(p, t, sm, tid, st);
+  __syncthreads();
+
+  for (int s = 0; s < p.S; ++s) {
+    reset_scale_state<NS>(st);
+    phase_warp<NS>(p, t, sm, tid, s);
+    __syncthreads();
+    phase_stats<NS, GRAD>(p, t, sm, tid, s, st);
+    __syncthreads();
+    const bool direct = (p.dh[s] == p.H && p.dw[s] == p.W);
+    if (GRAD) {
+      phase_grad<NS>(p, t, sm, tid, s, st);
+      __syncthreads();
+      if (direct) store_gdu_direct<NS>(p, t, tid, s, st);
+      else stage_gdu<NS>(p, t, sm, tid, st);
+    }
+    reduce_write<NS>(p, sm, tid, st);
+    __syncthreads();
+    if (GRAD && !direct) adjoint_rows<NS>(p, t, sm, tid, s);
+    reduce_stage1<NS>(p, sm, tid);
+    __syncthreads();
+    if (GRAD && !direct) adjoint_cols<NS>(p, t, sm, tid, s);
+    reduce_stage2<NS>(p, t, sm, tid, s);
+    // no barrier needed here: the next phase_warp writes only X/DU, which nobody reads any more
+    // (adjoint_cols / reduce_stage2 read the F region, next written after the following barrier) ...
+    // ... except adjoint_rows' input DU: all threads passed the barrier after adjoint_rows already.
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 3. finish
+// grid (B, S), 256 threads = 8 warps; warp y reduces values v = y, y+8, ... over the tiles of image b in a
+// fixed order (lane-strided, then xor-shuffle) -> deterministic.
+struct FinishParams {
+  int B, H, W, N, S, tiles_per_img, want_grad;
+  float smooth_w;
+  const float* part;        // [nblk][S][nv]
+  const float* mean_part;   // [S][B][kMeanBlocks]
+  const float* K;           // [B,4,4]
+  float* perimg;            // [S][B][3]
+  float* uT;                // [S][N][B][16] or null
+  float* coup;              // [S][B] or null
+};
+__global__ void __launch_bounds__(256) finish_kernel(FinishParams f) {
+  const int b = blockIdx.x, s = blockIdx.y;
+  const int nv = 3 + 12 * f.N;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  __shared__ float res[3 + 12 * kMaxN];
+  for (int v = wy; v < nv; v += 8) {
+    float a = 0.f;
+    for (int tl = lane; tl < f.tiles_per_img; tl += 32)
+      a += f.part[((size_t)(b * f.tiles_per_img + tl) * f.S + s) * nv + v];
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) res[v] = a;
+  }
+  __syncthreads();
+  const int tid = threadIdx.x;
+  if (tid < 3) f.perimg[(s * f.B + b) * 3 + tid] = res[tid];
+  if (!f.want_grad) return;
+  if (tid < 16 * f.N) {
+    // dL/dT[m][k] = sum_{j<3} K[j][m] * dL/dP[j][k]
+    int i = tid / 16, m = (tid % 16) / 4, k = tid % 4;
+    const float* Kb = f.K + b * 16;
+    float a = 0.f;
+    for (int j = 0; j < 3; ++j) a = fmaf(Kb[j * 4 + m], res[3 + 12 * i + j * 4 + k], a);
+    f.uT[(((size_t)s * f.N + i) * f.B + b) * 16 + m * 4 + k] = a;
+  }
+  if (tid == 64) {
+    const float* mp = f.mean_part + (s * f.B + b) * kMeanBlocks;
+    float mu = 0.f;
+    for (int k = 0; k < kMeanBlocks; ++k) mu += mp[k];
+    mu = mu / ((float)f.H * (float)f.W);
+    float inv = 1.0f / (fmaxf(mu, 0.001f) + 1e-7f);
+    float live = mu >= 0.001f ? 1.f : 0.f;
+    float kap = f.smooth_w / (float)(1 << s);
+    float Nx = (float)f.B * (float)f.H * (float)(f.W - 1), Ny = (float)f.B * (float)(f.H - 1) * (float)f.W;
+    // sum_q gn_q * n_q == kappa * (Sx/Nx + Sy/Ny) (Euler: the term is 1-homogeneous in n)
+    f.coup[s * f.B + b] = kap * (res[1] / Nx + res[2] / Ny) * inv * live / ((float)f.H * (float)f.W);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 4. final
+__global__ void final_kernel(const float* perimg, int B, int H, int W, int S, float smooth_w,
+                             float* loss_per_scale, float* loss_total) {
+  __shared__ float ls[kMaxS];
+  int s = threadIdx.x;
+  if (s < S) {
+    float ph = 0.f, sx = 0.f, sy = 0.f;
+    for (int b = 0; b < B; ++b) {
+      ph += perimg[(s * B + b) * 3 + 0];
+      sx += perimg[(s * B + b) * 3 + 1];
+      sy += perimg[(s * B + b) * 3 + 2];
+    }
+    float kap = smooth_w / (float)(1 << s);
+    float Nx = (float)B * (float)H * (float)(W - 1), Ny = (float)B * (float)(H - 1) * (float)W;
+    float l = ph / ((float)B * (float)H * (float)W) + kap * (sx / Nx + sy / Ny);
+    ls[s] = l;
+    loss_per_scale[s] = l;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < S; ++k) t += ls[k];
+    loss_total[0] = t / (float)S;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward (scaling)
+struct BackwardParams {
+  int B, H, W, N, S;
+  int dh[kMaxS], dw[kMaxS];
+  const float* g;                 // [S]
+  const float* u[kMaxS];
+  float* out[kMaxS];
+  const float* uT;                // [S][N][B][16]
+  const float* coup;              // [S][B]
+  float* gT[kMaxN];
+};
+__global__ void __launch_bounds__(256) backward_scale_kernel(BackwardParams q) {
+  const int s = blockIdx.y;
+  if (s == q.S) {   // pose: grad_T[i][b] = sum_s g_s uT[s][i][b]
+    int n = q.N * q.B * 16;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+      int i = e / (q.B * 16), r = e - i * q.B * 16;
+      float a = 0.f;
+      for (int k = 0; k < q.S; ++k) a = fmaf(q.g[k], q.uT[((size_t)k * q.N + i) * q.B * 16 + r], a);
+      q.gT[i][r] = a;
+    }
+    return;
+  }
+  const int h = q.dh[s], w = q.dw[s];
+  const size_t n = (size_t)q.B * h * w;
+  const float gs = q.g[s];
+  const bool exact = (q.H % h == 0) && (q.W % w == 0);
+  const float cwc = exact ? (float)((q.H / h) * (q.W / w)) : 0.f;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    int b = (int)(e / ((size_t)h * w));
+    float wgt = cwc;
+    if (!exact) {
+      int r = (int)(e - (size_t)b * h * w);
+      int i = r / w, j = r - i * w;
+      wgt = up_weight(i, h, q.H) * up_weight(j, w, q.W);
+    }
+    q.out[s][e] = gs * (q.u[s][e] - q.coup[s * q.B + b] * wgt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t mean_part, part, perimg, uT, coup, lossbuf, total;
+  int tiles_x, tiles_y, nblk;
+};
+static WsLayout ws_layout(const DvsShape& sh) {
+  WsLayout w;
+  w.tiles_x = (sh.W + PITCH_X - 1) / PITCH_X;
+  w.tiles_y = (sh.H + PITCH_Y - 1) / PITCH_Y;
+  w.nblk = sh.B * w.tiles_x * w.tiles_y;
+  size_t o = 0;
+  w.mean_part = o; o = align_up(o + sizeof(float) * sh.S * sh.B * kMeanBlocks, 256);
+  w.part = o;      o = align_up(o + sizeof(float) * (size_t)w.nblk * sh.S * nvals(sh.N), 256);
+  w.perimg = o;    o = align_up(o + sizeof(float) * sh.S * sh.B * 3, 256);
+  w.uT = o;        o = align_up(o + sizeof(float) * sh.S * sh.N * sh.B * 16, 256);   // used by backward_recompute
+  w.coup = o;      o = align_up(o + sizeof(float) * sh.S * sh.B, 256);
+  w.lossbuf = o;   o = align_up(o + sizeof(float) * 8, 256);
+  w.total = o;
+  return w;
+}
+
+static int check_shape(const DvsShape* sh) {
+  if (!sh) return DVS_EINVAL;
+  if (sh->B < 1 || sh->H < 2 || sh->W < 2) return DVS_EINVAL;
+  if (sh->N < 1 || sh->N > DVS_MAX_SOURCES || sh->S < 1 || sh->S > DVS_MAX_SCALES) return DVS_EINVAL;
+  for (int s = 0; s < sh->S; ++s)
+    if (sh->dh[s] < 1 || sh->dw[s] < 1 || sh->dh[s] > sh->H || sh->dw[s] > sh->W) return DVS_EINVAL;
+  if ((long long)sh->B * sh->H * sh->W * 3 >= (1LL << 31)) return DVS_EINVAL;   // 32-bit pixel offsets per image set
+  return DVS_OK;
+}
+
+template <int NS, bool GRAD>
+static cudaError_t launch_tile(const FusedParams& p, int nblk, cudaStream_t st) {
+  SmemLayout L{NS};
+  size_t bytes = (size_t)L.total() * sizeof(float);
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fused_tile_kernel<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  fused_tile_kernel<NS, GRAD><<<nblk, NT, bytes, st>>>(p);
+  return cudaGetLastError();
+}
+
+static cudaError_t dispatch_tile(const FusedParams& p, int nblk, cudaStream_t st) {
+  switch (p.N * 2 + (p.want_grad ? 1 : 0)) {
+    case 2: return launch_tile<1, false>(p, nblk, st);
+    case 3: return launch_tile<1, true>(p, nblk, st);
+    case 4: return launch_tile<2, false>(p, nblk, st);
+    case 5: return launch_tile<2, true>(p, nblk, st);
+    case 6: return launch_tile<3, false>(p, nblk, st);
+    case 7: return launch_tile<3, true>(p, nblk, st);
+    case 8: return launch_tile<4, false>(p, nblk, st);
+    case 9: return launch_tile<4, true>(p, nblk, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// Optional timing of the dominant kernel with events on the caller's stream (bench.py roofline leg).
+static bool g_profile = false;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static bool g_ev_valid = false;
+
+static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* const* disp, const float* target,
+                       const float* const* src, const float* K, const float* inv_K, const float* const* T,
+                       const float* const* noise, uint64_t seed, uint64_t offset, float* loss_per_scale,
+                       float* loss_total, uint8_t* const* sel, float* const* ugrad_disp, float* uT, float* coup,
+                       void* workspace, cudaStream_t st) {
+  int rc = check_shape(sh);
+  if (rc) return rc;
+  if (!pr || !disp || !target || !src || !K || !inv_K || !T || !loss_per_scale || !loss_total) return DVS_EINVAL;
+  if (!workspace || ((uintptr_t)workspace & 255)) return DVS_EWORKSPACE;
+  const bool want_grad = ugrad_disp != nullptr;
+  if (want_grad && (!uT || !coup)) return DVS_EINVAL;
+  WsLayout w = ws_layout(*sh);
+  char* base = static_cast<char*>(workspace);
+
+  FusedParams p{};
+  p.B = sh->B; p.H = sh->H; p.W = sh->W; p.N = sh->N; p.S = sh->S;
+  for (int s = 0; s < sh->S; ++s) {
+    if (!disp[s]) return DVS_EINVAL;
+    p.dh[s] = sh->dh[s]; p.dw[s] = sh->dw[s];
+    p.disp[s] = disp[s];
+    p.noise[s] = (noise && pr->auto_mask) ? noise[s] : nullptr;
+    p.sel[s] = sel ? sel[s] : nullptr;
+    p.gdisp[s] = want_grad ? ugrad_disp[s] : nullptr;
+    if (want_grad && !ugrad_disp[s]) return DVS_EINVAL;
+  }
+  for (int i = 0; i < sh->N; ++i) {
+    if (!src[i] || !T[i]) return DVS_EINVAL;
+    p.src[i] = src[i]; p.T[i] = T[i];
+  }
+  p.target = target; p.K = K; p.invK = inv_K;
+  p.seed = seed; p.offset = offset;
+  p.min_disp = 1.0f / pr->max_depth;
+  p.disp_range = 1.0f / pr->min_depth - 1.0f / pr->max_depth;
+  p.ssim_w = pr->ssim_ratio; p.l1_w = 1.0f - pr->ssim_ratio;
+  p.smooth_w = pr->smoothness_ratio; p.eps = pr->eps;
+  p.auto_mask = pr->auto_mask ? 1 : 0;
+  p.want_grad = want_grad ? 1 : 0;
+  p.mean_part = reinterpret_cast<float*>(base + w.mean_part);
+  p.part = reinterpret_cast<float*>(base + w.part);
+  p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y;
+
+  if (want_grad)
+    for (int s = 0; s < sh->S; ++s)
+      if (!(sh->dh[s] == sh->H && sh->dw[s] == sh->W))
+        DVS_CUDA_TRY(cudaMemsetAsync(ugrad_disp[s], 0, sizeof(float) * (size_t)sh->B * sh->dh[s] * sh->dw[s], st));
+
+  mean_partial_kernel<<<dim3(kMeanBlocks, sh->B, sh->S), 256, 0, st>>>(p, reinterpret_cast<float*>(base + w.mean_part));
+  DVS_CUDA_TRY(cudaGetLastError());
+  if (g_profile) {
+    if (!g_ev0) {
+      DVS_CUDA_TRY(cudaEventCreate(&g_ev0));
+      DVS_CUDA_TRY(cudaEventCreate(&g_ev1));
+    }
+    DVS_CUDA_TRY(cudaEventRecord(g_ev0, st));
+  }
+  DVS_CUDA_TRY(dispatch_tile(p, w.nblk, st));
+  if (g_profile) {
+    DVS_CUDA_TRY(cudaEventRecord(g_ev1, st));
+    g_ev_valid = true;
+  }
+
+  FinishParams f{};
+  f.B = sh->B; f.H = sh->H; f.W = sh->W; f.N = sh->N; f.S = sh->S;
+  f.tiles_per_img = w.tiles_x * w.tiles_y; f.want_grad = p.want_grad; f.smooth_w = p.smooth_w;
+  f.part = p.part; f.mean_part = p.mean_part; f.K = K;
+  f.perimg = reinterpret_cast<float*>(base + w.perimg);
+  f.uT = uT; f.coup = coup;
+  finish_kernel<<<dim3(sh->B, sh->S), 256, 0, st>>>(f);
+  DVS_CUDA_TRY(cudaGetLastError());
+  final_kernel<<<1, 32, 0, st>>>(f.perimg, sh->B, sh->H, sh->W, sh->S, p.smooth_w, loss_per_scale, loss_total);
+  DVS_CUDA_TRY(cudaGetLastError());
+  return DVS_OK;
+}
+
+static int run_backward(const DvsShape* sh, const float* g, const float* const* u, const float* uT, const float* coup,
+                        float* const* grad_disp, float* const* grad_T, cudaStream_t st) {
+  BackwardParams q{};
+  q.B = sh->B; q.H = sh->H; q.W = sh->W; q.N = sh->N; q.S = sh->S;
+  q.g = g; q.uT = uT; q.coup = coup;
+  for (int s = 0; s < sh->S; ++s) {
+    if (!u[s] || !grad_disp[s]) return DVS_EINVAL;
+    q.dh[s] = sh->dh[s]; q.dw[s] = sh->dw[s]; q.u[s] = u[s]; q.out[s] = grad_disp[s];
+  }
+  for (int i = 0; i < sh->N; ++i) {
+    if (!grad_T[i]) return DVS_EINVAL;
+    q.gT[i] = grad_T[i];
+  }
+  size_t n0 = (size_t)sh->B * sh->dh[0] * sh->dw[0];
+  int gx = (int)((n0 + 256 * 8 - 1) / (256 * 8));
+  if (gx < 1) gx = 1;
+  if (gx > 148 * 8) gx = 148 * 8;
+  backward_scale_kernel<<<dim3(gx, sh->S + 1), 256, 0, st>>>(q);
+  DVS_CUDA_TRY(cudaGetLastError());
+  return DVS_OK;
+}
+
+}  // namespace dvs
+
+// ================================================================================================ C ABI
+using namespace dvs;
+
+extern "C" int dvs_set_profiling(int enabled) {
+  g_profile = enabled != 0;
+  g_ev_valid = false;
+  return DVS_OK;
+}
+
+extern "C" int dvs_last_tile_kernel_ms(float* ms) {
+  if (!ms) return DVS_EINVAL;
+  if (!g_ev_valid) return DVS_EINVAL;
+  DVS_CUDA_TRY(cudaEventSynchronize(g_ev1));
+  DVS_CUDA_TRY(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+  return DVS_OK;
+}
+
+extern "C" int dvs_loss_workspace_bytes(const DvsShape* shape, size_t* bytes) {
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  if (!bytes) return DVS_EINVAL;
+  *bytes = ws_layout(*shape).total;
+  return DVS_OK;
+}
+
+// ugrad_T buffer = [S,N,B,16] unit pose gradients followed by [S,B] smoothness mean-coupling coefficients.
+static size_t ut_floats(const DvsShape* sh) { return (size_t)sh->S * sh->N * sh->B * 16; }
+
+extern "C" int dvs_photometric_forward(const DvsShape* shape, const DvsParams* params, const float* const* disp,
+                                       const float* target, const float* const* src, const float* K,
+                                       const float* inv_K, const float* const* T, const float* const* noise,
+                                       uint64_t seed, uint64_t offset, float* loss_per_scale, float* loss_total,
+                                       uint8_t* const* sel, float* const* ugrad_disp, float* ugrad_T,
+                                       void* workspace, void* stream) {
+  if ((ugrad_disp == nullptr) != (ugrad_T == nullptr)) return DVS_EINVAL;
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  float* coup = ugrad_T ? ugrad_T + ut_floats(shape) : nullptr;
+  return run_forward(shape, params, disp, target, src, K, inv_K, T, noise, seed, offset, loss_per_scale, loss_total,
+                     sel, ugrad_disp, ugrad_T, coup, workspace, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dvs_photometric_backward(const DvsShape* shape, const float* grad_per_scale,
+                                        const float* const* ugrad_disp, const float* ugrad_T,
+                                        float* const* grad_disp, float* const* grad_T, void* stream) {
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  if (!grad_per_scale || !ugrad_disp || !ugrad_T || !grad_disp || !grad_T) return DVS_EINVAL;
+  return run_backward(shape, grad_per_scale, ugrad_disp, ugrad_T, ugrad_T + ut_floats(shape), grad_disp, grad_T,
+                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dvs_photometric_backward_recompute(const DvsShape* shape, const DvsParams* params,
+                                                  const float* const* disp, const float* target,
+                                                  const float* const* src, const float* K, const float* inv_K,
+                                                  const float* const* T, const float* const* noise, uint64_t seed,
+                                                  uint64_t offset, const float* grad_per_scale,
+                                                  float* const* grad_disp, float* const* grad_T, void* workspace,
+                                                  void* stream) {
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  if (!grad_per_scale || !grad_disp || !grad_T) return DVS_EINVAL;
+  if (!workspace || ((uintptr_t)workspace & 255)) return DVS_EWORKSPACE;
+  WsLayout w = ws_layout(*shape);
+  char* base = static_cast<char*>(workspace);
+  float* uT = reinterpret_cast<float*>(base + w.uT);
+  float* coup = reinterpret_cast<float*>(base + w.coup);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* lp = reinterpret_cast<float*>(base + w.lossbuf);   // losses are recomputed but not returned
+  rc = run_forward(shape, params, disp, target, src, K, inv_K, T, noise, seed, offset, lp, lp + DVS_MAX_SCALES,
+                   nullptr, grad_disp, uT, coup, workspace, st);
+  if (rc) return rc;
+  return run_backward(shape, grad_per_scale, grad_disp, uT, coup, grad_disp, grad_T, st);
+}

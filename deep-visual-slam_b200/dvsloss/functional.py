@@ -1,0 +1,159 @@
+"""PyTorch autograd front-end of the fused view-synthesis loss (CUDA only).
+
+``view_synthesis_loss`` replaces, in one call, what the reference does with ~2 160 ATen launches in
+``MonodepthTrainer._generate_images_pred`` + ``_compute_losses`` (vo/learner_new.py:132-258): it
+returns ``loss`` and the per-scale ``loss/s`` attached to the autograd graph, with gradients flowing to
+the disparity maps and the 4x4 relative poses.  The forward launch already produces the gradients
+of every ``loss/s`` (one pass over the images); backward only scales them by the upstream gradient.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib
+from ._lib import DvsParams, check, fptr_array, lib, make_shape, ptr, require_cuda, stream_ptr, u8ptr_array
+
+_offset_counter = itertools.count()
+
+NoiseArg = Union[str, None, Sequence[torch.Tensor]]
+
+
+def _prep(t: torch.Tensor) -> torch.Tensor:
+    """The kernels compute in fp32 whatever the autocast state (the geometry is
+    unusable in half precision); inputs are up-converted here."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _ViewSynthesisLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg: dict, target, sources, K, inv_K, noise, S: int, N: int, *diff):
+        disps = [_prep(d) for d in diff[:S]]
+        Ts = [_prep(t) for t in diff[S:S + N]]
+        target, K, inv_K = _prep(target), _prep(K), _prep(inv_K)
+        sources = [_prep(s) for s in sources]
+        require_cuda(target, K, inv_K, *disps, *Ts, *sources)
+        dev = target.device
+        B, C3, H, W = target.shape
+        if C3 != 3:
+            raise _lib.DvsError("images must be [B,3,H,W]")
+        for d in disps:
+            if d.dim() != 4 or d.shape[0] != B or d.shape[1] != 1:
+                raise _lib.DvsError(f"disparity maps must be [B,1,h,w], got {tuple(d.shape)}")
+        for s_ in sources:
+            if s_.shape != target.shape:
+                raise _lib.DvsError("source images must have the target's shape")
+        for t in Ts + [K, inv_K]:
+            if tuple(t.shape) != (B, 4, 4):
+                raise _lib.DvsError("K, inv_K and T must be [B,4,4]")
+        shape = make_shape(B, H, W, N, [d.shape[2:] for d in disps])
+        params = DvsParams(cfg["min_depth"], cfg["max_depth"], cfg["ssim_ratio"], cfg["smoothness_ratio"], 1e-7,
+                           int(bool(cfg["auto_mask"])))
+        L = lib()
+        nbytes = C.c_size_t(0)
+        check(L.dvs_loss_workspace_bytes(C.byref(shape), C.byref(nbytes)), "dvs_loss_workspace_bytes")
+        ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+
+        want_grad = any(ctx.needs_input_grad[8:8 + S + N])
+        per_scale = torch.empty(S, dtype=torch.float32, device=dev)
+        total = torch.empty(1, dtype=torch.float32, device=dev)
+        sel = None
+        if cfg.get("return_selection"):
+            sel = [torch.empty(B, H, W, dtype=torch.uint8, device=dev) for _ in range(S)]
+        ugrad = uT = None
+        if want_grad:
+            ugrad = [torch.empty_like(d) for d in disps]
+            uT = torch.empty(S * N * B * 16 + S * B, dtype=torch.float32, device=dev)
+        noise_arr = None
+        if noise is not None:
+            noise = [_prep(n) for n in noise]
+            for n in noise:
+                if tuple(n.shape) != (B, N, H, W):
+                    raise _lib.DvsError(f"noise tensors must be [B,N,H,W], got {tuple(n.shape)}")
+            require_cuda(*noise)
+            noise_arr = fptr_array(noise)
+        with torch.cuda.device(dev):
+            rc = L.dvs_photometric_forward(
+                C.byref(shape), C.byref(params), fptr_array(disps), ptr(target), fptr_array(sources), ptr(K),
+                ptr(inv_K), fptr_array(Ts), noise_arr, C.c_uint64(cfg["seed"]), C.c_uint64(cfg["offset"]),
+                ptr(per_scale), ptr(total), u8ptr_array(sel) if sel is not None else None,
+                fptr_array(ugrad) if want_grad else None, ptr(uT), ws_ptr, stream_ptr(dev))
+        check(rc, "dvs_photometric_forward")
+        ctx.shape, ctx.S, ctx.N, ctx.B = shape, S, N, B
+        ctx.ugrad, ctx.uT = ugrad, uT
+        ctx.keep = (ws, noise, disps, Ts, sources, target, K, inv_K)   # keep inputs alive until the stream has used them
+        outs = (total.view(()), per_scale)
+        if sel is not None:
+            for s_ in sel:
+                ctx.mark_non_differentiable(s_)
+            outs = outs + tuple(sel)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_total, g_scale, *unused):
+        if ctx.ugrad is None:
+            raise _lib.DvsError("backward called but forward ran without gradient tracking")
+        S, N, B = ctx.S, ctx.N, ctx.B
+        dev = ctx.uT.device
+        g = torch.zeros(S, dtype=torch.float32, device=dev)
+        if g_scale is not None:
+            g = g + g_scale.float()
+        if g_total is not None:
+            g = g + g_total.float() / S
+        g = g.contiguous()
+        grad_disp = [torch.empty_like(u) for u in ctx.ugrad]
+        grad_T = [torch.empty(B, 4, 4, dtype=torch.float32, device=dev) for _ in range(N)]
+        with torch.cuda.device(dev):
+            rc = lib().dvs_photometric_backward(C.byref(ctx.shape), ptr(g), fptr_array(ctx.ugrad), ptr(ctx.uT),
+                                                fptr_array(grad_disp), fptr_array(grad_T), stream_ptr(dev))
+        check(rc, "dvs_photometric_backward")
+        return (None,) * 8 + tuple(grad_disp) + tuple(grad_T)
+
+
+def view_synthesis_loss(disps: Sequence[torch.Tensor], target: torch.Tensor, sources: Sequence[torch.Tensor],
+                        K: torch.Tensor, inv_K: torch.Tensor, Ts: Sequence[torch.Tensor], *,
+                        noise: NoiseArg = "kernel", min_depth: float = 0.1, max_depth: float = 10.0,
+                        ssim_ratio: float = 0.85, smoothness_ratio: float = 1e-3, auto_mask: bool = True,
+                        return_selection: bool = False, seed: Optional[int] = None
+                        ) -> Tuple[torch.Tensor, ...]:
+    """Fused Monodepth2 view-synthesis loss over S=len(disps) scales and N=len(sources) source frames.
+
+    disps[s] [B,1,h_s,w_s] sigmoid disparities (outputs[("disp", s)]), target/sources [B,3,H,W] in [0,1],
+    K/inv_K [B,4,4] scale-0 intrinsics, Ts[i] [B,4,4] cam_T_cam of source i.
+
+    noise: "kernel" -> automask tie-break noise from an in-kernel counter-based generator (fast);
+           "torch"  -> ``torch.randn([B,N,H,W])`` per scale, i.e. exactly the draws (shape, order, device)
+                       of vo/learner_new.py:228, so a seeded run consumes the RNG like the reference;
+           a list of S tensors [B,N,H,W] -> those draws;  None -> no noise.
+    Returns (loss, per_scale[S]) and, with return_selection, S uint8 maps [B,H,W] holding the argmin
+    channel over [identity_0..N-1, reproj_0..N-1] (``identity_selection/s`` of the reference is ``sel >= N``).
+    """
+    S, N = len(disps), len(sources)
+    if len(Ts) != N:
+        raise _lib.DvsError("need one pose per source frame")
+    B, _, H, W = target.shape
+    noise_t = None
+    if auto_mask:
+        if isinstance(noise, str):
+            if noise == "torch":
+                noise_t = [torch.randn([B, N, H, W], device=target.device) for _ in range(S)]
+            elif noise != "kernel":
+                raise _lib.DvsError(f"unknown noise mode {noise!r}")
+        elif noise is None:
+            noise_t = [torch.zeros(B, N, H, W, device=target.device)] * S
+        else:
+            noise_t = list(noise)
+            if len(noise_t) != S:
+                raise _lib.DvsError("need one noise tensor per scale")
+    cfg = dict(min_depth=float(min_depth), max_depth=float(max_depth), ssim_ratio=float(ssim_ratio),
+               smoothness_ratio=float(smoothness_ratio), auto_mask=bool(auto_mask),
+               return_selection=bool(return_selection),
+               seed=int(torch.initial_seed() if seed is None else seed) & (2 ** 64 - 1),
+               offset=next(_offset_counter))
+    return _ViewSynthesisLoss.apply(cfg, target, list(sources), K, inv_K, noise_t, S, N, *disps, *Ts)

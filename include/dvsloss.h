@@ -1,0 +1,192 @@
+/*
+ * dvsloss.h -- C ABI of libdvsloss.so: the B200 (sm_100a) implementation of the
+ * Monodepth2-style view-synthesis loss that dominates Deep-Visual-SLAM's VO training step.
+ *
+ * The reference has NO native boundary on this path: it is eager PyTorch
+ * (vo/learner_new.py:60-74,132-258 composing vo/learner_func.py:16-207 == model/layers.py:16-248).
+ * The functions below are what a ctypes / pybind shim inside the reference's Python modules binds
+ * instead of those ATen op sequences (INTEGRATION.md shows the stub).  Each entry point names the
+ * reference code it replaces.
+ *
+ * Conventions
+ *   - plain C: no torch types, no exceptions, no exit(); return 0 (DVS_OK) or a negative DVS_E* code.
+ *   - every pointer is a DEVICE pointer to contiguous memory (fp32 unless stated), owned by the caller,
+ *     never retained after the call returns; arrays of pointers (disp[], src[], ...) are HOST arrays.
+ *   - every call is asynchronous on the given cudaStream_t (passed as void*; NULL = legacy default stream).
+ *   - no hidden allocation: scratch memory is a caller-provided workspace sized by
+ *     dvs_loss_workspace_bytes(); distinct (stream, workspace) pairs may run concurrently.
+ *   - tensor layouts are the reference's: images [B,3,H,W], disparity [B,1,h_s,w_s], matrices [B,4,4]
+ *     row-major, sampling grids [B,H,W,2], point clouds [B,4,H*W].
+ */
+#ifndef DVSLOSS_H_
+#define DVSLOSS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVS_MAX_SCALES 4
+#define DVS_MAX_SOURCES 4
+
+enum {
+  DVS_OK = 0,
+  DVS_EINVAL = -1,   /* bad shape / null pointer / unsupported N or S                */
+  DVS_ECUDA = -2,    /* a CUDA runtime call failed (see dvs_last_cuda_error())        */
+  DVS_EWORKSPACE = -3 /* workspace pointer null or misaligned                         */
+};
+
+/* Problem shape.  dh/dw: size of the disparity map of each scale (the reference: H>>s, W>>s,
+ * model/depthnet.py:87-88); they are bilinearly up-sampled to HxW (vo/learner_new.py:136-140). */
+typedef struct DvsShape {
+  int32_t B, H, W;
+  int32_t N;                     /* source frames, 1..DVS_MAX_SOURCES (reference: 2)  */
+  int32_t S;                     /* scales, 1..DVS_MAX_SCALES (reference: 4)          */
+  int32_t dh[DVS_MAX_SCALES];
+  int32_t dw[DVS_MAX_SCALES];
+} DvsShape;
+
+/* Hyper-parameters = config['Train'] keys read at vo/learner_new.py:31-41. */
+typedef struct DvsParams {
+  float min_depth;               /* 0.1   */
+  float max_depth;               /* 10.0  */
+  float ssim_ratio;              /* 0.85  */
+  float smoothness_ratio;        /* 1e-3  */
+  float eps;                     /* Project3D eps, 1e-7 (vo/learner_func.py:140)      */
+  int32_t auto_mask;             /* 1     */
+} DvsParams;
+
+int dvs_version(void);
+const char* dvs_error_string(int code);
+/* cudaError_t of the last failing CUDA call on this host thread (0 if none). */
+int dvs_last_cuda_error(void);
+
+/* Measurement hook (bench.py): when enabled, dvs_photometric_forward brackets its dominant kernel (the fused
+ * tile kernel) with CUDA events on the caller's stream; dvs_last_tile_kernel_ms waits for the most recent
+ * one and returns its device duration.  Process-wide, not thread-safe; off by default. */
+int dvs_set_profiling(int enabled);
+int dvs_last_tile_kernel_ms(float* ms);
+
+/* Bytes of scratch the fused loss needs for this shape (>=256-byte aligned pointer expected). */
+int dvs_loss_workspace_bytes(const DvsShape* shape, size_t* bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused view-synthesis loss.  Replaces MonodepthTrainer._generate_images_pred
+ * (vo/learner_new.py:132-172) + _compute_losses (:175-258) for all S scales and N sources:
+ * disparity up-sampling, disp_to_depth, BackprojectDepth, Project3D, border grid_sample,
+ * SSIM+L1, identity automask, min over sources, edge-aware smoothness, per-scale reduction.
+ *
+ *   disp[s]      [B,1,dh[s],dw[s]]        target, src[i]  [B,3,H,W]
+ *   K, inv_K     [B,4,4] (scale-0 intrinsics, vo/learner_new.py:155-156)      T[i] [B,4,4] cam_T_cam
+ *   noise[s]     [B,N,H,W] standard-normal draws of vo/learner_new.py:228 (scaled by 1e-5 inside);
+ *                noise == NULL -> an in-kernel counter-based generator keyed by (seed, offset, s, pixel)
+ *                is used instead (same distribution, not the same stream); ignored if !auto_mask.
+ *   loss_per_scale [S]  = losses["loss/s"]          loss_total [1] = losses["loss"]
+ *   sel[s]       optional uint8 [B,H,W]: argmin channel over [identity_0..N-1, reproj_0..N-1]
+ *                (identity_selection/s of the reference == sel >= N);  sel or sel[s] may be NULL.
+ *   ugrad_disp[s], ugrad_T  optional.  When non-NULL the same pass also produces the gradient of
+ *                each loss/s w.r.t. disp[s] (ugrad_disp[s], same shape as disp[s]) and w.r.t. T
+ *                (ugrad_T, [S,N,B,4,4]), so that backward is a scaling (dvs_photometric_backward).
+ *                Both or neither must be given.
+ * ------------------------------------------------------------------------------------------ */
+int dvs_photometric_forward(const DvsShape* shape, const DvsParams* params,
+                            const float* const* disp, const float* target, const float* const* src,
+                            const float* K, const float* inv_K, const float* const* T,
+                            const float* const* noise, uint64_t seed, uint64_t offset,
+                            float* loss_per_scale, float* loss_total,
+                            uint8_t* const* sel,
+                            float* const* ugrad_disp, float* ugrad_T,
+                            void* workspace, void* stream);
+
+/* Backward of the above given what forward stored: for upstream gradients
+ * grad_per_scale[s] = d objective / d loss/s (device, [S]; add grad_total/S to each if the total is used)
+ *   grad_disp[s] = grad_per_scale[s] * ugrad_disp[s]            (in place allowed: grad_disp[s]==ugrad_disp[s])
+ *   grad_T[i]    = sum_s grad_per_scale[s] * ugrad_T[s,i]       ([B,4,4] each)
+ * Equals what autograd produces through vo/learner_new.py:132-258 for d/d outputs[("disp",s)]
+ * and d/d outputs[("cam_T_cam",0,f)]. */
+int dvs_photometric_backward(const DvsShape* shape, const float* grad_per_scale,
+                             const float* const* ugrad_disp, const float* ugrad_T,
+                             float* const* grad_disp, float* const* grad_T, void* stream);
+
+/* Stand-alone backward that recomputes the forward from the inputs (nothing saved between passes
+ * except nothing at all): same inputs as forward plus grad_per_scale; writes grad_disp[s], grad_T[i]. */
+int dvs_photometric_backward_recompute(const DvsShape* shape, const DvsParams* params,
+                                       const float* const* disp, const float* target, const float* const* src,
+                                       const float* K, const float* inv_K, const float* const* T,
+                                       const float* const* noise, uint64_t seed, uint64_t offset,
+                                       const float* grad_per_scale,
+                                       float* const* grad_disp, float* const* grad_T,
+                                       void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Granular operators: the reference's public primitives, one kernel each, forward and backward.
+ * ------------------------------------------------------------------------------------------ */
+
+/* disp_to_depth (vo/learner_func.py:16-26): scaled = 1/max + (1/min-1/max)*disp, depth = 1/scaled. n elements. */
+int dvs_disp_to_depth_fwd(const float* disp, float* scaled_disp, float* depth, int64_t n,
+                          float min_depth, float max_depth, void* stream);
+/* grad_disp = (grad_scaled - grad_depth*depth^2) * (1/min-1/max); either upstream may be NULL. */
+int dvs_disp_to_depth_bwd(const float* depth, const float* grad_scaled, const float* grad_depth,
+                          float* grad_disp, int64_t n, float min_depth, float max_depth, void* stream);
+
+/* F.interpolate(disp, [H,W], mode="bilinear", align_corners=False) (vo/learner_new.py:136-140); C channels. */
+int dvs_upsample_bilinear_fwd(const float* in, float* out, int B, int C, int h, int w, int H, int W, void* stream);
+int dvs_upsample_bilinear_bwd(const float* grad_out, float* grad_in, int B, int C, int h, int w, int H, int W,
+                              void* stream);
+
+/* BackprojectDepth.forward (vo/learner_func.py:130-135): depth [B,1,H,W], inv_K [B,4,4] -> cam_points [B,4,H*W]. */
+int dvs_backproject_fwd(const float* depth, const float* inv_K, float* cam_points, int B, int H, int W, void* stream);
+/* grad_depth [B,1,H,W] from grad_cam [B,4,H*W] (inv_K receives no gradient in the reference's use). */
+int dvs_backproject_bwd(const float* grad_cam, const float* inv_K, float* grad_depth, int B, int H, int W,
+                        void* stream);
+
+/* Project3D.forward (vo/learner_func.py:148-159): points [B,4,HW], K,T [B,4,4] -> normalised grid [B,H,W,2]. */
+int dvs_project3d_fwd(const float* points, const float* K, const float* T, float* pix, int B, int H, int W,
+                      float eps, void* stream);
+/* grad_points [B,4,HW] and grad_T [B,4,4] (either may be NULL) from grad_pix [B,H,W,2];
+ * workspace: dvs_project3d_bwd_workspace_bytes(). */
+int dvs_project3d_bwd_workspace_bytes(int B, int H, int W, size_t* bytes);
+int dvs_project3d_bwd(const float* grad_pix, const float* points, const float* K, const float* T,
+                      float* grad_points, float* grad_T, int B, int H, int W, float eps,
+                      void* workspace, void* stream);
+
+/* F.grid_sample(src, grid, padding_mode="border", align_corners=True), bilinear (vo/learner_new.py:165-170).
+ * src [B,C,H,W], grid [B,Ho,Wo,2] -> out [B,C,Ho,Wo]; backward w.r.t. the grid only (images are data). */
+int dvs_grid_sample_border_fwd(const float* src, const float* grid, float* out, int B, int C, int H, int W,
+                               int Ho, int Wo, void* stream);
+int dvs_grid_sample_border_bwd(const float* grad_out, const float* src, const float* grid, float* grad_grid,
+                               int B, int C, int H, int W, int Ho, int Wo, void* stream);
+
+/* SSIM.forward (vo/learner_func.py:190-207): x,y [B,C,H,W] -> clamp((1-SSIM)/2,0,1) [B,C,H,W]. */
+int dvs_ssim_fwd(const float* x, const float* y, float* out, int B, int C, int H, int W, void* stream);
+/* grad_x and/or grad_y (either may be NULL) from grad_out. */
+int dvs_ssim_bwd(const float* grad_out, const float* x, const float* y, float* grad_x, float* grad_y,
+                 int B, int C, int H, int W, void* stream);
+
+/* compute_reprojection_loss (vo/learner_new.py:60-74): pred,target [B,C,H,W] -> [B,1,H,W]. */
+int dvs_reprojection_loss_fwd(const float* pred, const float* target, float* out, int B, int C, int H, int W,
+                              float ssim_ratio, void* stream);
+int dvs_reprojection_loss_bwd(const float* grad_out, const float* pred, const float* target, float* grad_pred,
+                              int B, int C, int H, int W, float ssim_ratio, void* stream);
+
+/* get_smooth_loss (vo/learner_func.py:161-174): disp [B,1,H,W], img [B,C,H,W] -> scalar out[1].
+ * workspace: dvs_smooth_loss_workspace_bytes(). */
+int dvs_smooth_loss_workspace_bytes(int B, int H, int W, size_t* bytes);
+int dvs_smooth_loss_fwd(const float* disp, const float* img, float* out, int B, int C, int H, int W,
+                        void* workspace, void* stream);
+/* grad_disp [B,1,H,W] = grad_out[0] * d loss / d disp (grad_out is a device scalar). */
+int dvs_smooth_loss_bwd(const float* grad_out, const float* disp, const float* img, float* grad_disp,
+                        int B, int C, int H, int W, void* stream);
+
+/* transformation_from_parameters (vo/learner_func.py:29-104): axisangle, translation [B,3] -> M [B,4,4]. */
+int dvs_pose_matrix_fwd(const float* axisangle, const float* translation, float* M, int B, int invert,
+                        void* stream);
+int dvs_pose_matrix_bwd(const float* grad_M, const float* axisangle, const float* translation,
+                        float* grad_axisangle, float* grad_translation, int B, int invert, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVSLOSS_H_ */

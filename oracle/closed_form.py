@@ -133,7 +133,8 @@ def loss_and_grads(disps: Sequence[np.ndarray], target: np.ndarray, sources: Seq
                    K: np.ndarray, inv_K: np.ndarray, Ts: Sequence[np.ndarray],
                    noise: Optional[Sequence[np.ndarray]] = None, *, min_depth=0.1, max_depth=10.0,
                    ssim_ratio=0.85, smoothness_ratio=1e-3, auto_mask=True, eps=1e-7,
-                   grad_per_scale: Optional[Sequence[float]] = None) -> Dict[str, object]:
+                   grad_per_scale: Optional[Sequence[float]] = None,
+                   sel_override: Optional[Sequence[np.ndarray]] = None) -> Dict[str, object]:
     """disps[s]: [B,1,h_s,w_s]; target/sources: [B,3,H,W]; K,inv_K,Ts[i]: [B,4,4]; noise[s]: [B,N,H,W].
 
     Returns per_scale (S,), loss, sel [S x [B,H,W]], grad_disp [S x like disps], grad_T [N x [B,4,4]].
@@ -210,8 +211,12 @@ def loss_and_grads(disps: Sequence[np.ndarray], target: np.ndarray, sources: Seq
             comb = np.concatenate([idn, reproj], 1)
         else:
             comb = reproj
-        sel = np.argmin(comb, 1)
-        m = np.min(comb, 1)
+        if sel_override is not None:          # test-only: pin the selection (see reference_port.view_synthesis_loss)
+            sel = sel_override[s].astype(np.int64)
+            m = np.take_along_axis(comb, sel[:, None], 1)[:, 0]
+        else:
+            sel = np.argmin(comb, 1)
+            m = np.min(comb, 1)
         sels.append(sel)
         photo = m.mean()
 

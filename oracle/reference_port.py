@@ -165,19 +165,26 @@ def view_synthesis_loss(disps: Sequence[torch.Tensor], target: torch.Tensor,
                         Ts: Sequence[torch.Tensor], noise: Optional[Sequence[torch.Tensor]] = None,
                         *, min_depth: float = 0.1, max_depth: float = 10.0, ssim_ratio: float = 0.85,
                         smoothness_ratio: float = 1e-3, auto_mask: bool = True,
-                        keep: bool = False) -> Dict[str, object]:
+                        keep: bool = False,
+                        sel_override: Optional[Sequence[torch.Tensor]] = None) -> Dict[str, object]:
     """The whole hot path: learner_new.py:132-172 (_generate_images_pred) followed by
     :175-258 (_compute_losses), for S=len(disps) scales and N=len(sources) sources.
 
     ``noise[s]`` is the [B,N,H,W] standard-normal tensor the reference draws with
     ``torch.randn`` at learner_new.py:228 (multiplied by 1e-5 here); ``None`` means zeros.
     Returns ``loss`` (scalar), ``per_scale`` (list of S scalars), ``sel`` (list of
-    [B,1,H,W] int64 argmin maps) and, with ``keep=True``, the per-scale intermediates.
+    [B,1,H,W] int64 argmin maps), ``combined`` (the candidate stacks) and, with ``keep=True``,
+    the per-scale intermediates.
+
+    ``sel_override[s]`` ([B,1,H,W] int64) replaces the argmin (test-only): near-ties between
+    candidates flip under fp32 round-off, so gradient parity is checked with the selection
+    pinned to the one the implementation under test made.
     """
     B, _, H, W = target.shape
     S, N = len(disps), len(sources)
     per_scale: List[torch.Tensor] = []
     sels: List[torch.Tensor] = []
+    combs: List[torch.Tensor] = []
     extras: Dict[object, torch.Tensor] = {}
     total = 0
     for s in range(S):
@@ -200,11 +207,15 @@ def view_synthesis_loss(disps: Sequence[torch.Tensor], target: torch.Tensor,
             combined = torch.cat((ident, reproj), dim=1)
         else:
             combined = reproj
-        if combined.shape[1] == 1:
+        if sel_override is not None:
+            idx = sel_override[s]
+            to_opt = combined.gather(1, idx)
+        elif combined.shape[1] == 1:
             to_opt = combined
             idx = torch.zeros_like(combined, dtype=torch.int64)
         else:
             to_opt, idx = torch.min(combined, dim=1, keepdim=True)
+        combs.append(combined.detach())
         sels.append(idx)
         loss = to_opt.mean()
         mean_disp = disp_up.mean(2, True).mean(3, True)
@@ -213,7 +224,7 @@ def view_synthesis_loss(disps: Sequence[torch.Tensor], target: torch.Tensor,
         loss = loss + smoothness_ratio * smooth_loss(norm_disp, target) / (2 ** s)
         total = total + loss
         per_scale.append(loss)
-    out: Dict[str, object] = {"loss": total / S, "per_scale": per_scale, "sel": sels}
+    out: Dict[str, object] = {"loss": total / S, "per_scale": per_scale, "sel": sels, "combined": combs}
     if keep:
         out["extras"] = extras
     return out

@@ -1,0 +1,172 @@
+// CPU block emulator of the fused tile kernel -- TEST INFRASTRUCTURE ONLY (never shipped, never timed).
+//
+// Compiles deep-visual-slam_b200/csrc/dvs_fused_core.cuh with g++ and runs every CTA of
+// fused_tile_kernel sequentially: each phase function is executed for tid = 0..NT-1 before the next
+// phase starts, which is exactly the ordering the __syncthreads() barriers of dvs_fused.cu guarantee.
+// The small kernels around it (disparity mean, finish, final, backward scaling) are restated as loops.
+// tests/test_emulator.py drives this through ctypes with numpy arrays and compares with the oracle, so
+// tile / halo / reflection / adjoint logic is debugged here, where there is no GPU.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../deep-visual-slam_b200/csrc/dvs_fused_core.cuh"
+#include "../../include/dvsloss.h"
+
+using namespace dvs;
+
+namespace {
+
+template <int NS, bool GRAD>
+void run_block(const FusedParams& p, int blk, std::vector<float>& smv) {
+  float* sm = smv.data();
+  Tile t = make_tile(p, blk);
+  std::vector<ThreadState<NS>> st(NT);
+  for (int tid = 0; tid < NT; ++tid) { phase_consts<NS>(p, t, sm, tid); phase_load<NS>(p, t, sm, tid); }
+  for (int tid = 0; tid < NT; ++tid) phase_identity<NS>(p, t, sm, tid, st[tid]);
+  for (int s = 0; s < p.S; ++s) {
+    for (int tid = 0; tid < NT; ++tid) { reset_scale_state<NS>(st[tid]); phase_warp<NS>(p, t, sm, tid, s); }
+    for (int tid = 0; tid < NT; ++tid) phase_stats<NS, GRAD>(p, t, sm, tid, s, st[tid]);
+    const bool direct = (p.dh[s] == p.H && p.dw[s] == p.W);
+    if (GRAD) {
+      for (int tid = 0; tid < NT; ++tid) phase_grad<NS>(p, t, sm, tid, s, st[tid]);
+      for (int tid = 0; tid < NT; ++tid) {
+        if (direct) store_gdu_direct<NS>(p, t, tid, s, st[tid]);
+        else stage_gdu<NS>(p, t, sm, tid, st[tid]);
+      }
+    }
+    for (int tid = 0; tid < NT; ++tid) reduce_write<NS>(p, sm, tid, st[tid]);
+    for (int tid = 0; tid < NT; ++tid) {
+      if (GRAD && !direct) adjoint_rows<NS>(p, t, sm, tid, s);
+      reduce_stage1<NS>(p, sm, tid);
+    }
+    for (int tid = 0; tid < NT; ++tid) {
+      if (GRAD && !direct) adjoint_cols<NS>(p, t, sm, tid, s);
+      reduce_stage2<NS>(p, t, sm, tid, s);
+    }
+  }
+}
+
+template <int NS>
+void run_all(const FusedParams& p, int nblk) {
+  SmemLayout L{NS};
+  std::vector<float> sm(L.total());
+  for (int blk = 0; blk < nblk; ++blk) {
+    // poison shared memory so that reads of never-written words show up as NaN in the results
+    for (auto& v : sm) v = __builtin_nanf("");
+    if (p.want_grad) run_block<NS, true>(p, blk, sm);
+    else run_block<NS, false>(p, blk, sm);
+  }
+}
+
+}  // namespace
+
+extern "C" int emu_photometric_forward(const DvsShape* sh, const DvsParams* pr, const float* const* disp,
+                                       const float* target, const float* const* src, const float* K,
+                                       const float* inv_K, const float* const* T, const float* const* noise,
+                                       uint64_t seed, uint64_t offset, float* loss_per_scale, float* loss_total,
+                                       uint8_t* const* sel, float* const* ugrad_disp, float* ugrad_T) {
+  const bool want_grad = ugrad_disp != nullptr;
+  const int tiles_x = (sh->W + PITCH_X - 1) / PITCH_X, tiles_y = (sh->H + PITCH_Y - 1) / PITCH_Y;
+  const int nblk = sh->B * tiles_x * tiles_y, nv = nvals(sh->N);
+  std::vector<float> mean_part((size_t)sh->S * sh->B * kMeanBlocks, 0.f), part((size_t)nblk * sh->S * nv, 0.f);
+
+  FusedParams p{};
+  p.B = sh->B; p.H = sh->H; p.W = sh->W; p.N = sh->N; p.S = sh->S;
+  for (int s = 0; s < sh->S; ++s) {
+    p.dh[s] = sh->dh[s]; p.dw[s] = sh->dw[s]; p.disp[s] = disp[s];
+    p.noise[s] = (noise && pr->auto_mask) ? noise[s] : nullptr;
+    p.sel[s] = sel ? sel[s] : nullptr;
+    p.gdisp[s] = want_grad ? ugrad_disp[s] : nullptr;
+  }
+  for (int i = 0; i < sh->N; ++i) { p.src[i] = src[i]; p.T[i] = T[i]; }
+  p.target = target; p.K = K; p.invK = inv_K; p.seed = seed; p.offset = offset;
+  p.min_disp = 1.0f / pr->max_depth;
+  p.disp_range = 1.0f / pr->min_depth - 1.0f / pr->max_depth;
+  p.ssim_w = pr->ssim_ratio; p.l1_w = 1.0f - pr->ssim_ratio;
+  p.smooth_w = pr->smoothness_ratio; p.eps = pr->eps;
+  p.auto_mask = pr->auto_mask ? 1 : 0; p.want_grad = want_grad;
+  p.mean_part = mean_part.data(); p.part = part.data();
+  p.tiles_x = tiles_x; p.tiles_y = tiles_y;
+
+  // mean_partial_kernel
+  for (int s = 0; s < sh->S; ++s)
+    for (int b = 0; b < sh->B; ++b) {
+      int h = p.dh[s], w = p.dw[s], n = h * w, per = (n + kMeanBlocks - 1) / kMeanBlocks;
+      for (int c = 0; c < kMeanBlocks; ++c) {
+        float acc = 0.f;
+        for (int e = c * per; e < imin((c + 1) * per, n); ++e)
+          acc += up_weight(e / w, h, p.H) * up_weight(e % w, w, p.W) * disp[s][(size_t)b * n + e];
+        mean_part[(s * sh->B + b) * kMeanBlocks + c] = acc;
+      }
+    }
+  if (want_grad)
+    for (int s = 0; s < sh->S; ++s)
+      if (!(p.dh[s] == p.H && p.dw[s] == p.W))
+        memset(ugrad_disp[s], 0, sizeof(float) * (size_t)sh->B * p.dh[s] * p.dw[s]);
+
+  switch (sh->N) {
+    case 1: run_all<1>(p, nblk); break;
+    case 2: run_all<2>(p, nblk); break;
+    case 3: run_all<3>(p, nblk); break;
+    case 4: run_all<4>(p, nblk); break;
+    default: return DVS_EINVAL;
+  }
+
+  // finish_kernel + final_kernel
+  const int tpi = tiles_x * tiles_y;
+  float* coup = want_grad ? ugrad_T + (size_t)sh->S * sh->N * sh->B * 16 : nullptr;
+  const float Nx = (float)sh->B * sh->H * (sh->W - 1), Ny = (float)sh->B * (sh->H - 1) * sh->W;
+  float total = 0.f;
+  for (int s = 0; s < sh->S; ++s) {
+    float ph = 0.f, sx = 0.f, sy = 0.f;
+    const float kap = p.smooth_w / (float)(1 << s);
+    for (int b = 0; b < sh->B; ++b) {
+      std::vector<float> res(nv, 0.f);
+      for (int tl = 0; tl < tpi; ++tl)
+        for (int v = 0; v < nv; ++v) res[v] += part[((size_t)(b * tpi + tl) * sh->S + s) * nv + v];
+      ph += res[0]; sx += res[1]; sy += res[2];
+      if (!want_grad) continue;
+      for (int i = 0; i < sh->N; ++i)
+        for (int m = 0; m < 4; ++m)
+          for (int k = 0; k < 4; ++k) {
+            float a = 0.f;
+            for (int j = 0; j < 3; ++j) a += K[b * 16 + j * 4 + m] * res[3 + 12 * i + j * 4 + k];
+            ugrad_T[(((size_t)s * sh->N + i) * sh->B + b) * 16 + m * 4 + k] = a;
+          }
+      float mu = 0.f;
+      for (int k = 0; k < kMeanBlocks; ++k) mu += mean_part[(s * sh->B + b) * kMeanBlocks + k];
+      mu /= (float)sh->H * (float)sh->W;
+      float inv = 1.0f / (fmaxf(mu, 0.001f) + 1e-7f), live = mu >= 0.001f ? 1.f : 0.f;
+      coup[s * sh->B + b] = kap * (res[1] / Nx + res[2] / Ny) * inv * live / ((float)sh->H * (float)sh->W);
+    }
+    float l = ph / ((float)sh->B * sh->H * sh->W) + kap * (sx / Nx + sy / Ny);
+    loss_per_scale[s] = l;
+    total += l;
+  }
+  loss_total[0] = total / (float)sh->S;
+  return DVS_OK;
+}
+
+extern "C" int emu_photometric_backward(const DvsShape* sh, const float* g, const float* const* u, const float* uT,
+                                        float* const* grad_disp, float* const* grad_T) {
+  const float* coup = uT + (size_t)sh->S * sh->N * sh->B * 16;
+  for (int s = 0; s < sh->S; ++s) {
+    int h = sh->dh[s], w = sh->dw[s];
+    for (int b = 0; b < sh->B; ++b)
+      for (int i = 0; i < h; ++i)
+        for (int j = 0; j < w; ++j) {
+          size_t e = ((size_t)b * h + i) * w + j;
+          grad_disp[s][e] = g[s] * (u[s][e] - coup[s * sh->B + b] * up_weight(i, h, sh->H) * up_weight(j, w, sh->W));
+        }
+  }
+  for (int i = 0; i < sh->N; ++i)
+    for (int r = 0; r < sh->B * 16; ++r) {
+      float a = 0.f;
+      for (int s = 0; s < sh->S; ++s) a += g[s] * uT[((size_t)s * sh->N + i) * sh->B * 16 + r];
+      grad_T[i][r] = a;
+    }
+  return DVS_OK;
+}
