@@ -1,0 +1,335 @@
+"""Granular operators with the reference's call surface, as autograd functions over libdvsloss.so.
+
+One sm_100a kernel per direction (csrc/dvs_ops.cu).  These are what ``model/layers.py`` /
+``vo/learner_func.py`` of this repo expose as ``disp_to_depth``, ``BackprojectDepth``, ``Project3D``, ``SSIM``,
+``get_smooth_loss``, ``compute_reprojection_loss`` and ``transformation_from_parameters``
+(reference: vo/learner_func.py:16-207 == model/layers.py:16-248, vo/learner_new.py:60-74).
+CUDA fp32 only; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Tuple
+
+import torch
+
+from ._lib import DvsError, check, lib, ptr, require_cuda, stream_ptr
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ws(nbytes: int, dev) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 4), dtype=torch.uint8, device=dev)
+
+
+# --------------------------------------------------------------------------------------------- disp_to_depth
+class _DispToDepth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, min_depth, max_depth):
+        disp = _f32(disp)
+        require_cuda(disp)
+        scaled, depth = torch.empty_like(disp), torch.empty_like(disp)
+        with torch.cuda.device(disp.device):
+            check(lib().dvs_disp_to_depth_fwd(ptr(disp), ptr(scaled), ptr(depth), disp.numel(), min_depth, max_depth,
+                                              stream_ptr(disp.device)), "dvs_disp_to_depth_fwd")
+        ctx.save_for_backward(depth)
+        ctx.lim = (min_depth, max_depth)
+        return scaled, depth
+
+    @staticmethod
+    def backward(ctx, g_scaled, g_depth):
+        (depth,) = ctx.saved_tensors
+        gs = _f32(g_scaled) if g_scaled is not None else None
+        gd = _f32(g_depth) if g_depth is not None else None
+        out = torch.empty_like(depth)
+        with torch.cuda.device(depth.device):
+            check(lib().dvs_disp_to_depth_bwd(ptr(depth), ptr(gs), ptr(gd), ptr(out), depth.numel(), ctx.lim[0], ctx.lim[1],
+                                              stream_ptr(depth.device)), "dvs_disp_to_depth_bwd")
+        return out, None, None
+
+
+def disp_to_depth(disp: torch.Tensor, min_depth: float, max_depth: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """vo/learner_func.py:16-26: sigmoid disparity -> (scaled disparity, depth)."""
+    return _DispToDepth.apply(disp, float(min_depth), float(max_depth))
+
+
+# --------------------------------------------------------------------------------------------- up-sampling
+class _Upsample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W):
+        x = _f32(x)
+        require_cuda(x)
+        B, Cc, h, w = x.shape
+        out = torch.empty(B, Cc, H, W, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib().dvs_upsample_bilinear_fwd(ptr(x), ptr(out), B, Cc, h, w, H, W, stream_ptr(x.device)),
+                  "dvs_upsample_bilinear_fwd")
+        ctx.dims = (B, Cc, h, w, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Cc, h, w, H, W = ctx.dims
+        g = _f32(g)
+        gi = torch.empty(B, Cc, h, w, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(lib().dvs_upsample_bilinear_bwd(ptr(g), ptr(gi), B, Cc, h, w, H, W, stream_ptr(g.device)),
+                  "dvs_upsample_bilinear_bwd")
+        return gi, None, None
+
+
+def upsample_bilinear(x: torch.Tensor, size) -> torch.Tensor:
+    """F.interpolate(x, size, mode="bilinear", align_corners=False) (vo/learner_new.py:136-140)."""
+    return _Upsample.apply(x, int(size[0]), int(size[1]))
+
+
+# --------------------------------------------------------------------------------------------- BackprojectDepth
+class _Backproject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, inv_K):
+        depth, inv_K = _f32(depth), _f32(inv_K)
+        require_cuda(depth, inv_K)
+        B, _, H, W = depth.shape
+        out = torch.empty(B, 4, H * W, dtype=torch.float32, device=depth.device)
+        with torch.cuda.device(depth.device):
+            check(lib().dvs_backproject_fwd(ptr(depth), ptr(inv_K), ptr(out), B, H, W, stream_ptr(depth.device)),
+                  "dvs_backproject_fwd")
+        ctx.save_for_backward(inv_K)
+        ctx.dims = (B, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (inv_K,) = ctx.saved_tensors
+        B, H, W = ctx.dims
+        g = _f32(g)
+        gd = torch.empty(B, 1, H, W, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(lib().dvs_backproject_bwd(ptr(g), ptr(inv_K), ptr(gd), B, H, W, stream_ptr(g.device)),
+                  "dvs_backproject_bwd")
+        return gd, None
+
+
+def backproject(depth: torch.Tensor, inv_K: torch.Tensor) -> torch.Tensor:
+    return _Backproject.apply(depth, inv_K)
+
+
+# --------------------------------------------------------------------------------------------- Project3D
+class _Project3D(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, K, T, H, W, eps):
+        points, K, T = _f32(points), _f32(K), _f32(T)
+        require_cuda(points, K, T)
+        B = points.shape[0]
+        if tuple(points.shape) != (B, 4, H * W):
+            raise DvsError(f"points must be [B,4,{H * W}], got {tuple(points.shape)}")
+        pix = torch.empty(B, H, W, 2, dtype=torch.float32, device=points.device)
+        with torch.cuda.device(points.device):
+            check(lib().dvs_project3d_fwd(ptr(points), ptr(K), ptr(T), ptr(pix), B, H, W, eps, stream_ptr(points.device)),
+                  "dvs_project3d_fwd")
+        ctx.save_for_backward(points, K, T)
+        ctx.dims = (B, H, W, eps)
+        return pix
+
+    @staticmethod
+    def backward(ctx, g):
+        points, K, T = ctx.saved_tensors
+        B, H, W, eps = ctx.dims
+        g = _f32(g)
+        dev = g.device
+        gp = torch.empty_like(points) if ctx.needs_input_grad[0] else None
+        gT = torch.empty(B, 4, 4, dtype=torch.float32, device=dev) if ctx.needs_input_grad[2] else None
+        if gp is None and gT is None:
+            return None, None, None, None, None, None
+        n = C.c_size_t(0)
+        check(lib().dvs_project3d_bwd_workspace_bytes(B, H, W, C.byref(n)), "dvs_project3d_bwd_workspace_bytes")
+        ws = _ws(n.value, dev)
+        with torch.cuda.device(dev):
+            check(lib().dvs_project3d_bwd(ptr(g), ptr(points), ptr(K), ptr(T), ptr(gp), ptr(gT), B, H, W, eps, ptr(ws),
+                                          stream_ptr(dev)), "dvs_project3d_bwd")
+        return gp, None, gT, None, None, None
+
+
+def project3d(points, K, T, H: int, W: int, eps: float = 1e-7) -> torch.Tensor:
+    return _Project3D.apply(points, K, T, int(H), int(W), float(eps))
+
+
+# --------------------------------------------------------------------------------------------- grid_sample
+class _GridSampleBorder(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, grid):
+        src, grid = _f32(src), _f32(grid)
+        require_cuda(src, grid)
+        B, Cc, H, W = src.shape
+        _, Ho, Wo, two = grid.shape
+        if two != 2 or grid.shape[0] != B:
+            raise DvsError("grid must be [B,Ho,Wo,2]")
+        out = torch.empty(B, Cc, Ho, Wo, dtype=torch.float32, device=src.device)
+        with torch.cuda.device(src.device):
+            check(lib().dvs_grid_sample_border_fwd(ptr(src), ptr(grid), ptr(out), B, Cc, H, W, Ho, Wo,
+                                                   stream_ptr(src.device)), "dvs_grid_sample_border_fwd")
+        ctx.save_for_backward(src, grid)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        src, grid = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise DvsError("grid_sample_border: gradient w.r.t. the image is not provided (images are data on this path)")
+        g = _f32(g)
+        B, Cc, H, W = src.shape
+        _, Ho, Wo, _ = grid.shape
+        gg = torch.empty_like(grid)
+        with torch.cuda.device(g.device):
+            check(lib().dvs_grid_sample_border_bwd(ptr(g), ptr(src), ptr(grid), ptr(gg), B, Cc, H, W, Ho, Wo,
+                                                   stream_ptr(g.device)), "dvs_grid_sample_border_bwd")
+        return None, gg
+
+
+def grid_sample_border(src: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
+    """F.grid_sample(src, grid, padding_mode="border", align_corners=True), bilinear (vo/learner_new.py:165-170)."""
+    return _GridSampleBorder.apply(src, grid)
+
+
+# --------------------------------------------------------------------------------------------- SSIM
+class _SSIM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = _f32(x), _f32(y)
+        require_cuda(x, y)
+        if x.shape != y.shape or x.dim() != 4:
+            raise DvsError("SSIM expects two [B,C,H,W] tensors of the same shape")
+        B, Cc, H, W = x.shape
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(lib().dvs_ssim_fwd(ptr(x), ptr(y), ptr(out), B, Cc, H, W, stream_ptr(x.device)), "dvs_ssim_fwd")
+        ctx.save_for_backward(x, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        g = _f32(g)
+        B, Cc, H, W = x.shape
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        if gx is None and gy is None:
+            return None, None
+        with torch.cuda.device(g.device):
+            check(lib().dvs_ssim_bwd(ptr(g), ptr(x), ptr(y), ptr(gx), ptr(gy), B, Cc, H, W, stream_ptr(g.device)),
+                  "dvs_ssim_bwd")
+        return gx, gy
+
+
+def ssim(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    return _SSIM.apply(x, y)
+
+
+# --------------------------------------------------------------------------------------------- reprojection loss
+class _Reproj(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, ssim_ratio):
+        pred, target = _f32(pred), _f32(target)
+        require_cuda(pred, target)
+        if pred.shape != target.shape or pred.dim() != 4:
+            raise DvsError("compute_reprojection_loss expects two [B,C,H,W] tensors of the same shape")
+        B, Cc, H, W = pred.shape
+        out = torch.empty(B, 1, H, W, dtype=torch.float32, device=pred.device)
+        with torch.cuda.device(pred.device):
+            check(lib().dvs_reprojection_loss_fwd(ptr(pred), ptr(target), ptr(out), B, Cc, H, W, ssim_ratio,
+                                                  stream_ptr(pred.device)), "dvs_reprojection_loss_fwd")
+        ctx.save_for_backward(pred, target)
+        ctx.w = ssim_ratio
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            raise DvsError("compute_reprojection_loss: the target image is data on this path (no gradient)")
+        g = _f32(g)
+        B, Cc, H, W = pred.shape
+        gp = torch.empty_like(pred)
+        with torch.cuda.device(g.device):
+            check(lib().dvs_reprojection_loss_bwd(ptr(g), ptr(pred), ptr(target), ptr(gp), B, Cc, H, W, ctx.w,
+                                                  stream_ptr(g.device)), "dvs_reprojection_loss_bwd")
+        return gp, None, None
+
+
+def compute_reprojection_loss(pred: torch.Tensor, target: torch.Tensor, ssim_ratio: float = 0.85) -> torch.Tensor:
+    """vo/learner_new.py:60-74: ssim_ratio * mean_c SSIM + (1 - ssim_ratio) * mean_c |target - pred| -> [B,1,H,W]."""
+    return _Reproj.apply(pred, target, float(ssim_ratio))
+
+
+# --------------------------------------------------------------------------------------------- smoothness
+class _Smooth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, img):
+        disp, img = _f32(disp), _f32(img)
+        require_cuda(disp, img)
+        B, one, H, W = disp.shape
+        if one != 1 or img.shape[0] != B or tuple(img.shape[2:]) != (H, W):
+            raise DvsError("get_smooth_loss expects disp [B,1,H,W] and img [B,C,H,W]")
+        Cc = img.shape[1]
+        n = C.c_size_t(0)
+        check(lib().dvs_smooth_loss_workspace_bytes(B, H, W, C.byref(n)), "dvs_smooth_loss_workspace_bytes")
+        ws = _ws(n.value, disp.device)
+        out = torch.empty(1, dtype=torch.float32, device=disp.device)
+        with torch.cuda.device(disp.device):
+            check(lib().dvs_smooth_loss_fwd(ptr(disp), ptr(img), ptr(out), B, Cc, H, W, ptr(ws), stream_ptr(disp.device)),
+                  "dvs_smooth_loss_fwd")
+        ctx.save_for_backward(disp, img)
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        disp, img = ctx.saved_tensors
+        B, _, H, W = disp.shape
+        g = _f32(g).reshape(1)
+        gd = torch.empty_like(disp)
+        with torch.cuda.device(g.device):
+            check(lib().dvs_smooth_loss_bwd(ptr(g), ptr(disp), ptr(img), ptr(gd), B, img.shape[1], H, W,
+                                            stream_ptr(g.device)), "dvs_smooth_loss_bwd")
+        return gd, None
+
+
+def get_smooth_loss(disp: torch.Tensor, img: torch.Tensor) -> torch.Tensor:
+    """vo/learner_func.py:161-174."""
+    return _Smooth.apply(disp, img)
+
+
+# --------------------------------------------------------------------------------------------- pose matrix
+class _PoseMatrix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, axisangle, translation, invert):
+        shp = axisangle.shape
+        aa, tr = _f32(axisangle).reshape(-1, 3), _f32(translation).reshape(-1, 3)
+        require_cuda(aa, tr)
+        B = aa.shape[0]
+        M = torch.empty(B, 4, 4, dtype=torch.float32, device=aa.device)
+        with torch.cuda.device(aa.device):
+            check(lib().dvs_pose_matrix_fwd(ptr(aa), ptr(tr), ptr(M), B, int(invert), stream_ptr(aa.device)),
+                  "dvs_pose_matrix_fwd")
+        ctx.save_for_backward(aa, tr)
+        ctx.meta = (shp, translation.shape, int(invert))
+        return M
+
+    @staticmethod
+    def backward(ctx, g):
+        aa, tr = ctx.saved_tensors
+        shp_a, shp_t, invert = ctx.meta
+        g = _f32(g)
+        ga, gt = torch.empty_like(aa), torch.empty_like(tr)
+        with torch.cuda.device(g.device):
+            check(lib().dvs_pose_matrix_bwd(ptr(g), ptr(aa), ptr(tr), ptr(ga), ptr(gt), aa.shape[0], invert,
+                                            stream_ptr(g.device)), "dvs_pose_matrix_bwd")
+        return ga.view(shp_a), gt.view(shp_t), None
+
+
+def transformation_from_parameters(axisangle: torch.Tensor, translation: torch.Tensor, invert: bool = False) -> torch.Tensor:
+    """vo/learner_func.py:29-46: axisangle, translation [B,1,3] -> 4x4 (inverted when `invert`)."""
+    return _PoseMatrix.apply(axisangle, translation, bool(invert))

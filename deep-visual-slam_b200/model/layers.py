@@ -1,0 +1,117 @@
+"""Geometry and photometric primitives of the VO learner, backed by the sm_100a kernels of libdvsloss.so.
+
+Same call surface as the reference's ``model/layers.py:16-268`` (twin: ``vo/learner_func.py:16-207``):
+``disp_to_depth``, ``transformation_from_parameters``, ``get_translation_matrix``, ``rot_from_axisangle``,
+``BackprojectDepth``, ``Project3D``, ``SSIM``, ``get_smooth_loss``, ``upsample``, ``ConvBlock``, ``Conv3x3``,
+``compute_depth_errors``.  The first eight are autograd functions over hand-written CUDA kernels
+(``dvsloss.ops``); the decoder blocks stay stock PyTorch convolutions, as in the reference.
+The training hot path does not call these one by one -- ``vo/learner_new.py`` uses the fused
+``dvsloss.view_synthesis_loss`` -- they serve the callers that use single primitives
+(vo/predict.py:83, vo/eval_traj.py, the ros2 node) and keep old learner code working.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
+
+from dvsloss import ops as _ops  # noqa: E402
+
+disp_to_depth = _ops.disp_to_depth
+transformation_from_parameters = _ops.transformation_from_parameters
+get_smooth_loss = _ops.get_smooth_loss
+
+
+def get_translation_matrix(translation_vector: torch.Tensor) -> torch.Tensor:
+    """[B,1,3] (or [B,3]) translation -> [B,4,4] homogeneous matrix (reference: model/layers.py:49-62)."""
+    t = translation_vector.reshape(-1, 3)
+    M = torch.eye(4, dtype=t.dtype, device=t.device).repeat(t.shape[0], 1, 1)
+    M[:, :3, 3] = t
+    return M
+
+
+def rot_from_axisangle(vec: torch.Tensor) -> torch.Tensor:
+    """[B,1,3] axis-angle -> [B,4,4] rotation (reference: model/layers.py:65-104); the pose kernel with t = 0."""
+    return _ops.transformation_from_parameters(vec, torch.zeros_like(vec), False)
+
+
+class BackprojectDepth(nn.Module):
+    """depth [B,1,H,W], inv_K [B,4,4] -> homogeneous camera points [B,4,H*W] (reference: model/layers.py:139-168).
+    The reference keeps a [B,3,HW] pixel grid and a ones tensor as frozen parameters (79 MB at B=16, 640x480);
+    the kernel generates pixel coordinates from the thread index instead, so this module holds no state."""
+
+    def __init__(self, batch_size: int, height: int, width: int):
+        super().__init__()
+        self.batch_size, self.height, self.width = batch_size, height, width
+
+    def forward(self, depth: torch.Tensor, inv_K: torch.Tensor) -> torch.Tensor:
+        if tuple(depth.shape[2:]) != (self.height, self.width):
+            raise ValueError(f"depth must be [B,1,{self.height},{self.width}], got {tuple(depth.shape)}")
+        return _ops.backproject(depth, inv_K)
+
+
+class Project3D(nn.Module):
+    """points [B,4,HW], K, T [B,4,4] -> sampling grid [B,H,W,2] in [-1,1] (reference: model/layers.py:171-193)."""
+
+    def __init__(self, batch_size: int, height: int, width: int, eps: float = 1e-7):
+        super().__init__()
+        self.batch_size, self.height, self.width, self.eps = batch_size, height, width, eps
+
+    def forward(self, points: torch.Tensor, K: torch.Tensor, T: torch.Tensor) -> torch.Tensor:
+        return _ops.project3d(points, K, T, self.height, self.width, self.eps)
+
+
+class SSIM(nn.Module):
+    """3x3 mean-filter SSIM loss map clamp((1 - SSIM)/2, 0, 1) with reflection padding
+    (reference: model/layers.py:218-248)."""
+
+    def forward(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        return _ops.ssim(x, y)
+
+
+def upsample(x: torch.Tensor) -> torch.Tensor:
+    """Nearest-neighbour x2 (DepthNet decoder, reference: model/layers.py:196-199) -- stock PyTorch."""
+    return F.interpolate(x, scale_factor=2, mode="nearest")
+
+
+class Conv3x3(nn.Module):
+    """Reflection- (or zero-) padded 3x3 convolution of the decoder -- stock PyTorch."""
+
+    def __init__(self, in_channels: int, out_channels: int, use_refl: bool = True):
+        super().__init__()
+        self.pad = nn.ReflectionPad2d(1) if use_refl else nn.ZeroPad2d(1)
+        self.conv = nn.Conv2d(int(in_channels), int(out_channels), 3)
+
+    def forward(self, x):
+        return self.conv(self.pad(x))
+
+
+class ConvBlock(nn.Module):
+    """Conv3x3 + ELU of the decoder -- stock PyTorch."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.conv = Conv3x3(in_channels, out_channels)
+        self.nonlin = nn.ELU(inplace=True)
+
+    def forward(self, x):
+        return self.nonlin(self.conv(x))
+
+
+def compute_depth_errors(gt: torch.Tensor, pred: torch.Tensor):
+    """Standard depth metrics (abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3); evaluation only."""
+    ratio = torch.max(gt / pred, pred / gt)
+    a1, a2, a3 = [(ratio < 1.25 ** k).float().mean() for k in (1, 2, 3)]
+    diff = gt - pred
+    rmse = diff.pow(2).mean().sqrt()
+    rmse_log = (gt.log() - pred.log()).pow(2).mean().sqrt()
+    abs_rel = (diff.abs() / gt).mean()
+    sq_rel = (diff.pow(2) / gt).mean()
+    return abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3

@@ -11,7 +11,9 @@ Tolerances (BASELINE.json north_star):
     The bound is therefore  |impl - ref32| <= (1e-5 + 2*nu) * |ref32|  with  nu = max_s |ref32_s - ref64_s| / |ref32_s|
     the measured fp32 rounding uncertainty of the reference on that input (largest per-scale deviation of the
     reference's fp32 value from the float64 evaluation).  nu is ~1e-7 on the random / full-size cases, so there
-    the plain 1e-5 gate decides; it only opens the gate on the tiny ill-conditioned fixtures.
+    the plain 1e-5 gate decides; it only opens the gate on the tiny ill-conditioned fixtures.  On images of a
+    few thousand pixels the per-pixel SSIM round-off (~2e-5, independent between pixels) does not average out
+    either, so an absolute 4 * 2e-5 / sqrt(B*H*W) is added (1e-7 at 640x480, i.e. irrelevant at real sizes).
   * argmin selection: candidates closer than fp32 round-off may flip.  Every disagreeing pixel must be a near
     tie of the oracle's candidate stack (gap <= 1e-4 absolute: with unit-range images and SSIM's C2 = 9e-4 the
     fp32 cancellation in E[x^2]-E[x]^2 moves a single SSIM value by up to ~2e-5), and disagreements must be
@@ -125,14 +127,17 @@ def check_parity(impl: Callable[[Dict[str, object], Optional[Sequence[float]]], 
     ps_ref, ps_64 = np.asarray(ref32["per_scale"], np.float64), np.asarray(ref64["per_scale"], np.float64)
     ps_got = np.asarray(got["per_scale"], np.float64)
     nu = float((np.abs(ps_ref - ps_64) / np.abs(ps_ref)).max())
-    tol = (loss_rtol + 2 * nu) * np.abs(ps_ref)
+    # fp32 SSIM noise: eps * |E[x^2]| / C2 ~ 6e-8 * 0.3 / 9e-4 = 2e-5 per pixel, independent between pixels;
+    # the mean over B*H*W pixels keeps 2e-5 / sqrt(B*H*W) of it (4 sigma allowed) -- matters on tiny images only
+    pix_noise = 4 * 2e-5 / np.sqrt(B * H * W)
+    tol = (loss_rtol + 2 * nu) * np.abs(ps_ref) + pix_noise
     err = np.abs(ps_got - ps_ref)
     stats["per_scale_rel_max"] = float((err / np.abs(ps_ref)).max())
     stats["ref_fp32_noise_rel_max"] = float((np.abs(ps_ref - ps_64) / np.abs(ps_ref)).max())
     assert np.all(err <= tol), f"loss/s off: got {ps_got}, ref {ps_ref}, err {err}, tol {tol}"
     l_ref, l_64 = float(ref32["loss"]), float(ref64["loss"])
     stats["loss_rel"] = abs(got["loss"] - l_ref) / abs(l_ref)
-    assert abs(got["loss"] - l_ref) <= (loss_rtol + 2 * nu) * abs(l_ref), (got["loss"], l_ref, l_64, nu)
+    assert abs(got["loss"] - l_ref) <= (loss_rtol + 2 * nu) * abs(l_ref) + pix_noise, (got["loss"], l_ref, l_64, nu)
 
     # ---- selection
     flips = 0.0

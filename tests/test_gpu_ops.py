@@ -1,0 +1,269 @@
+"""GPU parity of the granular operators (csrc/dvs_ops.cu via dvsloss.ops / model.layers) against the oracle's
+op-for-op restatement of the reference primitives run with torch on the same device, forward and backward.
+fp32; tolerances are a few ulp of the quantity's scale and are written at each assert."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import parity
+from oracle import reference_port as port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rnd(*shape, seed=0, lo=0.0, hi=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (lo + (hi - lo) * torch.rand(*shape, generator=g)).to(DEV)
+
+
+def smooth_img(B, C, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(B, C, max(H // 6, 2), max(W // 6, 2), generator=g)
+    img = F.interpolate(low, size=(H, W), mode="bicubic", align_corners=False) + 0.03 * torch.rand(B, C, H, W, generator=g)
+    return img.clamp(0, 1).to(DEV)
+
+
+def relinf(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def intrinsics(B, H, W):
+    from dvsloss.synthetic import redwood_intrinsics
+    d = redwood_intrinsics(B, H, W)
+    return d[("K", 0)].to(DEV), d[("inv_K", 0)].to(DEV)
+
+
+def test_disp_to_depth():
+    from model.layers import disp_to_depth
+    d = rnd(2, 1, 37, 53, seed=1).requires_grad_(True)
+    s, z = disp_to_depth(d, 0.1, 10.0)
+    d2 = d.detach().clone().requires_grad_(True)
+    s_ref, z_ref = port.disp_to_depth(d2, 0.1, 10.0)
+    assert torch.equal(s, s_ref)                      # same op order as the eager reference: bit-identical
+    assert torch.equal(z, z_ref)
+    gs, gz = rnd(2, 1, 37, 53, seed=2), rnd(2, 1, 37, 53, seed=3)
+    (s * gs + z * gz).sum().backward()
+    (s_ref * gs + z_ref * gz).sum().backward()
+    assert relinf(d.grad, d2.grad) < 1e-6
+
+
+@pytest.mark.parametrize("h,w,H,W", [(24, 32, 48, 64), (6, 8, 48, 64), (20, 27, 48, 64), (48, 64, 48, 64), (5, 7, 33, 47)])
+def test_upsample_bilinear(h, w, H, W):
+    from dvsloss.ops import upsample_bilinear
+    x = rnd(2, 1, h, w, seed=4).requires_grad_(True)
+    y = upsample_bilinear(x, (H, W))
+    x2 = x.detach().clone().requires_grad_(True)
+    y_ref = F.interpolate(x2, [H, W], mode="bilinear", align_corners=False)
+    assert float((y - y_ref).abs().max()) <= 2e-7     # values in [0,1]: 1-2 ulp
+    g = rnd(2, 1, H, W, seed=5)
+    (y * g).sum().backward()
+    (y_ref * g).sum().backward()
+    assert relinf(x.grad, x2.grad) < 2e-6
+
+
+def test_backproject_and_project():
+    from model.layers import BackprojectDepth, Project3D
+    B, H, W = 2, 40, 56
+    K, inv_K = intrinsics(B, H, W)
+    depth = rnd(B, 1, H, W, seed=6, lo=0.5, hi=5.0).requires_grad_(True)
+    aa = (0.01 * torch.randn(B, 1, 3, generator=torch.Generator().manual_seed(7))).to(DEV)
+    tr = (0.05 * torch.randn(B, 1, 3, generator=torch.Generator().manual_seed(8))).to(DEV)
+    T = port.transformation_from_parameters(aa, tr, False).requires_grad_(True)
+    bp, pj = BackprojectDepth(B, H, W).to(DEV), Project3D(B, H, W).to(DEV)
+    cam = bp(depth, inv_K)
+    pix = pj(cam, K, T)
+    depth2, T2 = depth.detach().clone().requires_grad_(True), T.detach().clone().requires_grad_(True)
+    cam_ref = port.backproject(depth2, inv_K)
+    pix_ref = port.project(cam_ref, K, T2, H, W)
+    assert cam.shape == cam_ref.shape == (B, 4, H * W)
+    assert relinf(cam, cam_ref) < 5e-7
+    assert pix.shape == pix_ref.shape == (B, H, W, 2)
+    assert float((pix - pix_ref).abs().max()) < 2e-6   # normalised coordinates in ~[-1,1]
+    g = rnd(B, H, W, 2, seed=9, lo=-1.0, hi=1.0)
+    (pix * g).sum().backward()
+    (pix_ref * g).sum().backward()
+    assert relinf(depth.grad, depth2.grad) < 1e-4
+    assert relinf(T.grad, T2.grad) < 1e-4
+
+
+def test_grid_sample_border():
+    from dvsloss.ops import grid_sample_border
+    B, C, H, W = 2, 3, 33, 47
+    src = smooth_img(B, C, H, W, 10)
+    grid = rnd(B, H, W, 2, seed=11, lo=-1.15, hi=1.15).requires_grad_(True)      # some samples outside the image
+    out = grid_sample_border(src, grid)
+    grid2 = grid.detach().clone().requires_grad_(True)
+    ref = F.grid_sample(src, grid2, padding_mode="border", align_corners=True)
+    assert float((out - ref).abs().max()) < 1e-6
+    g = rnd(B, C, H, W, seed=12, lo=-1, hi=1)
+    (out * g).sum().backward()
+    (ref * g).sum().backward()
+    assert relinf(grid.grad, grid2.grad) < 1e-5
+    clipped = (grid2.detach()[..., 0].abs() >= 1)
+    assert float(grid.grad[..., 0][clipped].abs().max()) == 0.0      # border clip: zero gradient
+
+
+@pytest.mark.parametrize("H,W", [(32, 48), (9, 13), (2, 2), (40, 70)])
+def test_ssim_and_reprojection(H, W):
+    from model.layers import SSIM
+    from vo.loss import compute_reprojection_loss
+    B, C = 2, 3
+    x = smooth_img(B, C, H, W, 13).requires_grad_(True)
+    y = (x.detach() + 0.05 * rnd(B, C, H, W, seed=14, lo=-1, hi=1)).clamp(0, 1).requires_grad_(True)
+    out = SSIM().to(DEV)(x, y)
+    x2, y2 = x.detach().clone().requires_grad_(True), y.detach().clone().requires_grad_(True)
+    ref = port.ssim(x2, y2)
+    assert float((out - ref).abs().max()) < 5e-5      # fp32 cancellation noise of E[x^2]-E[x]^2 over C2 = 9e-4
+    g = rnd(B, C, H, W, seed=15)
+    (out * g).sum().backward()
+    (ref * g).sum().backward()
+    assert relinf(x.grad, x2.grad) < 2e-3
+    assert relinf(y.grad, y2.grad) < 2e-3
+    # reprojection loss: SSIM + L1, gradient w.r.t. pred only
+    p = x.detach().clone().requires_grad_(True)
+    p2 = x.detach().clone().requires_grad_(True)
+    r = compute_reprojection_loss(p, y.detach(), 0.85)
+    r_ref = port.reprojection_loss(p2, y.detach(), 0.85)
+    assert r.shape == r_ref.shape == (B, 1, H, W)
+    assert float((r - r_ref).abs().max()) < 5e-5
+    g1 = rnd(B, 1, H, W, seed=16)
+    (r * g1).sum().backward()
+    (r_ref * g1).sum().backward()
+    assert relinf(p.grad, p2.grad) < 2e-3
+
+
+def test_get_smooth_loss():
+    from model.layers import get_smooth_loss
+    B, H, W = 3, 37, 51
+    disp = rnd(B, 1, H, W, seed=17).requires_grad_(True)
+    img = smooth_img(B, 3, H, W, 18)
+    out = get_smooth_loss(disp, img)
+    d2 = disp.detach().clone().requires_grad_(True)
+    ref = port.smooth_loss(d2, img)
+    assert out.dim() == 0
+    assert abs(float(out) - float(ref)) < 1e-5 * abs(float(ref))
+    (out * 3.0).backward()
+    (ref * 3.0).backward()
+    assert relinf(disp.grad, d2.grad) < 1e-5
+
+
+@pytest.mark.parametrize("invert", [False, True])
+def test_transformation_from_parameters(invert):
+    from model.layers import transformation_from_parameters
+    B = 5
+    g = torch.Generator().manual_seed(19)
+    aa = (0.3 * torch.randn(B, 1, 3, generator=g)).to(DEV)
+    aa[0] = 0.0                                            # zero rotation: the reference's norm backward gives 0
+    tr = torch.randn(B, 1, 3, generator=g).to(DEV)
+    a1, t1 = aa.clone().requires_grad_(True), tr.clone().requires_grad_(True)
+    a2, t2 = aa.clone().requires_grad_(True), tr.clone().requires_grad_(True)
+    M = transformation_from_parameters(a1, t1, invert)
+    M_ref = port.transformation_from_parameters(a2, t2, invert)
+    assert M.shape == (B, 4, 4)
+    assert float((M - M_ref).abs().max()) < 5e-7
+    gm = torch.randn(B, 4, 4, generator=g).to(DEV)
+    (M * gm).sum().backward()
+    (M_ref * gm).sum().backward()
+    assert relinf(a1.grad, a2.grad) < 1e-4
+    assert relinf(t1.grad, t2.grad) < 1e-5
+
+
+def test_granular_chain_vs_reference_golden_intermediates():
+    """("depth", s) and ("color", f, s) of the live reference (stored in the first fixture) from the per-op kernels."""
+    from dvsloss import ops
+    g = parity.load_golden("ref_b2_48x64_consistent.npz")
+    raw, prob = g["raw"], g["prob"]
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=DEV)
+    H, W = prob["target"].shape[2:]
+    for s in range(4):
+        du = ops.upsample_bilinear(t(prob["disps"][s]), (H, W))
+        _, depth = ops.disp_to_depth(du, 0.1, 10.0)
+        assert relinf(depth, t(raw[f"depth{s}"])) < 1e-6
+        cam = ops.backproject(depth, t(prob["inv_K"]))
+        for i in range(2):
+            grid = ops.project3d(cam, t(prob["K"]), t(prob["Ts"][i]), H, W)
+            color = ops.grid_sample_border(t(prob["sources"][i]), grid)
+            assert float((color - t(raw[f"color{s}_{i}"])).abs().max()) < 2e-5   # coordinates differ by ~1e-5 px
+
+
+class _FakeDepthNet(torch.nn.Module):
+    """Tiny stand-in for DepthNet: 4 sigmoid disparity maps at H>>s (model/depthnet.py:87-88)."""
+
+    def __init__(self):
+        super().__init__()
+        self.convs = torch.nn.ModuleList([torch.nn.Conv2d(3, 1, 3, padding=1) for _ in range(4)])
+
+    def forward(self, x):
+        out = {}
+        for s in range(4):
+            xs = F.avg_pool2d(x, 2 ** s) if s else x
+            out[("disp", s)] = torch.sigmoid(self.convs[s](xs))
+        return out
+
+
+class _FakePoseNet(torch.nn.Module):
+    """Tiny stand-in for PoseNet: 6-channel pair -> (axisangle, translation) [B,1,1,3] (posenet_single.py:195-200)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(6, 6, 3, padding=1)
+
+    def forward(self, x):
+        o = 0.01 * self.conv(x).mean((2, 3)).view(-1, 1, 1, 6)
+        return o[..., :3], o[..., 3:]
+
+
+def _make_trainer(B, H, W, fused, noise):
+    from vo.learner_new import MonodepthTrainer
+    torch.manual_seed(0)
+    cfg = {"Train": dict(num_source=2, batch_size=B, img_h=H, img_w=W, smoothness_ratio=0.001, auto_mask=True,
+                         ssim_ratio=0.85, min_depth=0.1, max_depth=10.0, use_compile=False)}
+    return MonodepthTrainer(_FakeDepthNet().to(DEV), _FakePoseNet().to(DEV), cfg, torch.device(DEV), noise=noise, fused=fused)
+
+
+def test_monodepth_trainer_process_batch_contract():
+    """process_batch(sample) -> (outputs, losses) with the reference's keys; gradients reach both networks;
+    the fused path and the per-op path agree."""
+    from dvsloss.synthetic import make_problem
+    B, H, W = 2, 64, 96
+    p = make_problem(B, H, W, 2, 4, seed=21)
+    tf = _make_trainer(B, H, W, True, "torch")
+    sample = {k: v.clone() for k, v in p["sample"].items()}          # CPU tensors: moved to the device in place
+    torch.manual_seed(123)
+    outputs, losses = tf.process_batch(sample)
+    assert all(v.is_cuda for v in sample.values())
+    assert set(losses) == {"loss", "loss/0", "loss/1", "loss/2", "loss/3"}
+    assert all(losses[k].dim() == 0 and losses[k].is_cuda for k in losses)
+    for f in (-1, 1):
+        assert outputs[("cam_T_cam", 0, f)].shape == (B, 4, 4)
+        assert outputs[("axisangle", 0, f)].shape == (B, 1, 1, 3)
+    assert outputs["identity_selection/0"].shape == (B, 1, H, W)
+    losses["loss"].backward()
+    gd = [p_.grad.clone() for p_ in tf.depth_net.parameters()]
+    gp = [p_.grad.clone() for p_ in tf.pose_net.parameters()]
+    assert all(torch.isfinite(g).all() and g.abs().sum() > 0 for g in gd + gp)
+    # per-op path with the same weights and the same RNG stream for the automask noise
+    tg = _make_trainer(B, H, W, False, "torch")
+    tg.depth_net.load_state_dict(tf.depth_net.state_dict())
+    tg.pose_net.load_state_dict(tf.pose_net.state_dict())
+    torch.manual_seed(123)
+    outputs2, losses2 = tg.process_batch({k: v.clone() for k, v in p["sample"].items()})
+    for k in losses:
+        assert abs(float(losses[k]) - float(losses2[k])) <= 2e-5 * abs(float(losses2[k])) + 1e-7, k
+    losses2["loss"].backward()
+    for a, b in zip(gd + gp, [q.grad for q in list(tg.depth_net.parameters()) + list(tg.pose_net.parameters())]):
+        assert relinf(a, b) < 5e-3
+    # lazily materialised plotting outputs
+    tf.materialize_outputs(sample, outputs)
+    assert outputs[("depth", 0)].shape == (B, 1, H, W) and outputs[("color", -1, 3)].shape == (B, 3, H, W)
+
+
+def test_ops_reject_cpu_tensors():
+    from dvsloss import DvsError
+    from model.layers import SSIM, disp_to_depth
+    with pytest.raises(DvsError):
+        disp_to_depth(torch.rand(1, 1, 4, 4), 0.1, 10.0)
+    with pytest.raises(DvsError):
+        SSIM()(torch.rand(1, 3, 8, 8), torch.rand(1, 3, 8, 8))
