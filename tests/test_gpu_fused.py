@@ -111,7 +111,22 @@ def test_fused_identity_pose_selects_identity_or_reproj_equally():
     prob["Ts"] = [np.eye(4, dtype=np.float32)[None].copy() for _ in range(2)]
     got = cuda_impl(prob, None)
     ref = parity.oracle_eval(prob, want_grad=False)
-    np.testing.assert_allclose(got["per_scale"], ref["per_scale"], rtol=1e-5, atol=2e-7)
+    # the photometric residue is pure round-off, clamped at >= 0 (E ~ 3e-7), on top of the smoothness term (~1e-4)
+    np.testing.assert_allclose(got["per_scale"], ref["per_scale"], rtol=1e-5, atol=1e-6)
+    smooth_only = [1e-3 / 2 ** s * float(ref_s) for s, ref_s in enumerate(_smooth_terms(prob))]
+    np.testing.assert_allclose(got["per_scale"], smooth_only, rtol=1e-5, atol=1e-6)
+
+
+def _smooth_terms(prob):
+    from oracle import reference_port as port
+    import torch.nn.functional as F
+    tgt = torch.as_tensor(prob["target"])
+    out = []
+    for d in prob["disps"]:
+        du = F.interpolate(torch.as_tensor(d), tgt.shape[2:], mode="bilinear", align_corners=False)
+        nd = du / (du.mean((2, 3), keepdim=True).clamp(min=1e-3) + 1e-7)
+        out.append(port.smooth_loss(nd, tgt))
+    return out
 
 
 def test_fused_rejects_cpu_tensors():

