@@ -319,6 +319,9 @@ __global__ void __launch_bounds__(kThreads) gs_bwd_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------ SSIM / reprojection loss
 // vo/learner_func.py:190-207 and vo/learner_new.py:60-74.
 // 3x3 sums around (y,x) of one plane pair with 1-px reflection, straight from global memory (L1-resident rows).
+// The granular op reproduces the eager op order of the reference on CUDA exactly: x*x, y*y, x*y are rounded
+// products (separate tensors in vo/learner_func.py:199-201), ATen's avg_pool2d adds the window row-major into one
+// fp32 accumulator and divides by 9, and no multiply-add is contracted (hence the __f*_rn intrinsics).
 __device__ __forceinline__ void sums3x3(const float* __restrict__ X, const float* __restrict__ Y, int y, int x, int H,
                                         int W, float& sx, float& sy, float& sxx, float& syy, float& sxy) {
   sx = sy = sxx = syy = sxy = 0.f;
@@ -329,18 +332,20 @@ __device__ __forceinline__ void sums3x3(const float* __restrict__ X, const float
     for (int dx = -1; dx <= 1; ++dx) {
       int xx = reflect_clamp(x + dx, W);
       float a = X[yy * W + xx], b = Y[yy * W + xx];
-      sx += a; sy += b;
-      sxx = fmaf(a, a, sxx); syy = fmaf(b, b, syy); sxy = fmaf(a, b, sxy);
+      sx = __fadd_rn(sx, a); sy = __fadd_rn(sy, b);
+      sxx = __fadd_rn(sxx, __fmul_rn(a, a)); syy = __fadd_rn(syy, __fmul_rn(b, b)); sxy = __fadd_rn(sxy, __fmul_rn(a, b));
     }
   }
 }
-// exact-division SSIM loss value (granular op: follows the eager op order, IEEE division)
+// SSIM loss value in the eager op order (vo/learner_func.py:194-207), IEEE division, every op rounded on its own
 __device__ __forceinline__ float ssim_value(float sx, float sy, float sxx, float syy, float sxy) {
-  float mx = sx / 9.f, my = sy / 9.f;
-  float sgx = sxx / 9.f - mx * mx, sgy = syy / 9.f - my * my, sgxy = sxy / 9.f - mx * my;
-  float n = (2.f * mx * my + kC1) * (2.f * sgxy + kC2);
-  float d = (mx * mx + my * my + kC1) * (sgx + sgy + kC2);
-  return fminf(fmaxf((1.f - n / d) / 2.f, 0.f), 1.f);
+  float mx = __fdiv_rn(sx, 9.f), my = __fdiv_rn(sy, 9.f);
+  float mx2 = __fmul_rn(mx, mx), my2 = __fmul_rn(my, my), mxy = __fmul_rn(mx, my);
+  float sgx = __fsub_rn(__fdiv_rn(sxx, 9.f), mx2), sgy = __fsub_rn(__fdiv_rn(syy, 9.f), my2);
+  float sgxy = __fsub_rn(__fdiv_rn(sxy, 9.f), mxy);
+  float n = __fmul_rn(__fadd_rn(__fmul_rn(__fmul_rn(2.f, mx), my), kC1), __fadd_rn(__fmul_rn(2.f, sgxy), kC2));
+  float d = __fmul_rn(__fadd_rn(__fadd_rn(mx2, my2), kC1), __fadd_rn(__fadd_rn(sgx, sgy), kC2));
+  return fminf(fmaxf(__fdiv_rn(__fsub_rn(1.f, __fdiv_rn(n, d)), 2.f), 0.f), 1.f);
 }
 // REPROJ=false: out[b,c,y,x] = SSIM loss map.  REPROJ=true: out[b,0,y,x] = w*mean_c SSIM + (1-w)*mean_c |y-x|.
 template <bool REPROJ>
@@ -357,13 +362,14 @@ __global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(const float* __restr
       sums3x3(X, Y, py, px, H, W, sx, sy, sxx, syy, sxy);
       float S = ssim_value(sx, sy, sxx, syy, sxy);
       if (REPROJ) {
-        accS += S;
-        accL += fabsf(Y[p] - X[p]);
+        accS = __fadd_rn(accS, S);
+        accL = __fadd_rn(accL, fabsf(__fsub_rn(Y[p], X[p])));
       } else {
         out[((size_t)b * C + c) * HW + p] = S;
       }
     }
-    if (REPROJ) out[(size_t)b * HW + p] = w * (accS / (float)C) + (1.f - w) * (accL / (float)C);
+    if (REPROJ)
+      out[(size_t)b * HW + p] = __fadd_rn(__fmul_rn(w, __fdiv_rn(accS, (float)C)), __fmul_rn(1.f - w, __fdiv_rn(accL, (float)C)));
   }
 }
 // Backward w.r.t. the FIRST image argument (SSIM is symmetric: call with the arguments swapped for the other).

@@ -113,8 +113,9 @@ def test_fused_identity_pose_selects_identity_or_reproj_equally():
     ref = parity.oracle_eval(prob, want_grad=False)
     # the photometric residue is pure round-off, clamped at >= 0 (E ~ 3e-7), on top of the smoothness term (~1e-4)
     np.testing.assert_allclose(got["per_scale"], ref["per_scale"], rtol=1e-5, atol=1e-6)
+    # without the automask the identity warp leaves |target - warped| ~ 1e-4 px * image slope: ~1e-6 of L1 + SSIM residue
     smooth_only = [1e-3 / 2 ** s * float(ref_s) for s, ref_s in enumerate(_smooth_terms(prob))]
-    np.testing.assert_allclose(got["per_scale"], smooth_only, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got["per_scale"], smooth_only, rtol=1e-5, atol=5e-6)
 
 
 def _smooth_terms(prob):
