@@ -57,14 +57,14 @@ __global__ void __launch_bounds__(NT, (NS <= 2 ? 2 : 1)) fused_tile_kernel(const
   ThreadState<NS> st;
 
   phase_consts<NS>(p, t, sm, tid);
-  phase_load<NS>(p, t, sm, tid);
+  phase_load<NS>(p, t, sm, tid, st);
   __syncthreads();
   phase_identity<NS>(p, t, sm, tid, st);
   __syncthreads();
 
   for (int s = 0; s < p.S; ++s) {
     reset_scale_state<NS>(st);
-    phase_warp<NS>(p, t, sm, tid, s);
+    phase_warp<NS>(p, t, sm, tid, s, st);
     __syncthreads();
     phase_stats<NS, GRAD>(p, t, sm, tid, s, st);
     __syncthreads();
@@ -97,6 +97,7 @@ struct FinishParams {
   const float* part;        // [nblk][S][nv]
   const float* mean_part;   // [S][B][kMeanBlocks]
   const float* K;           // [B,4,4]
+  const float* invK;        // [B,4,4]
   float* perimg;            // [S][B][3]
   float* uT;                // [S][N][B][16] or null
   float* coup;              // [S][B] or null
@@ -117,13 +118,11 @@ __global__ void __launch_bounds__(256) finish_kernel(FinishParams f) {
   const int tid = threadIdx.x;
   if (tid < 3) f.perimg[(s * f.B + b) * 3 + tid] = res[tid];
   if (!f.want_grad) return;
-  if (tid < 16 * f.N) {
-    // dL/dT[m][k] = sum_{j<3} K[j][m] * dL/dP[j][k]
-    int i = tid / 16, m = (tid % 16) / 4, k = tid % 4;
-    const float* Kb = f.K + b * 16;
-    float a = 0.f;
-    for (int j = 0; j < 3; ++j) a = fmaf(Kb[j * 4 + m], res[3 + 12 * i + j * 4 + k], a);
-    f.uT[(((size_t)s * f.N + i) * f.B + b) * 16 + m * 4 + k] = a;
+  if (tid < f.N) {
+    // pose moments -> dL/dP -> dL/dT = K^T dL/dP
+    float dT[16];
+    moments_to_dT(res + 3 + 12 * tid, f.K + b * 16, f.invK + b * 16, dT);
+    for (int e = 0; e < 16; ++e) f.uT[(((size_t)s * f.N + tid) * f.B + b) * 16 + e] = dT[e];
   }
   if (tid == 64) {
     const float* mp = f.mean_part + (s * f.B + b) * kMeanBlocks;
@@ -335,7 +334,7 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
   FinishParams f{};
   f.B = sh->B; f.H = sh->H; f.W = sh->W; f.N = sh->N; f.S = sh->S;
   f.tiles_per_img = w.tiles_x * w.tiles_y; f.want_grad = p.want_grad; f.smooth_w = p.smooth_w;
-  f.part = p.part; f.mean_part = p.mean_part; f.K = K;
+  f.part = p.part; f.mean_part = p.mean_part; f.K = K; f.invK = inv_K;
   f.perimg = reinterpret_cast<float*>(base + w.perimg);
   f.uT = uT; f.coup = coup;
   finish_kernel<<<dim3(sh->B, sh->S), 256, 0, st>>>(f);

@@ -1,13 +1,24 @@
-// Fused view-synthesis loss: per-tile phase functions.
+// Fused view-synthesis loss: per-tile phase functions (v2).
 //
 // One CTA owns a 30x30 block of target pixels of one batch item ("R0") and evaluates SSIM statistics on
 // the surrounding 32x32 block ("R1", the window centres whose 3x3 adjoint reaches R0) from warped
 // colours on the 34x34 block ("R2").  It walks all S scales with the target / source tiles resident in
-// shared memory.  The phases are written as plain functions of (tid, shared memory, per-thread state) so
-// that the same source compiles
+// shared memory.  A thread owns four vertically adjacent pixels of one R1 column (lane == column), so
+// every shared-memory access of a warp is one conflict-free row segment.
+// The phases are written as plain functions of (tid, shared memory, per-thread state) so that the same
+// source compiles
 //   * under nvcc into the sm_100a kernel in dvs_fused.cu (phases separated by __syncthreads()), and
 //   * under g++ into a sequential block emulator used by the CPU-side unit tests (tests/emu),
 // which lets the tile logic be checked against the oracle without a GPU.
+//
+// The kernel is instruction-issue bound (about 40 B of compulsory traffic against several hundred fp32
+// operations per warped pixel), so the arithmetic is arranged for few instructions rather than few bytes:
+//   * projection  c = D * (A_i (u,v,1)) + p_i  with A_i = (K T_i)[:, :3] inv_K hoisted per tile
+//   * bilinear taps as lerps (value and both slopes share the differences)
+//   * SSIM on 9-sums with the 1/9 and 1/81 factors folded into the constants, separable 3x3 sums shared
+//     between the four pixels of a thread, target-side sums shared between the sources
+//   * pose gradient accumulated as 12 moments  sum g_c * D * (u, v, 1), sum g_c  (mapped to dL/dT in the
+//     finish kernel)
 //
 // Reference arithmetic being replaced (see oracle/closed_form.py for the explicit formulas):
 //   vo/learner_new.py:136-170   up-sample, disp_to_depth, BackprojectDepth, Project3D, border grid_sample
@@ -19,25 +30,29 @@
 
 #if defined(__CUDACC__)
 #define DVS_HD __host__ __device__ __forceinline__
+#define DVS_UNROLL _Pragma("unroll")
 #else
 #define DVS_HD inline
+#define DVS_UNROLL
 #endif
 
 namespace dvs {
 
 constexpr int kMaxS = 4;
 constexpr int kMaxN = 4;
-constexpr int TW = 32;                 // R1 width  (8 quads of 4 pixels)
-constexpr int TH = 32;                 // R1 height
+constexpr int TW = 32;                 // R1 width  (one lane per column)
+constexpr int TH = 32;                 // R1 height (8 warps x 4 rows)
 constexpr int PITCH_X = TW - 2;        // R0 width  = tile pitch in x
 constexpr int PITCH_Y = TH - 2;        // R0 height = tile pitch in y
 constexpr int RW2 = TW + 2;            // R2 width
 constexpr int RH2 = TH + 2;            // R2 height
-constexpr int PW = 36;                 // plane row stride (floats); col lx lives at lx+4, lx in [-1,TW]
-constexpr int PLANE = RH2 * PW + 4;    // 1228 floats; the +4 absorbs lx==TW of the last row
-constexpr int NT = 256;                // threads per CTA == quads in R1
+constexpr int PW = RW2;                // plane row stride (floats)
+constexpr int PLANE = RH2 * PW;        // 1156 floats; plane index of R2 pixel (ly,lx) is (ly+1)*PW + lx+1
+constexpr int NT = 256;                // threads per CTA
+constexpr int NIT = (PLANE + NT - 1) / NT;   // R2 pixels per thread in the load / warp phases (5)
 constexpr int kMeanBlocks = 16;        // partial sums per (scale, batch item) in the disparity-mean pre-pass
 constexpr float kC1 = 0.0001f, kC2 = 0.0009f;
+constexpr float kK1 = 81.0f * 0.0001f, kK2 = 81.0f * 0.0009f;   // SSIM constants on 9-sums
 constexpr int kSelNone = 255;
 
 // ------------------------------------------------------------------------------------------------
@@ -65,6 +80,8 @@ struct FusedParams {
   int tiles_x, tiles_y;
 };
 
+// per-block partial sums: [0] photometric, [1] smooth-x, [2] smooth-y, then per source 12 pose moments
+//   M[r*4 + 0..2] = sum g_c[r] * D * (u, v, 1),  M[r*4 + 3] = sum g_c[r]      (r = row of the 3x4 projection)
 DVS_HD int nvals(int N) { return 3 + 12 * N; }
 
 // ------------------------------------------------------------------------------------------------ math
@@ -84,6 +101,13 @@ DVS_HD float exp_fast(float x) {
   return expf(x);
 #endif
 }
+DVS_HD float sat01(float x) {
+#if defined(__CUDA_ARCH__)
+  return __saturatef(x);
+#else
+  return x != x ? 0.f : fminf(fmaxf(x, 0.f), 1.f);
+#endif
+}
 DVS_HD float sgn(float x) { return (float)(x > 0.f) - (float)(x < 0.f); }
 DVS_HD int imin(int a, int b) { return a < b ? a : b; }
 DVS_HD int imax(int a, int b) { return a > b ? a : b; }
@@ -93,14 +117,20 @@ DVS_HD int reflect_clamp(int g, int n) {
   g = g >= n ? 2 * (n - 1) - g : g;
   return imin(imax(g, 0), n - 1);
 }
-DVS_HD int pidx(int ly, int lx) { return (ly + 1) * PW + (lx + 4); }
+DVS_HD int pidx(int ly, int lx) { return (ly + 1) * PW + (lx + 1); }
 
 // ATen bilinear (align_corners=False) source taps for one output coordinate (UpSample.h:259-311).
 DVS_HD void up_taps(int dst, float scale, int in, int& i0, int& i1, float& lam) {
   float s = fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.f);
   i0 = imin((int)s, in - 1);
-  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  i1 = imin(i0 + 1, in - 1);
   lam = fminf(fmaxf(s - (float)i0, 0.f), 1.f);
+}
+// Weight of coarse index `coarse` in the up-sampled value at fine index `fine`: the taps above are the hat
+// function around the clamped source coordinate.
+DVS_HD float tap_weight(int fine, float scale, int in, int coarse) {
+  float s = fminf(fmaxf(scale * ((float)fine + 0.5f) - 0.5f, 0.f), (float)(in - 1));
+  return fmaxf(1.f - fabsf(s - (float)coarse), 0.f);
 }
 // Total weight that coarse index i receives from all `out` fine positions (== out/in for exact ratios).
 DVS_HD float up_weight(int i, int in, int out) {
@@ -118,34 +148,27 @@ DVS_HD float up_weight(int i, int in, int out) {
   return w;
 }
 
-DVS_HD float bilinear_disp(const float* __restrict__ d, int dh, int dw, int H, int W, int ry, int rx) {
-  if (dh == H && dw == W) return d[ry * dw + rx];
-  int y0, y1, x0, x1;
-  float ly, lx;
-  up_taps(ry, (float)dh / (float)H, dh, y0, y1, ly);
-  up_taps(rx, (float)dw / (float)W, dw, x0, x1, lx);
-  float a = d[y0 * dw + x0], b = d[y0 * dw + x1], c = d[y1 * dw + x0], e = d[y1 * dw + x1];
-  float top = a * (1.f - lx) + b * lx;
-  float bot = c * (1.f - lx) + e * lx;
-  return top * (1.f - ly) + bot * ly;
-}
-
-// Counter-based standard normal for the automask tie-break when no noise tensor is given.
+// Counter-based standard normals for the automask tie-break when no noise tensor is given: one Box-Muller
+// pair per (pixel, scale, source pair).
 DVS_HD unsigned int hash32(unsigned int x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
 }
-DVS_HD float hash_normal(unsigned long long seed, unsigned long long offset, unsigned int idx, unsigned int stream) {
+DVS_HD void hash_normal2(unsigned long long seed, unsigned long long offset, unsigned int idx, unsigned int stream,
+                         float& n0, float& n1) {
   unsigned int k = (unsigned int)(seed ^ (seed >> 32)) + 0x9e3779b9U * (unsigned int)(offset + stream);
   unsigned int h1 = hash32(idx ^ k);
   unsigned int h2 = hash32(h1 + 0x68bc21ebU + stream);
   float u1 = ((float)(h1 >> 8) + 1.0f) * (1.0f / 16777217.0f);   // (0,1)
   float u2 = (float)(h2 >> 8) * (1.0f / 16777216.0f);
 #if defined(__CUDA_ARCH__)
-  return sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530718f * u2);
+  float r = sqrtf(-2.0f * __logf(u1)), sn, cs;
+  __sincosf(6.28318530718f * u2, &sn, &cs);
 #else
-  return sqrtf(-2.0f * logf(u1)) * cosf(6.28318530718f * u2);
+  float r = sqrtf(-2.0f * logf(u1)), sn = sinf(6.28318530718f * u2), cs = cosf(6.28318530718f * u2);
 #endif
+  n0 = r * cs;
+  n1 = r * sn;
 }
 
 // ------------------------------------------------------------------------------------------------ shared memory
@@ -159,23 +182,25 @@ struct SmemLayout {
   DVS_HD int wx() const { return (13 + 3 * N) * PLANE; }
   DVS_HD int wy() const { return (14 + 3 * N) * PLANE; }
   DVS_HD int sel() const { return (15 + 3 * N) * PLANE; }            // PLANE bytes = PLANE/4 floats
-  DVS_HD int consts() const { return sel() + PLANE / 4; }            // kConstFloats floats
-  DVS_HD int total() const { return consts() + 64 + 16 * kMaxN; }
-  // scratch for block reductions / up-sample adjoint: aliases X (+F) once those are dead
+  DVS_HD int consts() const { return sel() + PLANE / 4; }
+  DVS_HD int total() const { return consts() + 8 + 12 * kMaxN; }
+  // scratch for block reductions / up-sample adjoint: aliases X (and the head of F) once those are dead
   DVS_HD int scratch() const { return x(0, 0); }
   DVS_HD int tbuf() const { return f(9) - 1152; }                     // last 1152 floats of F
   DVS_HD int rbuf() const { return f(9) - 1152 - 512; }               // 512 floats before it
 };
-// consts block: [0..8] inv_K 3x3, [9..12] inv_mu[s], [13..16] unused, [20+12i ..] P_i (3x4)
-constexpr int kC_iK = 0, kC_invmu = 9, kC_P = 20;
+// consts block: [0..3] inv_mu[s]; [8+12i ..] A_i (3x3 row-major) then p_i (3)
+constexpr int kC_invmu = 0, kC_A = 8;
 
 template <int NS>
 struct ThreadState {
-  float ident[NS][4];   // identity reprojection loss of the own quad (scale independent)
+  float ident[NS][4];      // identity reprojection loss of the own pixels (scale independent)
+  int pos[NIT];            // (ry << 16) | rx : reflected image coordinates of the R2 pixels this thread loads / warps
+  int flags;               // bit j: pixel j inside the image; bit 4+j: pixel j belongs to R0 (own)
   float acc[3];            // photometric sum, smooth-x sum, smooth-y sum of the current scale
-  float dP[NS][12];     // pose-gradient accumulators of the current scale
-  float gdu[4];            // d loss / d disp_up of the own quad, current scale
-  unsigned char tag[4];    // selected source of the own quad (kSelNone: identity / outside)
+  float dM[NS][12];        // pose-gradient moments of the current scale
+  float gdu[4];            // d loss / d disp_up of the own pixels, current scale
+  int tags;                // selected source of the 4 pixels, one byte each (kSelNone: identity / outside)
 };
 
 struct Tile {
@@ -195,24 +220,39 @@ DVS_HD Tile make_tile(const FusedParams& p, int blk) {
   return t;
 }
 
+// thread -> pixels: column cx = lane, rows r0 .. r0+3 of R1
+DVS_HD void quad_coords(int tid, int& r0, int& cx) { r0 = (tid >> 5) << 2; cx = tid & 31; }
+
 // ------------------------------------------------------------------------------------------------ phase 0
-// constants of the tile: inv_K, P_i = (K T_i)[:3,:], 1/(clamp(mean disp)+1e-7) per scale.
+// constants of the tile: A_i = (K T_i)[:3,:3] inv_K[:3,:3], p_i = (K T_i)[:3,3], 1/(clamp(mean disp)+1e-7) per scale.
 template <int NS>
 DVS_HD void phase_consts(const FusedParams& p, const Tile& t, float* sm, int tid) {
   SmemLayout L{NS};
   float* c = sm + L.consts();
-  if (tid < 9) {
-    int r = tid / 3, k = tid - r * 3;
-    c[kC_iK + tid] = p.invK[t.b * 16 + r * 4 + k];
-  } else if (tid >= 32 && tid < 32 + 12 * NS) {
-    int e = tid - 32, i = e / 12, j = (e % 12) / 4, k = e % 4;
+  if (tid < 12 * NS) {
+    int i = tid / 12, e = tid - i * 12;
     const float* Kb = p.K + t.b * 16;
     const float* Tb = p.T[i] + t.b * 16;
-    float a = 0.f;
-    for (int m = 0; m < 4; ++m) a = fmaf(Kb[j * 4 + m], Tb[m * 4 + k], a);
-    c[kC_P + e] = a;
-  } else if (tid >= 96 && tid < 96 + p.S) {
-    int s = tid - 96;
+    const float* iK = p.invK + t.b * 16;
+    // a few hundred double-precision operations per tile: keeps A within one fp32 rounding of the exact product,
+    // so the hoisting adds no coordinate error beyond the reference's own fp32 evaluation
+    if (e < 9) {
+      int r = e / 3, k = e - r * 3;
+      double a = 0.0;
+      for (int m = 0; m < 3; ++m) {
+        double P = 0.0;                                    // (K T)[r][m]
+        for (int n = 0; n < 4; ++n) P += (double)Kb[r * 4 + n] * (double)Tb[n * 4 + m];
+        a += P * (double)iK[m * 4 + k];
+      }
+      c[kC_A + 12 * i + e] = (float)a;
+    } else {
+      int r = e - 9;
+      double P = 0.0;
+      for (int n = 0; n < 4; ++n) P += (double)Kb[r * 4 + n] * (double)Tb[n * 4 + 3];
+      c[kC_A + 12 * i + e] = (float)P;
+    }
+  } else if (tid >= 64 && tid < 64 + p.S) {
+    int s = tid - 64;
     const float* mp = p.mean_part + (s * p.B + t.b) * kMeanBlocks;
     float m = 0.f;
     for (int k = 0; k < kMeanBlocks; ++k) m += mp[k];
@@ -221,292 +261,349 @@ DVS_HD void phase_consts(const FusedParams& p, const Tile& t, float* sm, int tid
   }
 }
 
-// load target (-> Y) and sources (-> X, for the identity terms) on R2 with reflection; zero F.
+// load target (-> Y) and sources (-> X, for the identity terms) on R2 with reflection; zero F; per-thread pixel flags.
 template <int NS>
-DVS_HD void phase_load(const FusedParams& p, const Tile& t, float* sm, int tid) {
+DVS_HD void phase_load(const FusedParams& p, const Tile& t, float* sm, int tid, ThreadState<NS>& st) {
   SmemLayout L{NS};
   const int HW = p.H * p.W;
-  for (int k = tid; k < RW2 * RH2; k += NT) {
-    int ly = k / RW2 - 1, lx = k % RW2 - 1;
+  DVS_UNROLL
+  for (int it = 0; it < NIT; ++it) {
+    int k = tid + it * NT;
+    st.pos[it] = 0;
+    if (k >= PLANE) continue;
+    int ly = k / PW - 1, lx = k % PW - 1;
     int gy = reflect_clamp(t.gy0 + ly, p.H), gx = reflect_clamp(t.gx0 + lx, p.W);
-    int o = gy * p.W + gx, q = pidx(ly, lx);
+    st.pos[it] = (gy << 16) | gx;
+    int o = gy * p.W + gx;
     const float* tg = p.target + (size_t)t.b * 3 * HW + o;
-    sm[L.y(0) + q] = tg[0];
-    sm[L.y(1) + q] = tg[HW];
-    sm[L.y(2) + q] = tg[2 * HW];
+    sm[L.y(0) + k] = tg[0];
+    sm[L.y(1) + k] = tg[HW];
+    sm[L.y(2) + k] = tg[2 * HW];
     if (p.auto_mask) {
+      DVS_UNROLL
       for (int i = 0; i < NS; ++i) {
         const float* sg = p.src[i] + (size_t)t.b * 3 * HW + o;
-        sm[L.x(i, 0) + q] = sg[0];
-        sm[L.x(i, 1) + q] = sg[HW];
-        sm[L.x(i, 2) + q] = sg[2 * HW];
+        sm[L.x(i, 0) + k] = sg[0];
+        sm[L.x(i, 1) + k] = sg[HW];
+        sm[L.x(i, 2) + k] = sg[2 * HW];
       }
     }
   }
   for (int k = tid; k < 9 * PLANE; k += NT) sm[L.f(0) + k] = 0.f;
-}
-
-// ------------------------------------------------------------------------------------------------ quad SSIM
-struct QuadStats {
-  float sx[4], sxx[4], sxy[4];
-};
-struct QuadY {
-  float yv[3][6];
-  float sy[4], syy[4];
-};
-
-DVS_HD void load_row6(const float* pl, int o, float* v) {
-  v[0] = pl[o - 1];
-  v[1] = pl[o];
-  v[2] = pl[o + 1];
-  v[3] = pl[o + 2];
-  v[4] = pl[o + 3];
-  v[5] = pl[o + 4];
-}
-
-DVS_HD void quad_y(const float* Y, int base, QuadY& q) {
-  float cy[6], cyy[6];
-  for (int r = 0; r < 3; ++r) {
-    load_row6(Y, base + (r - 1) * PW, q.yv[r]);
-    for (int k = 0; k < 6; ++k) {
-      float v = q.yv[r][k];
-      cy[k] = r ? cy[k] + v : v;
-      cyy[k] = r ? fmaf(v, v, cyy[k]) : v * v;
-    }
-  }
+  for (int k = tid; k < PLANE / 4; k += NT) reinterpret_cast<unsigned int*>(sm + L.sel())[k] = 0xffffffffu;   // kSelNone
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  int fl = 0;
+  const int gx = t.gx0 + cx;
   for (int j = 0; j < 4; ++j) {
-    q.sy[j] = cy[j] + cy[j + 1] + cy[j + 2];
-    q.syy[j] = cyy[j] + cyy[j + 1] + cyy[j + 2];
+    int gy = t.gy0 + r0 + j;
+    bool in = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+    bool own = in && (r0 + j) >= 1 && (r0 + j) <= TH - 2 && cx >= 1 && cx <= TW - 2;
+    fl |= (in ? 1 : 0) << j;
+    fl |= (own ? 1 : 0) << (4 + j);
   }
+  st.flags = fl;
 }
 
-DVS_HD void quad_x(const float* X, int base, const QuadY& y, QuadStats& q, float* xc) {
-  float cx[6], cxx[6], cxy[6];
-  for (int r = 0; r < 3; ++r) {
-    float xv[6];
-    load_row6(X, base + (r - 1) * PW, xv);
-    if (r == 1) { xc[0] = xv[1]; xc[1] = xv[2]; xc[2] = xv[3]; xc[3] = xv[4]; }
-    for (int k = 0; k < 6; ++k) {
-      float v = xv[k];
-      cx[k] = r ? cx[k] + v : v;
-      cxx[k] = r ? fmaf(v, v, cxx[k]) : v * v;
-      cxy[k] = r ? fmaf(v, y.yv[r][k], cxy[k]) : v * y.yv[r][k];
-    }
+// ------------------------------------------------------------------------------------------------ 3x3 sums, SSIM
+// Neighbourhood of the four pixels: rows m = 0..5 <-> R1 rows r0-1 .. r0+4, columns k = 0..2 <-> cx-1 .. cx+1.
+struct YN {
+  float v[6][3];           // target values
+  float sy[4];             // 9-sum of y
+  float ysq[4];            // sy^2
+  float ty[4];             // 9*sum(y^2) + 81*C2
+};
+struct XS {
+  float sx[4], sxx[4], sxy[4], xc[4];
+};
+// vertical 3-sums of 6 row values for the 4 pixels (two shared partial sums)
+DVS_HD void vsum4(const float* h, float* s) {
+  float u12 = h[1] + h[2], u34 = h[3] + h[4];
+  s[0] = h[0] + u12;
+  s[1] = u12 + h[3];
+  s[2] = h[2] + u34;
+  s[3] = u34 + h[5];
+}
+DVS_HD void load_yn(const float* Y, int base, YN& q) {
+  float hy[6], hyy[6];
+  for (int m = 0; m < 6; ++m) {
+    const float* row = Y + base + (m - 1) * PW;
+    float a = row[-1], b = row[0], c = row[1];
+    q.v[m][0] = a; q.v[m][1] = b; q.v[m][2] = c;
+    hy[m] = a + b + c;
+    hyy[m] = fmaf(c, c, fmaf(b, b, a * a));
   }
+  float syy[4];
+  vsum4(hy, q.sy);
+  vsum4(hyy, syy);
   for (int j = 0; j < 4; ++j) {
-    q.sx[j] = cx[j] + cx[j + 1] + cx[j + 2];
-    q.sxx[j] = cxx[j] + cxx[j + 1] + cxx[j + 2];
-    q.sxy[j] = cxy[j] + cxy[j + 1] + cxy[j + 2];
+    q.ysq[j] = q.sy[j] * q.sy[j];
+    q.ty[j] = fmaf(9.f, syy[j], kK2);
   }
 }
-
-// SSIM loss value from 9-sums; optionally the coefficient fields (a=dS/dm(x), b=dS/dm(x^2), c=dS/dm(xy)).
-template <bool COEF>
-DVS_HD float ssim_from_sums(float sx, float sxx, float sxy, float sy, float syy, float& a, float& b, float& c) {
-  const float i9 = 1.0f / 9.0f;
-  float mx = sx * i9, my = sy * i9;
-  float mxy = mx * my;
-  float mx2 = mx * mx, my2 = my * my;
-  float n1 = fmaf(2.f, mxy, kC1);
-  float n2 = fmaf(2.f, fmaf(sxy, i9, -mxy), kC2);
-  float d1 = mx2 + my2 + kC1;
-  float d2 = fmaf(sxx + syy, i9, -(mx2 + my2)) + kC2;
-  float n = n1 * n2, d = d1 * d2;
-  float rd = rcp_fast(d);
-  float raw = fmaf(-0.5f * n, rd, 0.5f);
-  float S = fminf(fmaxf(raw, 0.f), 1.f);
-  if (COEF) {
-    float live = (raw >= 0.f && raw <= 1.f) ? 1.f : 0.f;
-    float nrd = n * rd;
-    // a = -[my (n2-n1) - nrd mx (d2-d1)] / d ; b = 0.5 nrd / d2 ; c = -n1/d
-    a = -(my * (n2 - n1) - nrd * mx * (d2 - d1)) * rd * live;
-    b = 0.5f * nrd * rcp_fast(d2) * live;
-    c = -n1 * rd * live;
+DVS_HD void stats_x(const float* X, int base, const YN& y, XS& q) {
+  float hx[6], hxx[6], hxy[6];
+  for (int m = 0; m < 6; ++m) {
+    const float* row = X + base + (m - 1) * PW;
+    float a = row[-1], b = row[0], c = row[1];
+    if (m >= 1 && m <= 4) q.xc[m - 1] = b;
+    hx[m] = a + b + c;
+    hxx[m] = fmaf(c, c, fmaf(b, b, a * a));
+    hxy[m] = fmaf(c, y.v[m][2], fmaf(b, y.v[m][1], a * y.v[m][0]));
   }
-  return S;
+  vsum4(hx, q.sx);
+  vsum4(hxx, q.sxx);
+  vsum4(hxy, q.sxy);
 }
 
-// reprojection loss (ssim_w*mean_c SSIM + l1_w*mean_c |y-x|) of the own quad for image planes X[3]
-DVS_HD void quad_reproj(const float* sm, int xoff, int yoff, int base, float ssim_w3, float l1_w3, float* r) {
-  for (int j = 0; j < 4; ++j) r[j] = 0.f;
+// SSIM loss value clamp((1 - n/d)/2, 0, 1) from 9-sums.  With S* the sums, the reference's
+//   n = (2 mx my + C1)(2 sxy + C2), d = (mx^2 + my^2 + C1)(sx + sy + C2)
+// equal N1 N2 / 81^2 and D1 D2 / 81^2 of the quantities below (the factors cancel in n/d).
+struct SsimTerms {
+  float N1, N2, D1, D2, R, rd;
+};
+DVS_HD void ssim_terms(float sx, float sxx, float sxy, float sy, float ysq, float ty, SsimTerms& t) {
+  float pr = sx * sy;
+  float e = fmaf(sx, sx, ysq);
+  t.N1 = fmaf(2.f, pr, kK1);
+  t.N2 = fmaf(-2.f, pr, fmaf(18.f, sxy, kK2));
+  t.D1 = e + kK1;
+  t.D2 = fmaf(9.f, sxx, ty) - e;
+  t.rd = rcp_fast(t.D1 * t.D2);
+  t.R = (t.N1 * t.N2) * t.rd;
+}
+DVS_HD float ssim_value(float sx, float sxx, float sxy, float sy, float ysq, float ty) {
+  SsimTerms t;
+  ssim_terms(sx, sxx, sxy, sy, ysq, ty, t);
+  return sat01(fmaf(-0.5f, t.R, 0.5f));
+}
+// d S / d (sum x), d S / d (sum x^2), d S / d (sum x y) times `scale`; zero where the clamp is active
+// (torch.clamp passes the gradient at exactly 0 and 1).
+DVS_HD void ssim_coefs(float sx, float sxx, float sxy, float sy, float ysq, float ty, float scale, float& al, float& be,
+                       float& ga) {
+  SsimTerms t;
+  ssim_terms(sx, sxx, sxy, sy, ysq, ty, t);
+  float rk = (t.R >= -1.f && t.R <= 1.f) ? t.rd * scale : 0.f;
+  float w = fmaf(-(t.R * sx), t.D2 - t.D1, sy * (t.N2 - t.N1));
+  al = -w * rk;
+  be = 4.5f * (t.R * t.D1) * rk;
+  ga = -9.f * t.N1 * rk;
+}
+
+// reprojection losses ssim_w*mean_c SSIM + l1_w*mean_c |y-x| of the own pixels for all sources; X planes of
+// source i start at xoff + 3*i*PLANE.  Optionally the smoothness edge weights' |dy| sums.
+template <int NS, bool EDGES>
+DVS_HD void quad_reproj(const float* sm, int xoff, int yoff, int base, float ssim_w3, float l1_w3, float (*r)[4], float* ax,
+                        float* ay) {
+  float rs[NS][4], rl[NS][4];
+  DVS_UNROLL
+  for (int i = 0; i < NS; ++i)
+    for (int j = 0; j < 4; ++j) rs[i][j] = rl[i][j] = 0.f;
   for (int c = 0; c < 3; ++c) {
-    QuadY qy;
-    QuadStats qs;
-    float xc[4], a, b, cc;
-    quad_y(sm + yoff + c * PLANE, base, qy);
-    quad_x(sm + xoff + c * PLANE, base, qy, qs, xc);
-    for (int j = 0; j < 4; ++j) {
-      float S = ssim_from_sums<false>(qs.sx[j], qs.sxx[j], qs.sxy[j], qy.sy[j], qy.syy[j], a, b, cc);
-      r[j] = fmaf(ssim_w3, S, fmaf(l1_w3, fabsf(qy.yv[1][j + 1] - xc[j]), r[j]));
+    YN yn;
+    load_yn(sm + yoff + c * PLANE, base, yn);
+    if (EDGES)
+      for (int j = 0; j < 4; ++j) {
+        ax[j] += fabsf(yn.v[j + 1][1] - yn.v[j + 1][2]);
+        ay[j] += fabsf(yn.v[j + 1][1] - yn.v[j + 2][1]);
+      }
+    DVS_UNROLL
+    for (int i = 0; i < NS; ++i) {
+      XS xs;
+      stats_x(sm + xoff + (3 * i + c) * PLANE, base, yn, xs);
+      for (int j = 0; j < 4; ++j) {
+        rs[i][j] += ssim_value(xs.sx[j], xs.sxx[j], xs.sxy[j], yn.sy[j], yn.ysq[j], yn.ty[j]);
+        rl[i][j] += fabsf(yn.v[j + 1][1] - xs.xc[j]);
+      }
     }
   }
+  DVS_UNROLL
+  for (int i = 0; i < NS; ++i)
+    for (int j = 0; j < 4; ++j) r[i][j] = fmaf(ssim_w3, rs[i][j], l1_w3 * rl[i][j]);
 }
-
-DVS_HD void quad_coords(int tid, int& qr, int& qc) { qr = tid >> 3; qc = (tid & 7) << 2; }
 
 // ------------------------------------------------------------------------------------------------ phase 1
-// identity terms + smoothness edge weights of the own quad (scale independent).
+// identity terms + smoothness edge weights of the own pixels (scale independent).
 template <int NS>
 DVS_HD void phase_identity(const FusedParams& p, const Tile& t, float* sm, int tid, ThreadState<NS>& st) {
   SmemLayout L{NS};
-  int qr, qc;
-  quad_coords(tid, qr, qc);
-  int base = pidx(qr, qc);
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  const int base = pidx(r0, cx);
   const float sw3 = p.ssim_w * (1.f / 3.f), lw3 = p.l1_w * (1.f / 3.f);
-  if (p.auto_mask)
-    for (int i = 0; i < NS; ++i) quad_reproj(sm, L.x(i, 0), L.y(0), base, sw3, lw3, st.ident[i]);
-  int gy = t.gy0 + qr;
+  float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.auto_mask) {
+    quad_reproj<NS, true>(sm, L.x(0, 0), L.y(0), base, sw3, lw3, st.ident, ax, ay);
+  } else {
+    for (int c = 0; c < 3; ++c)
+      for (int j = 0; j < 4; ++j) {
+        int o = base + j * PW;
+        float y0 = sm[L.y(c) + o];
+        ax[j] += fabsf(y0 - sm[L.y(c) + o + 1]);
+        ay[j] += fabsf(y0 - sm[L.y(c) + o + PW]);
+      }
+    DVS_UNROLL
+    for (int i = 0; i < NS; ++i)
+      for (int j = 0; j < 4; ++j) st.ident[i][j] = 0.f;
+  }
+  const int gx = t.gx0 + cx;
   for (int j = 0; j < 4; ++j) {
-    int gx = t.gx0 + qc + j, o = base + j;
-    bool in = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-    float ax = 0.f, ay = 0.f;
-    for (int c = 0; c < 3; ++c) {
-      float y0 = sm[L.y(c) + o];
-      ax += fabsf(y0 - sm[L.y(c) + o + 1]);
-      ay += fabsf(y0 - sm[L.y(c) + o + PW]);
-    }
-    sm[L.wx() + o] = (in && gx < p.W - 1) ? exp_fast(-ax * (1.f / 3.f)) : 0.f;
-    sm[L.wy() + o] = (in && gy < p.H - 1) ? exp_fast(-ay * (1.f / 3.f)) : 0.f;
+    int gy = t.gy0 + r0 + j, o = base + j * PW;
+    bool in = (st.flags >> j) & 1;
+    sm[L.wx() + o] = (in && gx < p.W - 1) ? exp_fast(-ax[j] * (1.f / 3.f)) : 0.f;
+    sm[L.wy() + o] = (in && gy < p.H - 1) ? exp_fast(-ay[j] * (1.f / 3.f)) : 0.f;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ geometry
-struct Geo {
-  float D, ray[3], cam[3];
-};
-DVS_HD void pixel_geo(const float* c, float du, int rx, int ry, float min_disp, float range, Geo& g) {
-  float u = (float)rx, v = (float)ry;
-  g.D = rcp_fast(fmaf(du, range, min_disp));
-  for (int k = 0; k < 3; ++k) {
-    g.ray[k] = fmaf(c[kC_iK + 3 * k], u, fmaf(c[kC_iK + 3 * k + 1], v, c[kC_iK + 3 * k + 2]));
-    g.cam[k] = g.D * g.ray[k];
-  }
-}
+// Sampling position of one target pixel in source i: c = D * (A (u,v,1)) + p, pixel = c.xy / (c.z + eps),
+// border-clipped like F.grid_sample(padding_mode="border", align_corners=True).  The cell origin is clamped to
+// W-2 / H-2 so that the four taps are always in range (the weights make that exact: tx = 1 on the last column).
 struct Proj {
+  float q[3];            // A (u,v,1) = d c / d D
   float px, py, rz;      // un-clipped pixel coordinates, 1/(z+eps)
   float tx, ty;
-  int o00, o01, o10, o11;
-  float m01, m10, m11;   // tap validity (0/1): taps beyond the last row/column contribute 0
-  float livex, livey;    // 0 when the coordinate was clipped (ATen clip_coordinates_set_grad)
+  int o;                 // offset of the north-west tap inside a plane
 };
-DVS_HD void project(const float* P, const Geo& g, float eps, int H, int W, Proj& q) {
-  float c0 = fmaf(P[0], g.cam[0], fmaf(P[1], g.cam[1], fmaf(P[2], g.cam[2], P[3])));
-  float c1 = fmaf(P[4], g.cam[0], fmaf(P[5], g.cam[1], fmaf(P[6], g.cam[2], P[7])));
-  float c2 = fmaf(P[8], g.cam[0], fmaf(P[9], g.cam[1], fmaf(P[10], g.cam[2], P[11])));
-  q.rz = rcp_fast(c2 + eps);
-  q.px = c0 * q.rz;
-  q.py = c1 * q.rz;
-  float wm = (float)(W - 1), hm = (float)(H - 1);
-  q.livex = (q.px > 0.f && q.px < wm) ? 1.f : 0.f;
-  q.livey = (q.py > 0.f && q.py < hm) ? 1.f : 0.f;
-  float ix = fminf(fmaxf(q.px, 0.f), wm), iy = fminf(fmaxf(q.py, 0.f), hm);
-  int x0 = (int)ix, y0 = (int)iy;
-  q.tx = ix - (float)x0;
-  q.ty = iy - (float)y0;
-  int okx = x0 + 1 <= W - 1, oky = y0 + 1 <= H - 1;
-  int x1 = x0 + okx, y1 = y0 + oky;
-  q.o00 = y0 * W + x0; q.o01 = y0 * W + x1; q.o10 = y1 * W + x0; q.o11 = y1 * W + x1;
-  q.m01 = (float)okx; q.m10 = (float)oky; q.m11 = (float)(okx & oky);
+DVS_HD void project(const float* A, float u, float v, float D, float eps, int H, int W, Proj& r) {
+  r.q[0] = fmaf(A[0], u, fmaf(A[1], v, A[2]));
+  r.q[1] = fmaf(A[3], u, fmaf(A[4], v, A[5]));
+  r.q[2] = fmaf(A[6], u, fmaf(A[7], v, A[8]));
+  float c0 = fmaf(D, r.q[0], A[9]), c1 = fmaf(D, r.q[1], A[10]), c2 = fmaf(D, r.q[2], A[11]);
+  r.rz = rcp_fast(c2 + eps);
+  r.px = c0 * r.rz;
+  r.py = c1 * r.rz;
+  float ix = fminf(fmaxf(r.px, 0.f), (float)(W - 1)), iy = fminf(fmaxf(r.py, 0.f), (float)(H - 1));
+  int x0 = imin((int)ix, W - 2), y0 = imin((int)iy, H - 2);
+  r.tx = ix - (float)x0;
+  r.ty = iy - (float)y0;
+  r.o = y0 * W + x0;
 }
-// bilinear value (and, if SLOPE, d value / d ix, d value / d iy) of one channel plane
-template <bool SLOPE>
-DVS_HD float sample(const float* __restrict__ img, const Proj& q, float& dx, float& dy) {
-  float nw = img[q.o00], ne = img[q.o01] * q.m01, sw = img[q.o10] * q.m10, se = img[q.o11] * q.m11;
-  float wx1 = q.tx, wx0 = 1.f - q.tx, wy1 = q.ty, wy0 = 1.f - q.ty;
-  if (SLOPE) {
-    dx = ((ne - nw) * wy0 + (se - sw) * wy1) * q.livex;
-    dy = ((sw - nw) * wx0 + (se - ne) * wx1) * q.livey;
-  }
-  return nw * (wx0 * wy0) + ne * (wx1 * wy0) + sw * (wx0 * wy1) + se * (wx1 * wy1);
+DVS_HD float bilerp(const float* __restrict__ img, int W, const Proj& r) {
+  const float* a = img + r.o;
+  float nw = a[0], ne = a[1], sw = a[W], se = a[W + 1];
+  float top = fmaf(r.tx, ne - nw, nw), bot = fmaf(r.tx, se - sw, sw);
+  return fmaf(r.ty, bot - top, top);
+}
+// d value / d ix and d value / d iy of the bilinear interpolation
+DVS_HD void bilerp_slopes(const float* __restrict__ img, int W, const Proj& r, float& dx, float& dy) {
+  const float* a = img + r.o;
+  float nw = a[0], ne = a[1], sw = a[W], se = a[W + 1];
+  float dt = ne - nw, db = se - sw;
+  dx = fmaf(r.ty, db - dt, dt);
+  float top = fmaf(r.tx, dt, nw), bot = fmaf(r.tx, db, sw);
+  dy = bot - top;
+}
+
+DVS_HD float bilinear_disp(const float* __restrict__ d, int dh, int dw, float sy, float sx, int ry, int rx) {
+  int y0, y1, x0, x1;
+  float ly, lx;
+  up_taps(ry, sy, dh, y0, y1, ly);
+  up_taps(rx, sx, dw, x0, x1, lx);
+  float a = d[y0 * dw + x0], b = d[y0 * dw + x1], c = d[y1 * dw + x0], e = d[y1 * dw + x1];
+  float top = a * (1.f - lx) + b * lx;
+  float bot = c * (1.f - lx) + e * lx;
+  return top * (1.f - ly) + bot * ly;
 }
 
 // ------------------------------------------------------------------------------------------------ phase W
 // warp every source onto R2 for scale s; store up-sampled disparity.
 template <int NS>
-DVS_HD void phase_warp(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
+DVS_HD void phase_warp(const FusedParams& p, const Tile& t, float* sm, int tid, int s, const ThreadState<NS>& st) {
   SmemLayout L{NS};
   const float* c = sm + L.consts();
   const int HW = p.H * p.W;
-  const float* d = p.disp[s] + (size_t)t.b * p.dh[s] * p.dw[s];
-  for (int k = tid; k < RW2 * RH2; k += NT) {
-    int ly = k / RW2 - 1, lx = k % RW2 - 1;
-    int ry = reflect_clamp(t.gy0 + ly, p.H), rx = reflect_clamp(t.gx0 + lx, p.W);
-    int q = pidx(ly, lx);
-    float du = bilinear_disp(d, p.dh[s], p.dw[s], p.H, p.W, ry, rx);
-    sm[L.du() + q] = du;
-    Geo g;
-    pixel_geo(c, du, rx, ry, p.min_disp, p.disp_range, g);
+  const int dh = p.dh[s], dw = p.dw[s];
+  const float* d = p.disp[s] + (size_t)t.b * dh * dw;
+  const bool direct = dh == p.H && dw == p.W;
+  const float scy = (float)dh / (float)p.H, scx = (float)dw / (float)p.W;
+  DVS_UNROLL
+  for (int it = 0; it < NIT; ++it) {
+    int k = tid + it * NT;
+    if (k >= PLANE) break;
+    int rx = st.pos[it] & 0xffff, ry = st.pos[it] >> 16;
+    float du = direct ? d[ry * dw + rx] : bilinear_disp(d, dh, dw, scy, scx, ry, rx);
+    sm[L.du() + k] = du;
+    float D = rcp_fast(fmaf(du, p.disp_range, p.min_disp));
+    float u = (float)rx, v = (float)ry;
+    DVS_UNROLL
     for (int i = 0; i < NS; ++i) {
       Proj pr;
-      project(c + kC_P + 12 * i, g, p.eps, p.H, p.W, pr);
+      project(c + kC_A + 12 * i, u, v, D, p.eps, p.H, p.W, pr);
       const float* im = p.src[i] + (size_t)t.b * 3 * HW;
-      float dx, dy;
-      sm[L.x(i, 0) + q] = sample<false>(im, pr, dx, dy);
-      sm[L.x(i, 1) + q] = sample<false>(im + HW, pr, dx, dy);
-      sm[L.x(i, 2) + q] = sample<false>(im + 2 * HW, pr, dx, dy);
+      sm[L.x(i, 0) + k] = bilerp(im, p.W, pr);
+      sm[L.x(i, 1) + k] = bilerp(im + HW, p.W, pr);
+      sm[L.x(i, 2) + k] = bilerp(im + 2 * HW, p.W, pr);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ phase S
-// own quad: reprojection losses of all sources, automask + min, loss sums, smoothness (+ its gradient),
+// own pixels: reprojection losses of all sources, automask + min, loss sums, smoothness (+ its gradient),
 // selection tags, and (GRAD) the SSIM coefficient fields of the selected source into the F planes.
 template <int NS, bool GRAD>
 DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid, int s, ThreadState<NS>& st) {
   SmemLayout L{NS};
   const float* cst = sm + L.consts();
-  int qr, qc;
-  quad_coords(tid, qr, qc);
-  const int base = pidx(qr, qc);
-  const int gy = t.gy0 + qr;
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  const int base = pidx(r0, cx);
+  const int gx = t.gx0 + cx, gyb = t.gy0 + r0;
   const float sw3 = p.ssim_w * (1.f / 3.f), lw3 = p.l1_w * (1.f / 3.f);
   const int HW = p.H * p.W;
+  const int fl = st.flags;
+
+  float r[NS][4];
+  quad_reproj<NS, false>(sm, L.x(0, 0), L.y(0), base, sw3, lw3, r, nullptr, nullptr);
 
   float best[4];
   int tag[4], chan[4];
-  bool inimg[4], own[4];
   for (int j = 0; j < 4; ++j) {
-    int gx = t.gx0 + qc + j;
-    inimg[j] = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-    own[j] = inimg[j] && qr >= 1 && qr <= TH - 2 && (qc + j) >= 1 && (qc + j) <= TW - 2;
     best[j] = 3.0e38f;
     tag[j] = kSelNone;
     chan[j] = 0;
   }
   if (p.auto_mask) {
-    for (int i = 0; i < NS; ++i)
+    DVS_UNROLL
+    for (int i = 0; i < NS; i += 2)
       for (int j = 0; j < 4; ++j) {
-        float v = st.ident[i][j];
-        if (inimg[j]) {
-          int gx = t.gx0 + qc + j;
-          float nz;
-          if (p.noise[s])
-            nz = p.noise[s][((size_t)(t.b * NS + i) * p.H + gy) * p.W + gx];
-          else
-            nz = hash_normal(p.seed, p.offset, (unsigned)((t.b * p.H + gy) * p.W + gx), (unsigned)(s * kMaxN + i));
-          v = fmaf(nz, 0.00001f, v);
+        float n0 = 0.f, n1 = 0.f;
+        if ((fl >> j) & 1) {
+          int gy = gyb + j;
+          if (p.noise[s]) {
+            n0 = p.noise[s][((size_t)(t.b * NS + i) * p.H + gy) * p.W + gx];
+            if (i + 1 < NS) n1 = p.noise[s][((size_t)(t.b * NS + i + 1) * p.H + gy) * p.W + gx];
+          } else {
+            hash_normal2(p.seed, p.offset, (unsigned)((t.b * p.H + gy) * p.W + gx), (unsigned)(s * kMaxN + i), n0, n1);
+          }
         }
-        if (v < best[j]) { best[j] = v; chan[j] = i; }
+        float v0 = fmaf(n0, 0.00001f, st.ident[i][j]);
+        if (v0 < best[j]) { best[j] = v0; chan[j] = i; }
+        if (i + 1 < NS) {
+          float v1 = fmaf(n1, 0.00001f, st.ident[i + 1 < NS ? i + 1 : i][j]);
+          if (v1 < best[j]) { best[j] = v1; chan[j] = i + 1; }
+        }
       }
   }
   const int off = p.auto_mask ? NS : 0;
-  for (int i = 0; i < NS; ++i) {
-    float r[4];
-    quad_reproj(sm, L.x(i, 0), L.y(0), base, sw3, lw3, r);
+  DVS_UNROLL
+  for (int i = 0; i < NS; ++i)
     for (int j = 0; j < 4; ++j)
-      if (r[j] < best[j]) { best[j] = r[j]; chan[j] = off + i; tag[j] = i; }
-  }
+      if (r[i][j] < best[j]) { best[j] = r[i][j]; chan[j] = off + i; tag[j] = i; }
+
   // loss sums, selection output, tags
+  int tags = 0;
+  unsigned char* selp = reinterpret_cast<unsigned char*>(sm + L.sel());
   for (int j = 0; j < 4; ++j) {
-    if (!inimg[j]) tag[j] = kSelNone;
-    st.tag[j] = (unsigned char)tag[j];
-    if (own[j]) {
+    if (!((fl >> j) & 1)) tag[j] = kSelNone;
+    tags |= tag[j] << (8 * j);
+    selp[base + j * PW] = (unsigned char)tag[j];
+    if ((fl >> (4 + j)) & 1) {
       st.acc[0] += best[j];
-      if (p.sel[s]) p.sel[s][((size_t)t.b * p.H + gy) * p.W + t.gx0 + qc + j] = (unsigned char)chan[j];
+      if (p.sel[s]) p.sel[s][((size_t)t.b * p.H + gyb + j) * p.W + gx] = (unsigned char)chan[j];
     }
   }
-  unsigned char* selp = reinterpret_cast<unsigned char*>(sm + L.sel());
-  for (int j = 0; j < 4; ++j) selp[base + j] = st.tag[j];
+  st.tags = tags;
 
   // smoothness on the normalised up-sampled disparity (own pixels)
   const float inv_mu = cst[kC_invmu + s];
@@ -518,8 +615,8 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
   const float* WY = sm + L.wy();
   for (int j = 0; j < 4; ++j) {
     st.gdu[j] = 0.f;
-    if (!own[j]) continue;
-    int o = base + j;
+    if (!((fl >> (4 + j)) & 1)) continue;
+    int o = base + j * PW;
     // difference first, then normalise: a*m - b*m would be contracted into an FMA whose result is the
     // rounding error of a*m when a == b (flat, border-clamped regions of the up-sampled map) and the
     // sign() below must see an exact zero there.
@@ -536,121 +633,121 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
   }
   if (!GRAD) return;
 
-  // coefficient fields of the selected source(s) of this quad -> F planes (pre-scaled)
-  const float kF = p.ssim_w / (27.0f * (float)p.B * (float)HW);
+  // coefficient fields of the selected source(s) of these pixels -> F planes (pre-scaled)
+  const float kF = p.ssim_w / (3.0f * (float)p.B * (float)HW);
+  DVS_UNROLL
   for (int i = 0; i < NS; ++i) {
     bool any = false;
     for (int j = 0; j < 4; ++j) any = any || (tag[j] == i);
     if (!any) continue;
     for (int c = 0; c < 3; ++c) {
-      QuadY qy;
-      QuadStats qs;
-      float xc[4];
-      quad_y(sm + L.y(c), base, qy);
-      quad_x(sm + L.x(i, c), base, qy, qs, xc);
+      YN yn;
+      XS xs;
+      load_yn(sm + L.y(c), base, yn);
+      stats_x(sm + L.x(i, c), base, yn, xs);
       for (int j = 0; j < 4; ++j) {
         if (tag[j] != i) continue;
-        float a, b, cc;
-        ssim_from_sums<true>(qs.sx[j], qs.sxx[j], qs.sxy[j], qy.sy[j], qy.syy[j], a, b, cc);
-        sm[L.f(c * 3 + 0) + base + j] = a * kF;
-        sm[L.f(c * 3 + 1) + base + j] = b * kF;
-        sm[L.f(c * 3 + 2) + base + j] = cc * kF;
+        float al, be, ga;
+        ssim_coefs(xs.sx[j], xs.sxx[j], xs.sxy[j], yn.sy[j], yn.ysq[j], yn.ty[j], kF, al, be, ga);
+        int o = base + j * PW;
+        sm[L.f(c * 3 + 0) + o] = al;
+        sm[L.f(c * 3 + 1) + o] = be;
+        sm[L.f(c * 3 + 2) + o] = ga;
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ phase G
-// own quad, per source: pooled adjoint of the coefficient fields -> d loss / d warped colour -> sampling
-// coordinates -> depth / pose.  Accumulates st.gdu and st.dP.
+// own pixels, per source: pooled adjoint of the coefficient fields -> d loss / d warped colour -> sampling
+// coordinates -> depth / pose moments.  Accumulates st.gdu and st.dM.
 template <int NS>
 DVS_HD void phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, int s, ThreadState<NS>& st) {
   SmemLayout L{NS};
   const float* cst = sm + L.consts();
-  int qr, qc;
-  quad_coords(tid, qr, qc);
-  if (qr < 1 || qr > TH - 2) return;
-  const int base = pidx(qr, qc);
-  const int gy = t.gy0 + qr;
-  if (gy >= p.H) return;
+  if (!(st.flags >> 4)) return;                       // no own pixel
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  const int base = pidx(r0, cx);
+  const int gx = t.gx0 + cx, gyb = t.gy0 + r0;
   const int HW = p.H * p.W;
   const unsigned char* selp = reinterpret_cast<const unsigned char*>(sm + L.sel());
-  const float wup = (gy == 1) ? 2.f : 1.f, wdn = (gy == p.H - 2) ? 2.f : 1.f;
   const float l1k = p.l1_w / (3.0f * (float)p.B * (float)HW);
+  // reflection adjoint: the pad ring mirrors row/column 1 (and H-2 / W-2), so a pixel there appears twice in the
+  // window of the centre on the image border next to it
+  const float wl = (gx == 1) ? 2.f : 1.f, wr = (gx == p.W - 2) ? 2.f : 1.f;
+  const bool edge_rows = (gyb <= 1 && gyb + 3 >= 1) || (gyb <= p.H - 2 && gyb + 3 >= p.H - 2);
 
-  unsigned char tg[3][6];
-  for (int r = 0; r < 3; ++r)
-    for (int k = 0; k < 6; ++k) tg[r][k] = selp[base + (r - 1) * PW + k - 1];
+  unsigned char tg[6][3];
+  for (int m = 0; m < 6; ++m)
+    for (int k = 0; k < 3; ++k) tg[m][k] = selp[base + (m - 1) * PW + k - 1];
 
+  DVS_UNROLL
   for (int i = 0; i < NS; ++i) {
-    float m[3][6];
+    float mk[6][3];
     bool any = false;
-    for (int r = 0; r < 3; ++r) {
-      float wr = r == 0 ? wup : (r == 2 ? wdn : 1.f);
-      for (int k = 0; k < 6; ++k) {
-        bool hit = tg[r][k] == i;
+    for (int m = 0; m < 6; ++m)
+      for (int k = 0; k < 3; ++k) {
+        bool hit = tg[m][k] == i;
         any = any || hit;
-        m[r][k] = hit ? wr : 0.f;
+        mk[m][k] = hit ? (k == 0 ? wl : (k == 2 ? wr : 1.f)) : 0.f;
       }
-    }
     if (!any) continue;
     float G[3][4];
     for (int c = 0; c < 3; ++c) {
       float pooled[3][4];
       for (int f = 0; f < 3; ++f) {
-        const float* F = sm + L.f(c * 3 + f);
-        float cs[6];
-        for (int r = 0; r < 3; ++r) {
-          float v[6];
-          load_row6(F, base + (r - 1) * PW, v);
-          for (int k = 0; k < 6; ++k) cs[k] = r ? fmaf(v[k], m[r][k], cs[k]) : v[k] * m[r][k];
+        const float* F = sm + L.f(c * 3 + f) + base;
+        float h[6];
+        for (int m = 0; m < 6; ++m) {
+          const float* row = F + (m - 1) * PW;
+          h[m] = fmaf(row[1], mk[m][2], fmaf(row[0], mk[m][1], row[-1] * mk[m][0]));
         }
-        for (int j = 0; j < 4; ++j) {
-          int gx = t.gx0 + qc + j;
-          float v = cs[j] + cs[j + 1] + cs[j + 2];
-          if (gx == 1) v += cs[j];
-          if (gx == p.W - 2) v += cs[j + 2];
-          pooled[f][j] = v;
-        }
+        vsum4(h, pooled[f]);
+        if (edge_rows)
+          for (int j = 0; j < 4; ++j) {
+            if (gyb + j == 1) pooled[f][j] += h[j];
+            if (gyb + j == p.H - 2) pooled[f][j] += h[j + 2];
+          }
       }
       for (int j = 0; j < 4; ++j) {
-        float x = sm[L.x(i, c) + base + j], y = sm[L.y(c) + base + j];
+        int o = base + j * PW;
+        float x = sm[L.x(i, c) + o], y = sm[L.y(c) + o];
         float g = fmaf(2.f * x, pooled[1][j], fmaf(y, pooled[2][j], pooled[0][j]));
-        if (tg[1][j + 1] == i) g -= l1k * sgn(y - x);
+        if (tg[j + 1][1] == i) g -= l1k * sgn(y - x);
         G[c][j] = g;
       }
     }
     // chain through the bilinear gather and the projection (taps re-read; they are L1/L2 resident)
-    const float* P = cst + kC_P + 12 * i;
+    const float* A = cst + kC_A + 12 * i;
     const float* im = p.src[i] + (size_t)t.b * 3 * HW;
+    const float u = (float)gx;
     for (int j = 0; j < 4; ++j) {
-      int lx = qc + j, gx = t.gx0 + lx;
-      if (lx < 1 || lx > TW - 2 || gx >= p.W) continue;
-      Geo g;
-      pixel_geo(cst, sm[L.du() + base + j], gx, gy, p.min_disp, p.disp_range, g);
+      if (!((st.flags >> (4 + j)) & 1)) continue;
+      if (G[0][j] == 0.f && G[1][j] == 0.f && G[2][j] == 0.f) continue;
+      const float v = (float)(gyb + j);
+      const float D = rcp_fast(fmaf(sm[L.du() + base + j * PW], p.disp_range, p.min_disp));
       Proj pr;
-      project(P, g, p.eps, p.H, p.W, pr);
+      project(A, u, v, D, p.eps, p.H, p.W, pr);
       float gix = 0.f, giy = 0.f;
       for (int c = 0; c < 3; ++c) {
         float dx, dy;
-        sample<true>(im + c * HW, pr, dx, dy);
+        bilerp_slopes(im + c * HW, p.W, pr, dx, dy);
         gix = fmaf(G[c][j], dx, gix);
         giy = fmaf(G[c][j], dy, giy);
       }
-      float gc[3];
-      gc[0] = gix * pr.rz;
-      gc[1] = giy * pr.rz;
-      gc[2] = -(gix * pr.px + giy * pr.py) * pr.rz;
-      float gD = 0.f;
-      for (int k = 0; k < 3; ++k) {
-        float gcam = fmaf(gc[0], P[k], fmaf(gc[1], P[4 + k], gc[2] * P[8 + k]));
-        gD = fmaf(gcam, g.ray[k], gD);
-      }
-      st.gdu[j] = fmaf(gD * (-p.disp_range), g.D * g.D, st.gdu[j]);
-      for (int r = 0; r < 3; ++r) {
-        for (int k = 0; k < 3; ++k) st.dP[i][r * 4 + k] = fmaf(gc[r], g.cam[k], st.dP[i][r * 4 + k]);
-        st.dP[i][r * 4 + 3] += gc[r];
-      }
+      // ATen clip_coordinates_set_grad: zero gradient when the coordinate was clipped (border included)
+      if (!(pr.px > 0.f && pr.px < (float)(p.W - 1))) gix = 0.f;
+      if (!(pr.py > 0.f && pr.py < (float)(p.H - 1))) giy = 0.f;
+      float gc0 = gix * pr.rz, gc1 = giy * pr.rz;
+      float gc2 = -(gc0 * pr.px + gc1 * pr.py);
+      float gD = fmaf(gc0, pr.q[0], fmaf(gc1, pr.q[1], gc2 * pr.q[2]));
+      st.gdu[j] = fmaf(gD * (-p.disp_range), D * D, st.gdu[j]);
+      float w0 = gc0 * D, w1 = gc1 * D, w2 = gc2 * D;
+      float* M = st.dM[i];
+      M[0] = fmaf(w0, u, M[0]); M[1] = fmaf(w0, v, M[1]); M[2] += w0; M[3] += gc0;
+      M[4] = fmaf(w1, u, M[4]); M[5] = fmaf(w1, v, M[5]); M[6] += w1; M[7] += gc1;
+      M[8] = fmaf(w2, u, M[8]); M[9] = fmaf(w2, v, M[9]); M[10] += w2; M[11] += gc2;
     }
   }
 }
@@ -659,28 +756,18 @@ DVS_HD void phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, 
 // Scale whose disparity map is full resolution: direct store of the own pixels.
 template <int NS>
 DVS_HD void store_gdu_direct(const FusedParams& p, const Tile& t, int tid, int s, const ThreadState<NS>& st) {
-  int qr, qc;
-  quad_coords(tid, qr, qc);
-  int gy = t.gy0 + qr;
-  if (qr < 1 || qr > TH - 2 || gy >= p.H) return;
-  for (int j = 0; j < 4; ++j) {
-    int lx = qc + j, gx = t.gx0 + lx;
-    if (lx < 1 || lx > TW - 2 || gx >= p.W) continue;
-    p.gdisp[s][((size_t)t.b * p.H + gy) * p.W + gx] = st.gdu[j];
-  }
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  for (int j = 0; j < 4; ++j)
+    if ((st.flags >> (4 + j)) & 1) p.gdisp[s][((size_t)t.b * p.H + t.gy0 + r0 + j) * p.W + t.gx0 + cx] = st.gdu[j];
 }
 // Otherwise: put the own-pixel gradients in the (now dead) DU plane, zero elsewhere ...
 template <int NS>
 DVS_HD void stage_gdu(const FusedParams& p, const Tile& t, float* sm, int tid, const ThreadState<NS>& st) {
   SmemLayout L{NS};
-  int qr, qc;
-  quad_coords(tid, qr, qc);
-  int gy = t.gy0 + qr;
-  for (int j = 0; j < 4; ++j) {
-    int lx = qc + j, gx = t.gx0 + lx;
-    bool own = qr >= 1 && qr <= TH - 2 && lx >= 1 && lx <= TW - 2 && gy < p.H && gx < p.W;
-    sm[L.du() + pidx(qr, lx)] = own ? st.gdu[j] : 0.f;
-  }
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  for (int j = 0; j < 4; ++j) sm[L.du() + pidx(r0 + j, cx)] = ((st.flags >> (4 + j)) & 1) ? st.gdu[j] : 0.f;
 }
 // ... then the adjoint of the bilinear up-sample restricted to this tile, separably:
 // (a) rows of R0 x coarse columns into tbuf, (b) coarse rows x coarse columns -> atomic add to global.
@@ -701,15 +788,6 @@ DVS_HD CoarseBox coarse_box(const FusedParams& p, const Tile& t, int s) {
   return c;
 }
 constexpr int kTbufCols = 36;   // >= max coarse columns touched by 30 fine columns (+ slack), rows = 30
-DVS_HD float tap_weight(int fine, float scale, int in, int coarse) {
-  int a, b;
-  float l;
-  up_taps(fine, scale, in, a, b, l);
-  float w = 0.f;
-  if (a == coarse) w += 1.f - l;
-  if (b == coarse) w += l;
-  return w;
-}
 template <int NS>
 DVS_HD void adjoint_rows(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   SmemLayout L{NS};
@@ -719,13 +797,11 @@ DVS_HD void adjoint_rows(const FusedParams& p, const Tile& t, float* sm, int tid
   float inv = (float)p.W / (float)p.dw[s];
   for (int k = tid; k < nfy * ncj; k += NT) {
     int y = k / ncj, J = cb.j0 + k % ncj;
-    // fine columns that can touch coarse column J (conservative superset, exact test inside)
+    // fine columns that can touch coarse column J (conservative superset, exact weight inside)
     int xa = imax((int)(((float)J - 1.f) * inv) - 2, cb.fx0), xb = imin((int)(((float)J + 1.5f) * inv) + 2, cb.fx1);
     float acc = 0.f;
-    for (int x = xa; x <= xb; ++x) {
-      float w = tap_weight(x, scale, p.dw[s], J);
-      acc = fmaf(w, sm[L.du() + pidx(cb.fy0 + y - t.gy0, x - t.gx0)], acc);
-    }
+    const float* row = sm + L.du() + pidx(cb.fy0 + y - t.gy0, -t.gx0);
+    for (int x = xa; x <= xb; ++x) acc = fmaf(tap_weight(x, scale, p.dw[s], J), row[x], acc);
     sm[L.tbuf() + y * kTbufCols + (J - cb.j0)] = acc;
   }
 }
@@ -747,10 +823,8 @@ DVS_HD void adjoint_cols(const FusedParams& p, const Tile& t, float* sm, int tid
     int I = cb.i0 + k / ncj, Jl = k % ncj;
     int ya = imax((int)(((float)I - 1.f) * inv) - 2, cb.fy0), yb = imin((int)(((float)I + 1.5f) * inv) + 2, cb.fy1);
     float acc = 0.f;
-    for (int y = ya; y <= yb; ++y) {
-      float w = tap_weight(y, scale, p.dh[s], I);
-      acc = fmaf(w, sm[L.tbuf() + (y - cb.fy0) * kTbufCols + Jl], acc);
-    }
+    for (int y = ya; y <= yb; ++y)
+      acc = fmaf(tap_weight(y, scale, p.dh[s], I), sm[L.tbuf() + (y - cb.fy0) * kTbufCols + Jl], acc);
     atomic_add_f32(p.gdisp[s] + ((size_t)t.b * p.dh[s] + I) * p.dw[s] + cb.j0 + Jl, acc);
   }
 }
@@ -764,8 +838,9 @@ DVS_HD void reduce_write(const FusedParams& p, float* sm, int tid, const ThreadS
   constexpr int nv = 3 + 12 * NS;
   float* sc = sm + L.scratch() + tid * nv;
   sc[0] = st.acc[0]; sc[1] = st.acc[1]; sc[2] = st.acc[2];
+  DVS_UNROLL
   for (int i = 0; i < NS; ++i)
-    for (int k = 0; k < 12; ++k) sc[3 + 12 * i + k] = st.dP[i][k];
+    for (int k = 0; k < 12; ++k) sc[3 + 12 * i + k] = st.dM[i][k];
 }
 template <int NS>
 DVS_HD void reduce_stage1(const FusedParams& p, float* sm, int tid) {
@@ -792,8 +867,26 @@ DVS_HD void reduce_stage2(const FusedParams& p, const Tile& t, float* sm, int ti
 template <int NS>
 DVS_HD void reset_scale_state(ThreadState<NS>& st) {
   st.acc[0] = st.acc[1] = st.acc[2] = 0.f;
+  DVS_UNROLL
   for (int i = 0; i < NS; ++i)
-    for (int k = 0; k < 12; ++k) st.dP[i][k] = 0.f;
+    for (int k = 0; k < 12; ++k) st.dM[i][k] = 0.f;
+}
+
+// pose moments of one (image, scale, source) -> d loss / d T (4x4 row-major, last row zero):
+//   d/dP[r][k<3] = sum_j inv_K[k][j] M[r][j],  d/dP[r][3] = M[r][3],  d/dT = K[:3,:]^T d/dP
+DVS_HD void moments_to_dT(const float* M, const float* Kb, const float* iK, float* dT) {
+  float dP[12];
+  for (int r = 0; r < 3; ++r) {
+    for (int k = 0; k < 3; ++k)
+      dP[r * 4 + k] = fmaf(iK[k * 4 + 0], M[r * 4 + 0], fmaf(iK[k * 4 + 1], M[r * 4 + 1], iK[k * 4 + 2] * M[r * 4 + 2]));
+    dP[r * 4 + 3] = M[r * 4 + 3];
+  }
+  for (int m = 0; m < 4; ++m)
+    for (int k = 0; k < 4; ++k) {
+      float a = 0.f;
+      for (int j = 0; j < 3; ++j) a = fmaf(Kb[j * 4 + m], dP[j * 4 + k], a);
+      dT[m * 4 + k] = a;
+    }
 }
 
 }  // namespace dvs

@@ -24,10 +24,10 @@ void run_block(const FusedParams& p, int blk, std::vector<float>& smv) {
   float* sm = smv.data();
   Tile t = make_tile(p, blk);
   std::vector<ThreadState<NS>> st(NT);
-  for (int tid = 0; tid < NT; ++tid) { phase_consts<NS>(p, t, sm, tid); phase_load<NS>(p, t, sm, tid); }
+  for (int tid = 0; tid < NT; ++tid) { phase_consts<NS>(p, t, sm, tid); phase_load<NS>(p, t, sm, tid, st[tid]); }
   for (int tid = 0; tid < NT; ++tid) phase_identity<NS>(p, t, sm, tid, st[tid]);
   for (int s = 0; s < p.S; ++s) {
-    for (int tid = 0; tid < NT; ++tid) { reset_scale_state<NS>(st[tid]); phase_warp<NS>(p, t, sm, tid, s); }
+    for (int tid = 0; tid < NT; ++tid) { reset_scale_state<NS>(st[tid]); phase_warp<NS>(p, t, sm, tid, s, st[tid]); }
     for (int tid = 0; tid < NT; ++tid) phase_stats<NS, GRAD>(p, t, sm, tid, s, st[tid]);
     const bool direct = (p.dh[s] == p.H && p.dw[s] == p.W);
     if (GRAD) {
@@ -130,12 +130,8 @@ extern "C" int emu_photometric_forward(const DvsShape* sh, const DvsParams* pr, 
       ph += res[0]; sx += res[1]; sy += res[2];
       if (!want_grad) continue;
       for (int i = 0; i < sh->N; ++i)
-        for (int m = 0; m < 4; ++m)
-          for (int k = 0; k < 4; ++k) {
-            float a = 0.f;
-            for (int j = 0; j < 3; ++j) a += K[b * 16 + j * 4 + m] * res[3 + 12 * i + j * 4 + k];
-            ugrad_T[(((size_t)s * sh->N + i) * sh->B + b) * 16 + m * 4 + k] = a;
-          }
+        moments_to_dT(res.data() + 3 + 12 * i, K + b * 16, inv_K + b * 16,
+                      ugrad_T + (((size_t)s * sh->N + i) * sh->B + b) * 16);
       float mu = 0.f;
       for (int k = 0; k < kMeanBlocks; ++k) mu += mean_part[(s * sh->B + b) * kMeanBlocks + k];
       mu /= (float)sh->H * (float)sh->W;
