@@ -31,9 +31,11 @@
 #if defined(__CUDACC__)
 #define DVS_HD __host__ __device__ __forceinline__
 #define DVS_UNROLL _Pragma("unroll")
+#define DVS_NOUNROLL _Pragma("unroll 1")
 #else
 #define DVS_HD inline
 #define DVS_UNROLL
+#define DVS_NOUNROLL
 #endif
 
 namespace dvs {
@@ -172,7 +174,7 @@ DVS_HD void hash_normal2(unsigned long long seed, unsigned long long offset, uns
 }
 
 // ------------------------------------------------------------------------------------------------ shared memory
-// planes: Y[3] | X[3N] | F[9] | DU | WX | WY | SEL(bytes, PLANE of them) | consts
+// planes: Y[3] | X[3N] | F[9] | DU | WX | WY | POS (ints) | SEL(bytes, PLANE of them) | consts
 struct SmemLayout {
   int N;
   DVS_HD int y(int c) const { return c * PLANE; }
@@ -181,7 +183,8 @@ struct SmemLayout {
   DVS_HD int du() const { return (12 + 3 * N) * PLANE; }
   DVS_HD int wx() const { return (13 + 3 * N) * PLANE; }
   DVS_HD int wy() const { return (14 + 3 * N) * PLANE; }
-  DVS_HD int sel() const { return (15 + 3 * N) * PLANE; }            // PLANE bytes = PLANE/4 floats
+  DVS_HD int pos() const { return (15 + 3 * N) * PLANE; }            // (ry << 16) | rx of every R2 pixel
+  DVS_HD int sel() const { return (16 + 3 * N) * PLANE; }            // PLANE bytes = PLANE/4 floats
   DVS_HD int consts() const { return sel() + PLANE / 4; }
   DVS_HD int total() const { return consts() + 8 + 12 * kMaxN; }
   // scratch for block reductions / up-sample adjoint: aliases X (and the head of F) once those are dead
@@ -195,7 +198,6 @@ constexpr int kC_invmu = 0, kC_A = 8;
 template <int NS>
 struct ThreadState {
   float ident[NS][4];      // identity reprojection loss of the own pixels (scale independent)
-  int pos[NIT];            // (ry << 16) | rx : reflected image coordinates of the R2 pixels this thread loads / warps
   int flags;               // bit j: pixel j inside the image; bit 4+j: pixel j belongs to R0 (own)
   float acc[3];            // photometric sum, smooth-x sum, smooth-y sum of the current scale
   float dM[NS][12];        // pose-gradient moments of the current scale
@@ -266,14 +268,12 @@ template <int NS>
 DVS_HD void phase_load(const FusedParams& p, const Tile& t, float* sm, int tid, ThreadState<NS>& st) {
   SmemLayout L{NS};
   const int HW = p.H * p.W;
-  DVS_UNROLL
-  for (int it = 0; it < NIT; ++it) {
-    int k = tid + it * NT;
-    st.pos[it] = 0;
-    if (k >= PLANE) continue;
+  int* posp = reinterpret_cast<int*>(sm + L.pos());
+  DVS_NOUNROLL
+  for (int k = tid; k < PLANE; k += NT) {
     int ly = k / PW - 1, lx = k % PW - 1;
     int gy = reflect_clamp(t.gy0 + ly, p.H), gx = reflect_clamp(t.gx0 + lx, p.W);
-    st.pos[it] = (gy << 16) | gx;
+    posp[k] = (gy << 16) | gx;           // reflected image coordinates, re-used by the warp phase of every scale
     int o = gy * p.W + gx;
     const float* tg = p.target + (size_t)t.b * 3 * HW + o;
     sm[L.y(0) + k] = tg[0];
@@ -378,9 +378,9 @@ DVS_HD float ssim_value(float sx, float sxx, float sxy, float sy, float ysq, flo
   return sat01(fmaf(-0.5f, t.R, 0.5f));
 }
 // d S / d (sum x), d S / d (sum x^2), d S / d (sum x y) times `scale`; zero where the clamp is active
-// (torch.clamp passes the gradient at exactly 0 and 1).
-DVS_HD void ssim_coefs(float sx, float sxx, float sxy, float sy, float ysq, float ty, float scale, float& al, float& be,
-                       float& ga) {
+// (torch.clamp passes the gradient at exactly 0 and 1).  Returns the loss value.
+DVS_HD float ssim_coefs(float sx, float sxx, float sxy, float sy, float ysq, float ty, float scale, float& al, float& be,
+                        float& ga) {
   SsimTerms t;
   ssim_terms(sx, sxx, sxy, sy, ysq, ty, t);
   float rk = (t.R >= -1.f && t.R <= 1.f) ? t.rd * scale : 0.f;
@@ -388,6 +388,7 @@ DVS_HD void ssim_coefs(float sx, float sxx, float sxy, float sy, float ysq, floa
   al = -w * rk;
   be = 4.5f * (t.R * t.D1) * rk;
   ga = -9.f * t.N1 * rk;
+  return sat01(fmaf(-0.5f, t.R, 0.5f));
 }
 
 // reprojection losses ssim_w*mean_c SSIM + l1_w*mean_c |y-x| of the own pixels for all sources; X planes of
@@ -414,6 +415,44 @@ DVS_HD void quad_reproj(const float* sm, int xoff, int yoff, int base, float ssi
       for (int j = 0; j < 4; ++j) {
         rs[i][j] += ssim_value(xs.sx[j], xs.sxx[j], xs.sxy[j], yn.sy[j], yn.ysq[j], yn.ty[j]);
         rl[i][j] += fabsf(yn.v[j + 1][1] - xs.xc[j]);
+      }
+    }
+  }
+  DVS_UNROLL
+  for (int i = 0; i < NS; ++i)
+    for (int j = 0; j < 4; ++j) r[i][j] = fmaf(ssim_w3, rs[i][j], l1_w3 * rl[i][j]);
+}
+
+// Same, and in the same pass the SSIM coefficient fields (NS <= 2): the fields of every source but the last go
+// straight to the F planes, those of the last source are held in registers until the selection is known
+// (`hold[c][f][j]`); the caller then overwrites F where the last source won.  With two equally good sources the
+// per-pixel selection is salt-and-pepper, so nearly every thread needs both anyway and a second statistics pass
+// for "the selected source only" would cost a full pass.
+template <int NS>
+DVS_HD void quad_reproj_coefs(float* sm, int xoff, int yoff, int foff, int base, float ssim_w3, float l1_w3, float kF,
+                              float (*r)[4], float (*hold)[3][4]) {
+  float rs[NS][4], rl[NS][4];
+  DVS_UNROLL
+  for (int i = 0; i < NS; ++i)
+    for (int j = 0; j < 4; ++j) rs[i][j] = rl[i][j] = 0.f;
+  DVS_UNROLL
+  for (int c = 0; c < 3; ++c) {
+    YN yn;
+    load_yn(sm + yoff + c * PLANE, base, yn);
+    DVS_UNROLL
+    for (int i = 0; i < NS; ++i) {
+      XS xs;
+      stats_x(sm + xoff + (3 * i + c) * PLANE, base, yn, xs);
+      for (int j = 0; j < 4; ++j) {
+        float al, be, ga;
+        rs[i][j] += ssim_coefs(xs.sx[j], xs.sxx[j], xs.sxy[j], yn.sy[j], yn.ysq[j], yn.ty[j], kF, al, be, ga);
+        rl[i][j] += fabsf(yn.v[j + 1][1] - xs.xc[j]);
+        if (i == NS - 1) {
+          hold[c][0][j] = al; hold[c][1][j] = be; hold[c][2][j] = ga;
+        } else {
+          int o = foff + (c * 3) * PLANE + base + j * PW;
+          sm[o] = al; sm[o + PLANE] = be; sm[o + 2 * PLANE] = ga;
+        }
       }
     }
   }
@@ -517,11 +556,11 @@ DVS_HD void phase_warp(const FusedParams& p, const Tile& t, float* sm, int tid, 
   const float* d = p.disp[s] + (size_t)t.b * dh * dw;
   const bool direct = dh == p.H && dw == p.W;
   const float scy = (float)dh / (float)p.H, scx = (float)dw / (float)p.W;
-  DVS_UNROLL
-  for (int it = 0; it < NIT; ++it) {
-    int k = tid + it * NT;
-    if (k >= PLANE) break;
-    int rx = st.pos[it] & 0xffff, ry = st.pos[it] >> 16;
+  const int* posp = reinterpret_cast<const int*>(sm + L.pos());
+  DVS_NOUNROLL
+  for (int k = tid; k < PLANE; k += NT) {
+    int pk = posp[k];
+    int rx = pk & 0xffff, ry = pk >> 16;
     float du = direct ? d[ry * dw + rx] : bilinear_disp(d, dh, dw, scy, scx, ry, rx);
     sm[L.du() + k] = du;
     float D = rcp_fast(fmaf(du, p.disp_range, p.min_disp));
@@ -553,8 +592,12 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
   const int HW = p.H * p.W;
   const int fl = st.flags;
 
+  constexpr bool kSinglePass = GRAD && NS <= 2;
+  const float kF = p.ssim_w / (3.0f * (float)p.B * (float)HW);
   float r[NS][4];
-  quad_reproj<NS, false>(sm, L.x(0, 0), L.y(0), base, sw3, lw3, r, nullptr, nullptr);
+  float hold[3][3][4];
+  if (kSinglePass) quad_reproj_coefs<NS>(sm, L.x(0, 0), L.y(0), L.f(0), base, sw3, lw3, kF, r, hold);
+  else quad_reproj<NS, false>(sm, L.x(0, 0), L.y(0), base, sw3, lw3, r, nullptr, nullptr);
 
   float best[4];
   int tag[4], chan[4];
@@ -633,8 +676,17 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
   }
   if (!GRAD) return;
 
-  // coefficient fields of the selected source(s) of these pixels -> F planes (pre-scaled)
-  const float kF = p.ssim_w / (3.0f * (float)p.B * (float)HW);
+  if (kSinglePass) {
+    // F already holds the fields of source 0 (N == 2); the last source's go in where it was selected
+    for (int j = 0; j < 4; ++j) {
+      if (tag[j] != NS - 1) continue;
+      int o = L.f(0) + base + j * PW;
+      for (int c = 0; c < 3; ++c)
+        for (int f = 0; f < 3; ++f) sm[o + (c * 3 + f) * PLANE] = hold[c][f][j];
+    }
+    return;
+  }
+  // more than two sources: coefficient fields of the selected source(s) of these pixels -> F planes (second pass)
   DVS_UNROLL
   for (int i = 0; i < NS; ++i) {
     bool any = false;
@@ -661,6 +713,11 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
 // ------------------------------------------------------------------------------------------------ phase G
 // own pixels, per source: pooled adjoint of the coefficient fields -> d loss / d warped colour -> sampling
 // coordinates -> depth / pose moments.  Accumulates st.gdu and st.dM.
+DVS_HD float pick4(const float* a, int j) { return j == 0 ? a[0] : (j == 1 ? a[1] : (j == 2 ? a[2] : a[3])); }
+
+// The loops over sources and over the four pixels are deliberately NOT unrolled: the kernel is sensitive to its
+// instruction footprint (the per-scale loop must stay resident in the instruction cache: at 140 KB of SASS a third
+// of all stall samples were "no instruction").  Per-pixel values are picked with selects instead of indexing.
 template <int NS>
 DVS_HD void phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, int s, ThreadState<NS>& st) {
   SmemLayout L{NS};
@@ -677,12 +734,13 @@ DVS_HD void phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, 
   // window of the centre on the image border next to it
   const float wl = (gx == 1) ? 2.f : 1.f, wr = (gx == p.W - 2) ? 2.f : 1.f;
   const bool edge_rows = (gyb <= 1 && gyb + 3 >= 1) || (gyb <= p.H - 2 && gyb + 3 >= p.H - 2);
+  const float u = (float)gx;
 
-  unsigned char tg[6][3];
+  int tg[6][3];
   for (int m = 0; m < 6; ++m)
     for (int k = 0; k < 3; ++k) tg[m][k] = selp[base + (m - 1) * PW + k - 1];
 
-  DVS_UNROLL
+  DVS_NOUNROLL
   for (int i = 0; i < NS; ++i) {
     float mk[6][3];
     bool any = false;
@@ -694,8 +752,10 @@ DVS_HD void phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, 
       }
     if (!any) continue;
     float G[3][4];
+    DVS_UNROLL
     for (int c = 0; c < 3; ++c) {
       float pooled[3][4];
+      DVS_UNROLL
       for (int f = 0; f < 3; ++f) {
         const float* F = sm + L.f(c * 3 + f) + base;
         float h[6];
@@ -710,9 +770,10 @@ DVS_HD void phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, 
             if (gyb + j == p.H - 2) pooled[f][j] += h[j + 2];
           }
       }
+      const float* X = sm + L.x(0, c) + i * 3 * PLANE + base;
+      const float* Y = sm + L.y(c) + base;
       for (int j = 0; j < 4; ++j) {
-        int o = base + j * PW;
-        float x = sm[L.x(i, c) + o], y = sm[L.y(c) + o];
+        float x = X[j * PW], y = Y[j * PW];
         float g = fmaf(2.f * x, pooled[1][j], fmaf(y, pooled[2][j], pooled[0][j]));
         if (tg[j + 1][1] == i) g -= l1k * sgn(y - x);
         G[c][j] = g;
@@ -721,34 +782,43 @@ DVS_HD void phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, 
     // chain through the bilinear gather and the projection (taps re-read; they are L1/L2 resident)
     const float* A = cst + kC_A + 12 * i;
     const float* im = p.src[i] + (size_t)t.b * 3 * HW;
-    const float u = (float)gx;
+    float M[12];
+    for (int k = 0; k < 12; ++k) M[k] = 0.f;
+    float ga[4] = {0.f, 0.f, 0.f, 0.f};
+    DVS_NOUNROLL
     for (int j = 0; j < 4; ++j) {
+      float g0 = pick4(G[0], j), g1 = pick4(G[1], j), g2 = pick4(G[2], j);
       if (!((st.flags >> (4 + j)) & 1)) continue;
-      if (G[0][j] == 0.f && G[1][j] == 0.f && G[2][j] == 0.f) continue;
+      if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
       const float v = (float)(gyb + j);
       const float D = rcp_fast(fmaf(sm[L.du() + base + j * PW], p.disp_range, p.min_disp));
       Proj pr;
       project(A, u, v, D, p.eps, p.H, p.W, pr);
-      float gix = 0.f, giy = 0.f;
-      for (int c = 0; c < 3; ++c) {
-        float dx, dy;
-        bilerp_slopes(im + c * HW, p.W, pr, dx, dy);
-        gix = fmaf(G[c][j], dx, gix);
-        giy = fmaf(G[c][j], dy, giy);
-      }
+      float dx, dy, gix, giy;
+      bilerp_slopes(im, p.W, pr, dx, dy);
+      gix = g0 * dx; giy = g0 * dy;
+      bilerp_slopes(im + HW, p.W, pr, dx, dy);
+      gix = fmaf(g1, dx, gix); giy = fmaf(g1, dy, giy);
+      bilerp_slopes(im + 2 * HW, p.W, pr, dx, dy);
+      gix = fmaf(g2, dx, gix); giy = fmaf(g2, dy, giy);
       // ATen clip_coordinates_set_grad: zero gradient when the coordinate was clipped (border included)
       if (!(pr.px > 0.f && pr.px < (float)(p.W - 1))) gix = 0.f;
       if (!(pr.py > 0.f && pr.py < (float)(p.H - 1))) giy = 0.f;
       float gc0 = gix * pr.rz, gc1 = giy * pr.rz;
       float gc2 = -(gc0 * pr.px + gc1 * pr.py);
       float gD = fmaf(gc0, pr.q[0], fmaf(gc1, pr.q[1], gc2 * pr.q[2]));
-      st.gdu[j] = fmaf(gD * (-p.disp_range), D * D, st.gdu[j]);
+      float gd = gD * (-p.disp_range) * (D * D);
+      ga[0] += j == 0 ? gd : 0.f; ga[1] += j == 1 ? gd : 0.f; ga[2] += j == 2 ? gd : 0.f; ga[3] += j == 3 ? gd : 0.f;
       float w0 = gc0 * D, w1 = gc1 * D, w2 = gc2 * D;
-      float* M = st.dM[i];
       M[0] = fmaf(w0, u, M[0]); M[1] = fmaf(w0, v, M[1]); M[2] += w0; M[3] += gc0;
       M[4] = fmaf(w1, u, M[4]); M[5] = fmaf(w1, v, M[5]); M[6] += w1; M[7] += gc1;
       M[8] = fmaf(w2, u, M[8]); M[9] = fmaf(w2, v, M[9]); M[10] += w2; M[11] += gc2;
     }
+    for (int j = 0; j < 4; ++j) st.gdu[j] += ga[j];
+    DVS_UNROLL
+    for (int ii = 0; ii < NS; ++ii)
+      if (ii == i)
+        for (int k = 0; k < 12; ++k) st.dM[ii][k] += M[k];
   }
 }
 
@@ -787,6 +857,19 @@ DVS_HD CoarseBox coarse_box(const FusedParams& p, const Tile& t, int s) {
   up_taps(c.fx1, (float)p.dw[s] / (float)p.W, p.dw[s], a, b, l); c.j1 = b;
   return c;
 }
+// Fine indices whose up-sampling taps can include coarse index J: for an integer ratio f = out/in the hat function
+// around J covers [J f - f/2, J f + 3f/2 - 1] (one spare element on each side for odd f; the border clamps only
+// shrink it); otherwise a generous float bound.
+DVS_HD void fine_range(int J, int out, int in, float inv, int& lo, int& hi) {
+  if (out % in == 0) {
+    int f = out / in;
+    lo = J * f - f / 2 - 1;
+    hi = J * f + (3 * f) / 2;
+  } else {
+    lo = (int)(((float)J - 1.f) * inv) - 2;
+    hi = (int)(((float)J + 1.5f) * inv) + 2;
+  }
+}
 constexpr int kTbufCols = 36;   // >= max coarse columns touched by 30 fine columns (+ slack), rows = 30
 template <int NS>
 DVS_HD void adjoint_rows(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
@@ -797,8 +880,10 @@ DVS_HD void adjoint_rows(const FusedParams& p, const Tile& t, float* sm, int tid
   float inv = (float)p.W / (float)p.dw[s];
   for (int k = tid; k < nfy * ncj; k += NT) {
     int y = k / ncj, J = cb.j0 + k % ncj;
-    // fine columns that can touch coarse column J (conservative superset, exact weight inside)
-    int xa = imax((int)(((float)J - 1.f) * inv) - 2, cb.fx0), xb = imin((int)(((float)J + 1.5f) * inv) + 2, cb.fx1);
+    // fine columns that can touch coarse column J (superset, exact weight inside)
+    int xa, xb;
+    fine_range(J, p.W, p.dw[s], inv, xa, xb);
+    xa = imax(xa, cb.fx0); xb = imin(xb, cb.fx1);
     float acc = 0.f;
     const float* row = sm + L.du() + pidx(cb.fy0 + y - t.gy0, -t.gx0);
     for (int x = xa; x <= xb; ++x) acc = fmaf(tap_weight(x, scale, p.dw[s], J), row[x], acc);
@@ -821,7 +906,9 @@ DVS_HD void adjoint_cols(const FusedParams& p, const Tile& t, float* sm, int tid
   float inv = (float)p.H / (float)p.dh[s];
   for (int k = tid; k < nci * ncj; k += NT) {
     int I = cb.i0 + k / ncj, Jl = k % ncj;
-    int ya = imax((int)(((float)I - 1.f) * inv) - 2, cb.fy0), yb = imin((int)(((float)I + 1.5f) * inv) + 2, cb.fy1);
+    int ya, yb;
+    fine_range(I, p.H, p.dh[s], inv, ya, yb);
+    ya = imax(ya, cb.fy0); yb = imin(yb, cb.fy1);
     float acc = 0.f;
     for (int y = ya; y <= yb; ++y)
       acc = fmaf(tap_weight(y, scale, p.dh[s], I), sm[L.tbuf() + (y - cb.fy0) * kTbufCols + Jl], acc);
@@ -847,7 +934,7 @@ DVS_HD void reduce_stage1(const FusedParams& p, float* sm, int tid) {
   SmemLayout L{NS};
   constexpr int nv = 3 + 12 * NS;
   for (int w = tid; w < nv * 8; w += NT) {
-    int v = w >> 3, g = w & 7;
+    int g = w / nv, v = w - g * nv;            // consecutive lanes -> consecutive words
     float a = 0.f;
     for (int k = 0; k < 32; ++k) a += sm[L.scratch() + (g * 32 + k) * nv + v];
     sm[L.rbuf() + w] = a;
@@ -859,7 +946,7 @@ DVS_HD void reduce_stage2(const FusedParams& p, const Tile& t, float* sm, int ti
   constexpr int nv = 3 + 12 * NS;
   if (tid < nv) {
     float a = 0.f;
-    for (int g = 0; g < 8; ++g) a += sm[L.rbuf() + tid * 8 + g];
+    for (int g = 0; g < 8; ++g) a += sm[L.rbuf() + g * nv + tid];
     p.part[((size_t)t.blk * p.S + s) * nv + tid] = a;
   }
 }
