@@ -16,6 +16,9 @@ for one batch.  Metric: warped pixels per second, B*S*N*H*W / t, whole job.  Pri
                achieved = bytes_alg(B,H,W,N,S) / t   (SURVEY 8d figure, 303.9 B per full-res pixel at N=2,S=4)
   cpu_baseline the oracle port (op-for-op restatement of the reference's PyTorch path) on the host cores, on a
                bounded sample (batch 2 of the same workload); rank 0, N=1 only
+  eager_cuda_baseline   the same op sequence run eagerly on the GPU (the reference's own CUDA path), N=1 only
+  train_step   BASELINE configs[2]: full VO training step (stock ResNet-18 DepthNet + PoseNet in bf16 autocast, fused
+               fp32 loss, Adam, batch 32/GPU, DDP/NCCL when N>1) in triplets per second, whole job
   --impl reference   times that CPU path alone (all host threads), same metric/config
 """
 from __future__ import annotations
@@ -38,6 +41,11 @@ import torch  # noqa: E402
 H, W, NSRC, NSCALE = 480, 640, 2, 4
 METRIC = "photometric_loss_fwd_bwd_warped_pixels_per_s"
 UNIT = "Gpix/s"
+
+
+def workload_text(B):
+    return (f"isolated photometric loss fwd+bwd, {W}x{H}, batch {B}/GPU, {NSRC} sources, {NSCALE} scales "
+            f"(BASELINE configs[1]); consistent synthetic triplets")
 
 
 def bytes_alg(B, Hh, Ww, N, S):
@@ -154,11 +162,84 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"photometric loss fwd+bwd {W}x{H} N={NSRC} S={NSCALE} (bounded CPU sample: batch {B_s})"},
+            "config": {"workload": workload_text(args.batch), "sample": f"bounded CPU sample: batch {B_s} per step"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ eager CUDA leg
+def time_eager_cuda(host, dev, steps=3, warmup=2):
+    """The reference's eager PyTorch op sequence (oracle port, op-for-op) on the SAME GPU: the denominator of
+    north_star's ">= 20x the reference's own eager CUDA-PyTorch loss throughput".  Checker code, timed as a
+    baseline only."""
+    from oracle import reference_port as port
+    B = host["target"].shape[0]
+    tgt, srcs = host["target"].to(dev), [s.to(dev) for s in host["sources"]]
+    K, iK = host["K"].to(dev), host["inv_K"].to(dev)
+
+    def step():
+        disps = [d.to(dev).requires_grad_(True) for d in host["disps"]]
+        Ts = [T.to(dev).requires_grad_(True) for T in host["Ts"]]
+        noise = [torch.randn(B, NSRC, H, W, device=dev) for _ in range(NSCALE)]
+        out = port.view_synthesis_loss(disps, tgt, srcs, K, iK, Ts, noise)
+        out["loss"].backward()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "value": B * NSCALE * NSRC * H * W / (ms * 1e-3) / 1e9, "unit": UNIT,
+            "what": f"oracle/reference_port.py (the reference's ATen op sequence) fwd+bwd on this GPU, fp32, batch {B}"}
+
+
+# ------------------------------------------------------------------------------------------------ training-step leg
+def run_train(args, world, rank, local, dev):
+    """BASELINE configs[2]: full VO training step, ResNet-18 DepthNet + PoseNet (bf16 autocast, channels_last),
+    fused fp32 loss, Adam, batch 32/GPU, 640x480, batch-sharded DDP (NCCL all-reduce of the network gradients)."""
+    import torch.distributed as dist
+    from vo.train import Trainer, synthetic_sample, DEFAULT_CONFIG
+    import copy
+    Bt = args.train_batch
+    cfg = copy.deepcopy(DEFAULT_CONFIG)
+    cfg["Train"]["batch_size"] = Bt
+    torch.manual_seed(0)                                   # identical initial weights on every rank
+    tr = Trainer(cfg, device=dev, num_layers=18, pretrained=False, net_dtype=torch.bfloat16, distributed=world > 1,
+                 noise="kernel", sync_losses=False)
+    sample = synthetic_sample(Bt, H, W, seed=100 + rank, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        tr.train_mono_step(dict(sample))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        total, _, _ = tr.train_mono_step(dict(sample))
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item()) / args.train_steps
+    loss = float(total)
+    del tr
+    torch.cuda.empty_cache()
+    return {"metric": "train_frames_per_s", "value": world * Bt / dt, "unit": "triplets/s", "ms_per_step": dt * 1e3,
+            "batch_per_gpu": Bt, "steps": args.train_steps, "warmup": 3, "final_loss": loss,
+            "config": "ResNet-18 DepthNet+PoseNet (stock PyTorch, bf16 autocast, channels_last), fused fp32 view-synthesis "
+                      f"loss, Adam, {W}x{H}, batch {Bt}/GPU, DDP over NCCL (BASELINE configs[2]); synthetic triplets resident in HBM"}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -279,6 +360,22 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * pix_step * args.steps / float(te.item()) / 1e9
 
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager:
+        try:
+            eager = time_eager_cuda(host, dev)
+        except Exception as e:                       # pragma: no cover - reported, never fatal for the headline number
+            eager = {"error": repr(e)[:200]}
+        torch.cuda.empty_cache()
+    train = None
+    if not args.no_train:
+        del d_buf, h_out, flush
+        torch.cuda.empty_cache()
+        try:
+            train = run_train(args, world, rank, local, dev)
+        except Exception as e:                       # pragma: no cover
+            train = {"error": repr(e)[:300]}
+
     if rank == 0:
         peak, how = measured_peak_gbs()
         ba = bytes_alg(B, H, W, NSRC, NSCALE)
@@ -305,11 +402,13 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"isolated photometric loss fwd+bwd, {W}x{H}, batch {B}/GPU, {NSRC} sources, {NSCALE} scales "
-                                       f"(BASELINE configs[1]); consistent synthetic triplets; automask noise from the in-kernel generator",
+                "config": {"workload": workload_text(B), "noise": "automask noise from the in-kernel generator",
                            "l2": "256 MB buffer written between timed steps (outside the event pairs)", "sharding": f"batch, {world} independent rank(s), no data-path collective"},
                 "clocks": clocks, "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": 5 * args.steps, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": 5 * args.steps, "roofline": roof, "cpu_baseline": cpu, "eager_cuda_baseline": eager,
+                "train_step": train}
+        if eager and "value" in eager:
+            line["eager_cuda_baseline"]["speedup_device_timed"] = value / eager["value"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -324,6 +423,10 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="batch per GPU (BASELINE configs[1]: 16)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-CUDA reference leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE configs[2])")
+    ap.add_argument("--train-batch", type=int, default=32, help="training-step batch per GPU (configs[2]: 32)")
+    ap.add_argument("--train-steps", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

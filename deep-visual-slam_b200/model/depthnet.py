@@ -1,0 +1,46 @@
+"""DepthNet: ResNet encoder + Monodepth2-style decoder with four sigmoid disparity heads -- stock PyTorch.
+Same constructor and output dict as the reference (model/depthnet.py:16-90): ``("disp", s)`` of shape
+``[B, 1, H / 2**s, W / 2**s]`` for s in ``scales``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .layers import Conv3x3, ConvBlock, upsample
+from .resnet_encoder import ResnetEncoder
+
+
+class DepthNet(nn.Module):
+    def __init__(self, num_layers: int = 18, pretrained: bool = True, num_input_images: int = 1, scales=range(4),
+                 num_output_channels: int = 1, use_skips: bool = True):
+        super().__init__()
+        self.scales = list(scales)
+        self.use_skips = use_skips
+        self.num_output_channels = num_output_channels
+        self.encoder = ResnetEncoder(num_layers, pretrained, num_input_images)
+        self.num_ch_enc = self.encoder.num_ch_enc
+        self.num_ch_dec = np.array([16, 32, 64, 128, 256])
+        self.up0, self.up1, self.heads = nn.ModuleDict(), nn.ModuleDict(), nn.ModuleDict()
+        for i in range(4, -1, -1):
+            c_in = self.num_ch_enc[-1] if i == 4 else self.num_ch_dec[i + 1]
+            self.up0[str(i)] = ConvBlock(c_in, self.num_ch_dec[i])
+            c_in = self.num_ch_dec[i] + (self.num_ch_enc[i - 1] if use_skips and i > 0 else 0)
+            self.up1[str(i)] = ConvBlock(c_in, self.num_ch_dec[i])
+        for s in self.scales:
+            self.heads[str(s)] = Conv3x3(self.num_ch_dec[s], num_output_channels)
+
+    def forward(self, input_data: torch.Tensor) -> dict:
+        feats = self.encoder(input_data)
+        outputs = {}
+        x = feats[-1]
+        for i in range(4, -1, -1):
+            x = upsample(self.up0[str(i)](x))
+            if self.use_skips and i > 0:
+                x = torch.cat([x, feats[i - 1]], 1)
+            x = self.up1[str(i)](x)
+            if i in self.scales:
+                outputs[("disp", i)] = torch.sigmoid(self.heads[str(i)](x))
+        self.outputs = outputs
+        return outputs

@@ -1,0 +1,161 @@
+"""VO training step on B200: stock PyTorch networks + the fused view-synthesis loss, batch-sharded over GPUs.
+
+This is the caller of the accelerated path, kept to the contract of the reference's ``Trainer``
+(vo/train.py:38-199): the same config dict (vo/config.yaml), Adam + PolynomialLR, and
+``train_mono_step(sample) -> (total_loss, outputs, losses)`` = ``zero_grad(set_to_none)`` ->
+``learner.process_batch`` -> ``backward`` -> ``optimizer.step``.  What is new relative to the reference:
+
+  * multi-GPU: one process per GPU (``torchrun``), DepthNet and PoseNet wrapped in ONE
+    ``DistributedDataParallel`` module so PoseNet's two forward calls live inside a single DDP forward; the
+    gradient all-reduce is NCCL over NVLink/NVSwitch, overlapped with the convolution backward by DDP's buckets.
+    The loss shards over the batch with no collective of its own (every reduction is per image or a batch mean,
+    so equal local batches + gradient averaging reproduce the global-batch gradients: SURVEY 8e).
+  * ``net_dtype=torch.bfloat16``: autocast for the networks only; the loss op computes in fp32 whatever the
+    autocast state (the geometry is unusable in half precision).
+  * ``sync_losses=False`` keeps the five loss scalars on the device (the reference copies them to the host
+    every step, vo/train.py:196-197, which serialises the step).
+
+The dataset side of the reference (vo/dataset/*, disk I/O) is out of scope; ``synthetic_sample`` builds a
+Redwood-shaped batch with the sample-dict format of ``MonoDataset.__getitem__`` (vo/dataset/common.py:48-92).
+"""
+from __future__ import annotations
+
+import os
+import sys
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch import optim
+from torch.optim.lr_scheduler import PolynomialLR
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
+
+from model.depthnet import DepthNet  # noqa: E402
+from model.posenet_single import PoseNet  # noqa: E402
+from vo.learner_new import MonodepthTrainer  # noqa: E402
+
+DEFAULT_CONFIG = {
+    "Directory": {"exp_name": "b200"},
+    "Train": dict(mode="axisAngle", use_amp=False, use_compile=False, num_source=1, num_scale=4, min_depth=0.1,
+                  max_depth=10.0, ssim_ratio=0.85, smoothness_ratio=0.001, auto_mask=True, img_w=640, img_h=480,
+                  weight_decay=0.00001, beta1=0.9, batch_size=16, epoch=31, init_lr=0.0001, final_lr=0.00001),
+}
+
+
+class VoNets(nn.Module):
+    """DepthNet + PoseNet behind one ``forward`` (so DDP sees a single forward per step)."""
+
+    def __init__(self, depth_net: nn.Module, pose_net: nn.Module):
+        super().__init__()
+        self.depth_net, self.pose_net = depth_net, pose_net
+
+    def forward(self, target: torch.Tensor, pairs):
+        disp = self.depth_net(target)
+        poses = [self.pose_net(p) for p in pairs]
+        return disp, poses
+
+
+class _Bound:
+    """Callable view of one network of a (possibly DDP-wrapped) VoNets whose results were computed by the joint
+    forward; the learner calls ``depth_net(x)`` / ``pose_net(pair)`` in the reference's order."""
+
+    def __init__(self, owner: "JointForward", kind: str):
+        self.owner, self.kind = owner, kind
+
+    def __call__(self, x):
+        return self.owner.take(self.kind, x)
+
+    def parameters(self):
+        m = self.owner.module
+        m = m.module if hasattr(m, "module") else m
+        return (m.depth_net if self.kind == "depth" else m.pose_net).parameters()
+
+
+class JointForward:
+    """Runs VoNets once per step and hands the results to the learner's separate network calls."""
+
+    def __init__(self, module: nn.Module, frame_ids=(-1, 1)):
+        self.module, self.frame_ids = module, list(frame_ids)
+        self._disp, self._poses = None, []
+
+    def run(self, sample: Dict) -> None:
+        tgt = sample[("target_image", 0)]
+        pairs = []
+        for f in self.frame_ids:
+            src = sample[("source_left", 0) if f == -1 else ("source_right", 0) if f == 1 else ("source", f)]
+            pairs.append(torch.cat([src, tgt], 1) if f < 0 else torch.cat([tgt, src], 1))
+        self._disp, poses = self.module(tgt, pairs)
+        self._poses = list(poses)
+
+    def take(self, kind: str, x):
+        if kind == "depth":
+            return dict(self._disp)
+        return self._poses.pop(0)
+
+
+class Trainer:
+    def __init__(self, config: Optional[dict] = None, device: Optional[torch.device] = None, num_layers: int = 18,
+                 pretrained: bool = False, net_dtype: Optional[torch.dtype] = None, distributed: bool = False,
+                 noise: str = "kernel", sync_losses: bool = True, channels_last: bool = True):
+        self.config = config or DEFAULT_CONFIG
+        tr = self.config["Train"]
+        self.device = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
+        self.net_dtype = net_dtype
+        self.sync_losses = sync_losses
+        self.channels_last = channels_last and self.device.type == "cuda"
+        depth_net = DepthNet(num_layers=num_layers, pretrained=pretrained, num_input_images=1)
+        pose_net = PoseNet(num_layers=num_layers, pretrained=pretrained, num_input_images=2)
+        nets = VoNets(depth_net, pose_net).to(self.device)
+        if self.channels_last:
+            nets = nets.to(memory_format=torch.channels_last)
+        self.nets = nets
+        module: nn.Module = nets
+        if distributed:
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            ids = [self.device.index] if self.device.type == "cuda" else None
+            module = DDP(nets, device_ids=ids, gradient_as_bucket_view=True)
+        self.module = module
+        self.depth_net, self.pose_net = depth_net, pose_net
+        self.optimizer = optim.Adam(list(depth_net.parameters()) + list(pose_net.parameters()), lr=tr["init_lr"])
+        self.scheduler = PolynomialLR(self.optimizer, total_iters=tr["epoch"], power=0.9)
+        self.joint = JointForward(module)
+        self.learner = MonodepthTrainer(_Bound(self.joint, "depth"), _Bound(self.joint, "pose"), self.config, self.device,
+                                        noise=noise)
+
+    def train_mono_step(self, sample: Dict) -> Tuple[torch.Tensor, Dict, Dict]:
+        """reference: vo/train.py:173-199 (the non-AMP branch; bf16 autocast needs no GradScaler)."""
+        self.optimizer.zero_grad(set_to_none=True)
+        for key, val in sample.items():
+            if isinstance(val, torch.Tensor):
+                sample[key] = val.to(self.device, non_blocking=True)
+        if self.net_dtype is not None:
+            with torch.autocast(self.device.type, dtype=self.net_dtype):
+                self.joint.run(self._images(sample))
+        else:
+            self.joint.run(self._images(sample))
+        outputs, losses = self.learner.process_batch(sample)
+        total = losses["loss"]
+        total.backward()
+        self.optimizer.step()
+        total = total.detach()
+        for k in losses:
+            losses[k] = losses[k].detach().cpu() if self.sync_losses else losses[k].detach()
+        return total, outputs, losses
+
+    def _images(self, sample: Dict) -> Dict:
+        if not self.channels_last:
+            return sample
+        out = dict(sample)
+        for k in (("target_image", 0), ("source_left", 0), ("source_right", 0)):
+            out[k] = sample[k].contiguous(memory_format=torch.channels_last)
+        return out
+
+
+def synthetic_sample(B: int, H: int, W: int, seed: int = 0, device="cpu") -> Dict:
+    """Redwood-shaped (t-1, t, t+1) batch in the collated sample-dict format."""
+    from dvsloss.synthetic import make_problem
+    p = make_problem(B, H, W, 2, 4, seed=seed, consistent=True)
+    return {k: v.to(device) for k, v in p["sample"].items()}
