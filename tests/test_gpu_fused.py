@@ -136,3 +136,75 @@ def test_fused_rejects_cpu_tensors():
     with pytest.raises(DvsError):
         view_synthesis_loss(p["disps"], p["target"], p["sources"], p["K"], p["inv_K"],
                             [torch.eye(4)[None]] * 2, noise=None)
+
+
+def _run_torch(p, prob_noise=True, sl=None, **kw):
+    """Fused loss on (a batch slice of) a synthetic problem, torch tensors in and out."""
+    from dvsloss import view_synthesis_loss
+    from dvsloss.synthetic import pose_matrix
+    dev = torch.device("cuda:0")
+    B = p["target"].shape[0]
+    sl = slice(0, B) if sl is None else sl
+    cut = lambda t: t[sl].to(dev).contiguous()
+    disps = [cut(d).requires_grad_(True) for d in p["disps"]]
+    Ts = [cut(pose_matrix(a.view(B, 3), t.view(B, 3), inv)).requires_grad_(True)
+          for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+    noise = [cut(n) for n in p["noise"]]
+    loss, per_scale = view_synthesis_loss(disps, cut(p["target"]), [cut(s) for s in p["sources"]], cut(p["K"]),
+                                          cut(p["inv_K"]), Ts, noise=noise, **kw)
+    return loss, per_scale, disps, Ts
+
+
+def test_fused_config2_batch_decomposition_and_linearity():
+    """BASELINE configs[1] at its full size (batch 16, 640x480, 2 sources, 4 scales): size-independent properties.
+    (1) every reduction of the loss is a batch mean, so the batch-16 result is the mean of the 16 single-item
+    results and the gradients of item b are 1/16 of the single-item gradients (this is also what makes the
+    batch-sharded multi-GPU step exact);  (2) backward is linear in the upstream gradient."""
+    B = 16
+    p = make_problem(B, 480, 640, 2, 4, seed=9, consistent=True)
+    loss, per_scale, disps, Ts = _run_torch(p)
+    loss.backward()
+    acc = torch.zeros(4, dtype=torch.float64)
+    for b in range(B):
+        l1, ps1, d1, T1 = _run_torch(p, sl=slice(b, b + 1))
+        acc += ps1.detach().double().cpu()
+        if b in (0, 7, 15):
+            l1.backward()
+            for s in range(4):
+                ref = d1[s].grad / B
+                err = (disps[s].grad[b:b + 1] - ref).abs().max()
+                assert float(err) <= 2e-5 * float(ref.abs().max()), (b, s)
+            for i in range(2):
+                ref = T1[i].grad / B
+                assert float((Ts[i].grad[b:b + 1] - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-12
+    np.testing.assert_allclose(per_scale.detach().double().cpu().numpy(), (acc / B).numpy(), rtol=2e-6)
+    # linearity: d(sum_s w_s loss/s) = sum_s w_s d(loss/s)
+    w = torch.tensor([3.0, -1.0, 0.5, 2.0], device="cuda")
+    _, ps, dA, TA = _run_torch(p, sl=slice(0, 2))
+    (ps * w).sum().backward()
+    tot = [torch.zeros_like(d) for d in dA]
+    for s in range(4):
+        _, ps_s, dS, _ = _run_torch(p, sl=slice(0, 2))
+        ps_s[s].backward()
+        tot[s] = dS[s].grad * w[s]
+        others = [dS[k].grad for k in range(4) if k != s]
+        assert all(g is None or float(g.abs().max()) == 0.0 for g in others)      # loss/s touches disp[s] only
+    for s in range(4):
+        assert float((dA[s].grad - tot[s]).abs().max()) <= 1e-6 * float(tot[s].abs().max())
+
+
+def test_fused_config4_shape_parity():
+    """BASELINE configs[3] frame: 1280x960, 4 source frames (+-1, +-2), 4 scales; batch 1 against the oracle port on the GPU."""
+    p = make_problem(1, 960, 1280, 4, 4, seed=13, consistent=True)
+    prob = parity.problem_from_synthetic(p, True)
+    stats = parity.check_parity(cuda_impl, prob, device="cuda", verbose=True)
+    assert stats["loss_rel"] < 1e-5
+
+
+@pytest.mark.parametrize("H,W,N", [(240, 320, 1), (720, 960, 2), (1440, 1920, 1)])
+def test_fused_sweep_shapes_loss_parity(H, W, N):
+    """BASELINE configs[4] corner shapes (320x240 ... 1920x1440, 1-2 sources): losses and selection vs the oracle on the GPU."""
+    p = make_problem(1, H, W, N, 4, seed=H + N, consistent=True)
+    prob = parity.problem_from_synthetic(p, True)
+    stats = parity.check_parity(cuda_impl, prob, device="cuda", check_grad=(H <= 720), verbose=True)
+    assert stats["loss_rel"] < 1e-5
