@@ -189,7 +189,7 @@ def check_parity(impl: Callable[[Dict[str, object], Optional[Sequence[float]]], 
             bad = err[ok] > lim[ok]
             # stragglers: at most 2 in 100 000 elements (kinks the float64 locator above missed by a hair) may sit
             # outside the element-wise bound, and then by no more than 10x; the inf-norm bound above has no exception
-            assert bad.mean() <= 2e-5 and np.all(err[ok] <= 10 * lim[ok]), \
+            assert bad.size == 0 or (bad.mean() <= 2e-5 and np.all(err[ok] <= 10 * lim[ok])), \
                 f"grad_disp[{s}]: {int(bad.sum())} of {bad.size} elements outside rtol 1e-3 / atol 1e-6"
             stats["grad_disp_stragglers"] = stats.get("grad_disp_stragglers", 0) + int(bad.sum())
             assert np.all(err[risky] <= 0.25 * rmax), f"grad_disp[{s}]: near-kink elements off by {err[risky].max() / rmax:.3e}"
