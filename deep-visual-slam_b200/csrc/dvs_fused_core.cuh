@@ -110,6 +110,50 @@ DVS_HD float sat01(float x) {
   return x != x ? 0.f : fminf(fmaxf(x, 0.f), 1.f);
 #endif
 }
+// Packed pairs of fp32 (Blackwell FADD2 / FMUL2 / FFMA2: two lanes per issued instruction; same lane throughput as
+// the scalar forms, half the issue slots -- profiles/tools/ffma2_bench.cu).  The kernel is issue bound, so the row sums
+// and the per-pixel SSIM algebra are written on pairs.  Host build (block emulator): plain scalar arithmetic.
+struct f2 {
+  float x, y;
+};
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned long long f2_pk(f2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ f2 f2_up(unsigned long long r) {
+  f2 a;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+  return a;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pk(a)), "l"(f2_pk(b)));
+  return f2_up(r);
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pk(a)), "l"(f2_pk(b)));
+  return f2_up(r);
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pk(a)), "l"(f2_pk(b)));
+  return f2_up(r);
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pk(a)), "l"(f2_pk(b)), "l"(f2_pk(c)));
+  return f2_up(r);
+}
+#else
+inline f2 add2(f2 a, f2 b) { return f2{a.x + b.x, a.y + b.y}; }
+inline f2 sub2(f2 a, f2 b) { return f2{a.x - b.x, a.y - b.y}; }
+inline f2 mul2(f2 a, f2 b) { return f2{a.x * b.x, a.y * b.y}; }
+inline f2 fma2(f2 a, f2 b, f2 c) { return f2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+#endif
+
 DVS_HD float sgn(float x) { return (float)(x > 0.f) - (float)(x < 0.f); }
 DVS_HD int imin(int a, int b) { return a < b ? a : b; }
 DVS_HD int imax(int a, int b) { return a > b ? a : b; }
@@ -308,30 +352,32 @@ DVS_HD void phase_load(const FusedParams& p, const Tile& t, float* sm, int tid, 
 // ------------------------------------------------------------------------------------------------ 3x3 sums, SSIM
 // Neighbourhood of the four pixels: rows m = 0..5 <-> R1 rows r0-1 .. r0+4, columns k = 0..2 <-> cx-1 .. cx+1.
 struct YN {
-  float v[6][3];           // target values
+  f2 vp[3][3];             // target values: vp[m2][k] = rows (2 m2, 2 m2 + 1), column k
   float sy[4];             // 9-sum of y
   float ysq[4];            // sy^2
   float ty[4];             // 9*sum(y^2) + 81*C2
 };
+DVS_HD float yn_at(const YN& q, int m, int k) { return (m & 1) ? q.vp[m >> 1][k].y : q.vp[m >> 1][k].x; }
 struct XS {
   float sx[4], sxx[4], sxy[4], xc[4];
 };
-// vertical 3-sums of 6 row values for the 4 pixels (two shared partial sums)
-DVS_HD void vsum4(const float* h, float* s) {
-  float u12 = h[1] + h[2], u34 = h[3] + h[4];
-  s[0] = h[0] + u12;
-  s[1] = u12 + h[3];
-  s[2] = h[2] + u34;
-  s[3] = u34 + h[5];
+// vertical 3-sums of 6 row values (three row pairs) for the 4 pixels (two shared partial sums)
+DVS_HD void vsum4(const f2* h, float* s) {
+  float u12 = h[0].y + h[1].x, u34 = h[1].y + h[2].x;
+  s[0] = h[0].x + u12;
+  s[1] = u12 + h[1].y;
+  s[2] = h[1].x + u34;
+  s[3] = u34 + h[2].y;
 }
 DVS_HD void load_yn(const float* Y, int base, YN& q) {
-  float hy[6], hyy[6];
-  for (int m = 0; m < 6; ++m) {
-    const float* row = Y + base + (m - 1) * PW;
-    float a = row[-1], b = row[0], c = row[1];
-    q.v[m][0] = a; q.v[m][1] = b; q.v[m][2] = c;
-    hy[m] = a + b + c;
-    hyy[m] = fmaf(c, c, fmaf(b, b, a * a));
+  f2 hy[3], hyy[3];
+  for (int m2 = 0; m2 < 3; ++m2) {
+    const float* r0 = Y + base + (2 * m2 - 1) * PW;
+    const float* r1 = r0 + PW;
+    f2 a{r0[-1], r1[-1]}, b{r0[0], r1[0]}, c{r0[1], r1[1]};
+    q.vp[m2][0] = a; q.vp[m2][1] = b; q.vp[m2][2] = c;
+    hy[m2] = add2(add2(a, b), c);
+    hyy[m2] = fma2(c, c, fma2(b, b, mul2(a, a)));
   }
   float syy[4];
   vsum4(hy, q.sy);
@@ -342,14 +388,17 @@ DVS_HD void load_yn(const float* Y, int base, YN& q) {
   }
 }
 DVS_HD void stats_x(const float* X, int base, const YN& y, XS& q) {
-  float hx[6], hxx[6], hxy[6];
-  for (int m = 0; m < 6; ++m) {
-    const float* row = X + base + (m - 1) * PW;
-    float a = row[-1], b = row[0], c = row[1];
-    if (m >= 1 && m <= 4) q.xc[m - 1] = b;
-    hx[m] = a + b + c;
-    hxx[m] = fmaf(c, c, fmaf(b, b, a * a));
-    hxy[m] = fmaf(c, y.v[m][2], fmaf(b, y.v[m][1], a * y.v[m][0]));
+  f2 hx[3], hxx[3], hxy[3];
+  for (int m2 = 0; m2 < 3; ++m2) {
+    const float* r0 = X + base + (2 * m2 - 1) * PW;
+    const float* r1 = r0 + PW;
+    f2 a{r0[-1], r1[-1]}, b{r0[0], r1[0]}, c{r0[1], r1[1]};
+    if (m2 == 0) q.xc[0] = b.y;
+    if (m2 == 1) { q.xc[1] = b.x; q.xc[2] = b.y; }
+    if (m2 == 2) q.xc[3] = b.x;
+    hx[m2] = add2(add2(a, b), c);
+    hxx[m2] = fma2(c, c, fma2(b, b, mul2(a, a)));
+    hxy[m2] = fma2(c, y.vp[m2][2], fma2(b, y.vp[m2][1], mul2(a, y.vp[m2][0])));
   }
   vsum4(hx, q.sx);
   vsum4(hxx, q.sxx);
@@ -405,8 +454,8 @@ DVS_HD void quad_reproj(const float* sm, int xoff, int yoff, int base, float ssi
     load_yn(sm + yoff + c * PLANE, base, yn);
     if (EDGES)
       for (int j = 0; j < 4; ++j) {
-        ax[j] += fabsf(yn.v[j + 1][1] - yn.v[j + 1][2]);
-        ay[j] += fabsf(yn.v[j + 1][1] - yn.v[j + 2][1]);
+        ax[j] += fabsf(yn_at(yn, j + 1, 1) - yn_at(yn, j + 1, 2));
+        ay[j] += fabsf(yn_at(yn, j + 1, 1) - yn_at(yn, j + 2, 1));
       }
     DVS_UNROLL
     for (int i = 0; i < NS; ++i) {
@@ -414,7 +463,7 @@ DVS_HD void quad_reproj(const float* sm, int xoff, int yoff, int base, float ssi
       stats_x(sm + xoff + (3 * i + c) * PLANE, base, yn, xs);
       for (int j = 0; j < 4; ++j) {
         rs[i][j] += ssim_value(xs.sx[j], xs.sxx[j], xs.sxy[j], yn.sy[j], yn.ysq[j], yn.ty[j]);
-        rl[i][j] += fabsf(yn.v[j + 1][1] - xs.xc[j]);
+        rl[i][j] += fabsf(yn_at(yn, j + 1, 1) - xs.xc[j]);
       }
     }
   }
@@ -446,7 +495,7 @@ DVS_HD void quad_reproj_coefs(float* sm, int xoff, int yoff, int foff, int base,
       for (int j = 0; j < 4; ++j) {
         float al, be, ga;
         rs[i][j] += ssim_coefs(xs.sx[j], xs.sxx[j], xs.sxy[j], yn.sy[j], yn.ysq[j], yn.ty[j], kF, al, be, ga);
-        rl[i][j] += fabsf(yn.v[j + 1][1] - xs.xc[j]);
+        rl[i][j] += fabsf(yn_at(yn, j + 1, 1) - xs.xc[j]);
         if (i == NS - 1) {
           hold[c][0][j] = al; hold[c][1][j] = be; hold[c][2][j] = ga;
         } else {
@@ -742,13 +791,14 @@ DVS_HD void phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, 
 
   DVS_NOUNROLL
   for (int i = 0; i < NS; ++i) {
-    float mk[6][3];
+    f2 mk[3][3];                                        // masks on row pairs (2 m2, 2 m2 + 1)
     bool any = false;
     for (int m = 0; m < 6; ++m)
       for (int k = 0; k < 3; ++k) {
         bool hit = tg[m][k] == i;
         any = any || hit;
-        mk[m][k] = hit ? (k == 0 ? wl : (k == 2 ? wr : 1.f)) : 0.f;
+        float w = hit ? (k == 0 ? wl : (k == 2 ? wr : 1.f)) : 0.f;
+        if (m & 1) mk[m >> 1][k].y = w; else mk[m >> 1][k].x = w;
       }
     if (!any) continue;
     float G[3][4];
@@ -758,17 +808,20 @@ DVS_HD void phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, 
       DVS_UNROLL
       for (int f = 0; f < 3; ++f) {
         const float* F = sm + L.f(c * 3 + f) + base;
-        float h[6];
-        for (int m = 0; m < 6; ++m) {
-          const float* row = F + (m - 1) * PW;
-          h[m] = fmaf(row[1], mk[m][2], fmaf(row[0], mk[m][1], row[-1] * mk[m][0]));
+        f2 h[3];
+        for (int m2 = 0; m2 < 3; ++m2) {
+          const float* r0 = F + (2 * m2 - 1) * PW;
+          const float* r1 = r0 + PW;
+          h[m2] = fma2(f2{r0[1], r1[1]}, mk[m2][2], fma2(f2{r0[0], r1[0]}, mk[m2][1], mul2(f2{r0[-1], r1[-1]}, mk[m2][0])));
         }
         vsum4(h, pooled[f]);
-        if (edge_rows)
+        if (edge_rows) {
+          const float hs[6] = {h[0].x, h[0].y, h[1].x, h[1].y, h[2].x, h[2].y};
           for (int j = 0; j < 4; ++j) {
-            if (gyb + j == 1) pooled[f][j] += h[j];
-            if (gyb + j == p.H - 2) pooled[f][j] += h[j + 2];
+            if (gyb + j == 1) pooled[f][j] += hs[j];
+            if (gyb + j == p.H - 2) pooled[f][j] += hs[j + 2];
           }
+        }
       }
       const float* X = sm + L.x(0, c) + i * 3 * PLANE + base;
       const float* Y = sm + L.y(c) + base;

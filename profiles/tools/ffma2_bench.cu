@@ -29,6 +29,12 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, int ite
     } else if (MODE == 3) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { p[i] = fma2(p[i], ss, ss); q[i] = iop(q[i], q[(i + 1) & 7]); q[(i + 3) & 7] = iop(q[(i + 3) & 7], q[i]); }
+    } else if (MODE == 4) {          // 16 FFMA + 8 independent integer ops: issue bound if FFMA is 1 slot (24 slots)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { a[i] = fma1(a[i], s, s); if (i & 1) q[i >> 1] = iop(q[i >> 1], 0x9e3779b9u); }
+    } else if (MODE == 5) {          // 8 FFMA2 + 8 independent integer ops: 16 slots if FFMA2 takes one issue slot, 24 if two
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { p[i] = fma2(p[i], ss, ss); q[i] = iop(q[i], 0x9e3779b9u); }
     }
   }
   float r = 0; unsigned z = 0;
@@ -58,6 +64,8 @@ int main() {
   run<1>("FFMA2 x8", d, iters, 16, 8);
   run<2>("FFMA x16 + LOP3 x16", d, iters, 16, 32);
   run<3>("FFMA2 x8 + LOP3 x16", d, iters, 16, 24);
+  run<4>("FFMA x16 + LOP3 x8 (indep)", d, iters, 16, 24);
+  run<5>("FFMA2 x8 + LOP3 x8 (indep)", d, iters, 16, 16);
   cudaError_t e = cudaDeviceSynchronize();
   printf("status %s\n", cudaGetErrorString(e));
   return e != cudaSuccess;

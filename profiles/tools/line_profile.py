@@ -77,6 +77,18 @@ def main():
     print("\n== top lines")
     for (f, ln), (a, b) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:40]:
         print(f"{f}:{ln:<5d} {100 * a / tot_i:6.2f}% {100 * b / max(tot_s, 1):6.2f}%  {fn.get(ln, '') if f.endswith('core.cuh') else ''}")
+    print("\n== top lines by stall samples (line, samples %, dominant stall reasons)")
+    reasons = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    by_line_r = defaultdict(lambda: defaultdict(int))
+    for r, ((f, ln), op) in zip(body[:n], ann[:n]):
+        for h in reasons:
+            v = int(r[ci[h]] or 0)
+            if v:
+                by_line_r[(f, ln)][h] += v
+    for (f, ln), (a, b) in sorted(by_line.items(), key=lambda kv: -kv[1][1])[:30]:
+        top = sorted(by_line_r[(f, ln)].items(), key=lambda kv: -kv[1])[:3]
+        print(f"{f}:{ln:<5d} {100 * b / max(tot_s, 1):6.2f}%  {fn.get(ln, '') if f.endswith('core.cuh') else '':18s} " +
+              " ".join(f"{k[6:]}={v}" for k, v in top))
     print("\n== by opcode")
     for k, a in sorted(by_op.items(), key=lambda kv: -kv[1])[:25]:
         print(f"{k:12s} {100 * a / tot_i:6.2f}%")
