@@ -725,7 +725,7 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
   }
   if (!GRAD) return;
 
-  if (kSinglePass) {
+  if constexpr (kSinglePass) {
     // F already holds the fields of source 0 (N == 2); the last source's go in where it was selected
     for (int j = 0; j < 4; ++j) {
       if (tag[j] != NS - 1) continue;
@@ -733,8 +733,7 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
       for (int c = 0; c < 3; ++c)
         for (int f = 0; f < 3; ++f) sm[o + (c * 3 + f) * PLANE] = hold[c][f][j];
     }
-    return;
-  }
+  } else {
   // more than two sources: coefficient fields of the selected source(s) of these pixels -> F planes (second pass)
   DVS_UNROLL
   for (int i = 0; i < NS; ++i) {
@@ -756,6 +755,7 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
         sm[L.f(c * 3 + 2) + o] = ga;
       }
     }
+  }
   }
 }
 
