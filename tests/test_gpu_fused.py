@@ -208,3 +208,45 @@ def test_fused_sweep_shapes_loss_parity(H, W, N):
     prob = parity.problem_from_synthetic(p, True)
     stats = parity.check_parity(cuda_impl, prob, device="cuda", check_grad=(H <= 720), verbose=True)
     assert stats["loss_rel"] < 1e-5
+
+
+def test_c_abi_backward_recompute_matches_forward_saved_gradients():
+    """dvs_photometric_backward_recompute (stand-alone backward, nothing saved between passes) called straight
+    through the C ABI with raw device pointers equals forward(unit gradients) + dvs_photometric_backward."""
+    import ctypes as C
+    from dvsloss import _lib
+    from dvsloss._lib import DvsParams, fptr_array, lib, make_shape, ptr, stream_ptr
+    g = parity.load_golden("ref_b2_48x64_consistent.npz")
+    prob = g["prob"]
+    gps = [0.7, -0.2, 1.5, 0.25]
+    ref = cuda_impl(prob, gps)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dev)
+    disps, Ts = [t(d) for d in prob["disps"]], [t(T) for T in prob["Ts"]]
+    tgt, srcs, K, iK = t(prob["target"]), [t(s) for s in prob["sources"]], t(prob["K"]), t(prob["inv_K"])
+    noise = [t(n) for n in prob["noise"]]
+    B, _, H, W = tgt.shape
+    shape = make_shape(B, H, W, len(srcs), [d.shape[2:] for d in disps])
+    params = DvsParams(0.1, 10.0, 0.85, 1e-3, 1e-7, 1)
+    L = lib()
+    nbytes = C.c_size_t(0)
+    assert L.dvs_loss_workspace_bytes(C.byref(shape), C.byref(nbytes)) == 0
+    ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
+    wsp = (ws.data_ptr() + 255) // 256 * 256
+    gd = [torch.full_like(d, float("nan")) for d in disps]
+    gT = [torch.full((B, 4, 4), float("nan"), device=dev) for _ in Ts]
+    gvec = t(np.asarray(gps, np.float32))
+    rc = L.dvs_photometric_backward_recompute(C.byref(shape), C.byref(params), fptr_array(disps), ptr(tgt), fptr_array(srcs),
+                                              ptr(K), ptr(iK), fptr_array(Ts), fptr_array(noise), C.c_uint64(0), C.c_uint64(0),
+                                              ptr(gvec), fptr_array(gd), fptr_array(gT), wsp, stream_ptr(dev))
+    _lib.check(rc, "dvs_photometric_backward_recompute")
+    torch.cuda.synchronize()
+    for s in range(4):
+        a, b = gd[s].cpu().numpy(), ref["grad_disp"][s]
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max() + 1e-12, s      # same kernels; atomics may reorder the coarse sums
+    for i in range(2):
+        assert np.array_equal(gT[i].cpu().numpy(), ref["grad_T"][i])
+    # misuse is reported, not executed
+    assert L.dvs_photometric_backward_recompute(C.byref(shape), C.byref(params), fptr_array(disps), ptr(tgt), fptr_array(srcs),
+                                                ptr(K), ptr(iK), fptr_array(Ts), None, 0, 0, None, fptr_array(gd), fptr_array(gT),
+                                                wsp, stream_ptr(dev)) == -1
