@@ -211,6 +211,7 @@ def run_train(args, world, rank, local, dev):
     cfg = copy.deepcopy(DEFAULT_CONFIG)
     cfg["Train"]["batch_size"] = Bt
     torch.manual_seed(0)                                   # identical initial weights on every rank
+    torch.backends.cudnn.benchmark = True                  # fixed shapes: let cuDNN pick its fastest convolution algorithms
     tr = Trainer(cfg, device=dev, num_layers=18, pretrained=False, net_dtype=torch.bfloat16, distributed=world > 1,
                  noise="kernel", sync_losses=False)
     sample = synthetic_sample(Bt, H, W, seed=100 + rank, device=dev)
