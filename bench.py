@@ -207,14 +207,16 @@ def run_train(args, world, rank, local, dev):
     import torch.distributed as dist
     from vo.train import Trainer, synthetic_sample, DEFAULT_CONFIG
     import copy
-    Bt = args.train_batch
+    big = args.train_variant == "r50x4"                  # BASELINE configs[3]: ResNet-50, 1280x960, 4 sources, batch 8/GPU
+    Bt = args.train_batch if args.train_batch > 0 else (8 if big else 32)
+    Ht, Wt, layers, fids = (960, 1280, 50, (-1, 1, -2, 2)) if big else (H, W, 18, (-1, 1))
     cfg = copy.deepcopy(DEFAULT_CONFIG)
-    cfg["Train"]["batch_size"] = Bt
+    cfg["Train"].update(batch_size=Bt, img_h=Ht, img_w=Wt)
     torch.manual_seed(0)                                   # identical initial weights on every rank
     torch.backends.cudnn.benchmark = True                  # fixed shapes: let cuDNN pick its fastest convolution algorithms
-    tr = Trainer(cfg, device=dev, num_layers=18, pretrained=False, net_dtype=torch.bfloat16, distributed=world > 1,
-                 noise="kernel", sync_losses=False)
-    sample = synthetic_sample(Bt, H, W, seed=100 + rank, device=dev)
+    tr = Trainer(cfg, device=dev, num_layers=layers, pretrained=False, net_dtype=torch.bfloat16, distributed=world > 1,
+                 noise="kernel", sync_losses=False, frame_ids=fids)
+    sample = synthetic_sample(Bt, Ht, Wt, seed=100 + rank, device=dev, num_sources=len(fids))
 
     def barrier():
         if world > 1:
@@ -239,8 +241,9 @@ def run_train(args, world, rank, local, dev):
     torch.cuda.empty_cache()
     return {"metric": "train_frames_per_s", "value": world * Bt / dt, "unit": "triplets/s", "ms_per_step": dt * 1e3,
             "batch_per_gpu": Bt, "steps": args.train_steps, "warmup": 3, "final_loss": loss,
-            "config": "ResNet-18 DepthNet+PoseNet (stock PyTorch, bf16 autocast, channels_last), fused fp32 view-synthesis "
-                      f"loss, Adam, {W}x{H}, batch {Bt}/GPU, DDP over NCCL (BASELINE configs[2]); synthetic triplets resident in HBM"}
+            "config": f"ResNet-{layers} DepthNet+PoseNet (stock PyTorch, bf16 autocast, channels_last), fused fp32 view-synthesis "
+                      f"loss with {len(fids)} source frames, Adam, {Wt}x{Ht}, batch {Bt}/GPU, DDP over NCCL "
+                      f"(BASELINE configs[{3 if big else 2}]); synthetic frames resident in HBM"}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -426,7 +429,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-CUDA reference leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE configs[2])")
-    ap.add_argument("--train-batch", type=int, default=32, help="training-step batch per GPU (configs[2]: 32)")
+    ap.add_argument("--train-batch", type=int, default=0, help="training-step batch per GPU (default: 32, or 8 for r50x4)")
+    ap.add_argument("--train-variant", default="r18", choices=["r18", "r50x4"],
+                    help="r18 = BASELINE configs[2]; r50x4 = configs[3] (ResNet-50, 1280x960, sources +-1 and +-2)")
     ap.add_argument("--train-steps", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":

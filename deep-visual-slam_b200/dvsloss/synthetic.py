@@ -173,6 +173,8 @@ def make_problem(B: int, H: int, W: int, num_sources: int = 2, num_scales: int =
         sample[("source_left", 0)] = sources[0]
     if num_sources >= 2:
         sample[("source_right", 0)] = sources[1]
+    for i in range(2, num_sources):                     # further frames (+-2, ...): keyed by their frame id
+        sample[("source", frame_ids[i])] = sources[i]
 
     def mv(t):
         return t.to(device).contiguous()

@@ -99,7 +99,7 @@ class JointForward:
 class Trainer:
     def __init__(self, config: Optional[dict] = None, device: Optional[torch.device] = None, num_layers: int = 18,
                  pretrained: bool = False, net_dtype: Optional[torch.dtype] = None, distributed: bool = False,
-                 noise: str = "kernel", sync_losses: bool = True, channels_last: bool = True):
+                 noise: str = "kernel", sync_losses: bool = True, channels_last: bool = True, frame_ids=(-1, 1)):
         self.config = config or DEFAULT_CONFIG
         tr = self.config["Train"]
         self.device = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
@@ -123,9 +123,10 @@ class Trainer:
         # fused=True: one multi-tensor kernel for the whole Adam update instead of ~10 launches per parameter group
         self.optimizer = optim.Adam(params, lr=tr["init_lr"], fused=self.device.type == "cuda")
         self.scheduler = PolynomialLR(self.optimizer, total_iters=tr["epoch"], power=0.9)
-        self.joint = JointForward(module)
+        self.frame_ids = list(frame_ids)
+        self.joint = JointForward(module, self.frame_ids)
         self.learner = MonodepthTrainer(_Bound(self.joint, "depth"), _Bound(self.joint, "pose"), self.config, self.device,
-                                        noise=noise)
+                                        frame_ids=self.frame_ids, noise=noise)
 
     def train_mono_step(self, sample: Dict) -> Tuple[torch.Tensor, Dict, Dict]:
         """reference: vo/train.py:173-199 (the non-AMP branch; bf16 autocast needs no GradScaler)."""
@@ -151,13 +152,14 @@ class Trainer:
         if not self.channels_last:
             return sample
         out = dict(sample)
-        for k in (("target_image", 0), ("source_left", 0), ("source_right", 0)):
-            out[k] = sample[k].contiguous(memory_format=torch.channels_last)
+        for k, v in sample.items():
+            if isinstance(v, torch.Tensor) and v.dim() == 4 and v.shape[1] == 3:
+                out[k] = v.contiguous(memory_format=torch.channels_last)
         return out
 
 
-def synthetic_sample(B: int, H: int, W: int, seed: int = 0, device="cpu") -> Dict:
-    """Redwood-shaped (t-1, t, t+1) batch in the collated sample-dict format."""
+def synthetic_sample(B: int, H: int, W: int, seed: int = 0, device="cpu", num_sources: int = 2) -> Dict:
+    """Redwood-shaped (t-1, t, t+1[, t-2, t+2]) batch in the collated sample-dict format."""
     from dvsloss.synthetic import make_problem
-    p = make_problem(B, H, W, 2, 4, seed=seed, consistent=True)
+    p = make_problem(B, H, W, num_sources, 4, seed=seed, consistent=True)
     return {k: v.to(device) for k, v in p["sample"].items()}
