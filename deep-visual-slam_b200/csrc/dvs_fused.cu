@@ -230,6 +230,7 @@ static WsLayout ws_layout(const DvsShape& sh) {
 static int check_shape(const DvsShape* sh) {
   if (!sh) return DVS_EINVAL;
   if (sh->B < 1 || sh->H < 2 || sh->W < 2) return DVS_EINVAL;
+  if (sh->H > 32767 || sh->W > 65535) return DVS_EINVAL;                          // (row << 16) | column position table
   if (sh->N < 1 || sh->N > DVS_MAX_SOURCES || sh->S < 1 || sh->S > DVS_MAX_SCALES) return DVS_EINVAL;
   for (int s = 0; s < sh->S; ++s)
     if (sh->dh[s] < 1 || sh->dw[s] < 1 || sh->dh[s] > sh->H || sh->dw[s] > sh->W) return DVS_EINVAL;
