@@ -230,14 +230,15 @@ struct SmemLayout {
   DVS_HD int pos() const { return (15 + 3 * N) * PLANE; }            // (ry << 16) | rx of every R2 pixel
   DVS_HD int sel() const { return (16 + 3 * N) * PLANE; }            // PLANE bytes = PLANE/4 floats
   DVS_HD int consts() const { return sel() + PLANE / 4; }
-  DVS_HD int total() const { return consts() + 8 + 12 * kMaxN; }
+  DVS_HD int total() const { return consts() + 8 + 12 * kMaxN + 8 * kMaxS; }
   // scratch for block reductions / up-sample adjoint: aliases X (and the head of F) once those are dead
   DVS_HD int scratch() const { return x(0, 0); }
   DVS_HD int tbuf() const { return f(9) - 1152; }                     // last 1152 floats of F
   DVS_HD int rbuf() const { return f(9) - 1152 - 512; }               // 512 floats before it
 };
-// consts block: [0..3] inv_mu[s]; [8+12i ..] A_i (3x3 row-major) then p_i (3)
-constexpr int kC_invmu = 0, kC_A = 8;
+// consts block: [0..3] inv_mu[s]; [8+12i ..] A_i (3x3 row-major) then p_i (3); then per scale 8 ints for the up-sample
+// adjoint: coarse box i0, i1, j0, j1 of the tile and the integer ratios H/dh, W/dw (0 when not integer)
+constexpr int kC_invmu = 0, kC_A = 8, kC_adj = 8 + 12 * kMaxN;
 
 template <int NS>
 struct ThreadState {
@@ -268,6 +269,23 @@ DVS_HD Tile make_tile(const FusedParams& p, int blk) {
 
 // thread -> pixels: column cx = lane, rows r0 .. r0+3 of R1
 DVS_HD void quad_coords(int tid, int& r0, int& cx) { r0 = (tid >> 5) << 2; cx = tid & 31; }
+
+struct CoarseBox {
+  int i0, i1, j0, j1;   // inclusive coarse ranges touched by the tile
+  int fy0, fy1, fx0, fx1;  // fine ranges of R0 clipped to the image (inclusive)
+};
+DVS_HD CoarseBox coarse_box(const FusedParams& p, const Tile& t, int s) {
+  CoarseBox c;
+  c.fy0 = t.gy0 + 1; c.fy1 = imin(t.gy0 + TH - 2, p.H - 1);
+  c.fx0 = t.gx0 + 1; c.fx1 = imin(t.gx0 + TW - 2, p.W - 1);
+  int a, b;
+  float l;
+  up_taps(c.fy0, (float)p.dh[s] / (float)p.H, p.dh[s], a, b, l); c.i0 = a;
+  up_taps(c.fy1, (float)p.dh[s] / (float)p.H, p.dh[s], a, b, l); c.i1 = b;
+  up_taps(c.fx0, (float)p.dw[s] / (float)p.W, p.dw[s], a, b, l); c.j0 = a;
+  up_taps(c.fx1, (float)p.dw[s] / (float)p.W, p.dw[s], a, b, l); c.j1 = b;
+  return c;
+}
 
 // ------------------------------------------------------------------------------------------------ phase 0
 // constants of the tile: A_i = (K T_i)[:3,:3] inv_K[:3,:3], p_i = (K T_i)[:3,3], 1/(clamp(mean disp)+1e-7) per scale.
@@ -304,6 +322,13 @@ DVS_HD void phase_consts(const FusedParams& p, const Tile& t, float* sm, int tid
     for (int k = 0; k < kMeanBlocks; ++k) m += mp[k];
     m = m / ((float)p.H * (float)p.W);
     c[kC_invmu + s] = 1.0f / (fmaxf(m, 0.001f) + 1e-7f);
+  } else if (tid >= 96 && tid < 96 + p.S) {
+    int s = tid - 96;
+    int* a = reinterpret_cast<int*>(c + kC_adj + 8 * s);
+    CoarseBox cb = coarse_box(p, t, s);
+    a[0] = cb.i0; a[1] = cb.i1; a[2] = cb.j0; a[3] = cb.j1;
+    a[4] = (p.H % p.dh[s] == 0) ? p.H / p.dh[s] : 0;
+    a[5] = (p.W % p.dw[s] == 0) ? p.W / p.dw[s] : 0;
   }
 }
 
@@ -333,7 +358,12 @@ DVS_HD void phase_load(const FusedParams& p, const Tile& t, float* sm, int tid, 
       }
     }
   }
+#if defined(__CUDA_ARCH__)
+  float4* f4 = reinterpret_cast<float4*>(sm + L.f(0));          // 9 planes of 1156 floats: 16-byte aligned, 2601 float4
+  for (int k = tid; k < 9 * PLANE / 4; k += NT) f4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
   for (int k = tid; k < 9 * PLANE; k += NT) sm[L.f(0) + k] = 0.f;
+#endif
   for (int k = tid; k < PLANE / 4; k += NT) reinterpret_cast<unsigned int*>(sm + L.sel())[k] = 0xffffffffu;   // kSelNone
   int r0, cx;
   quad_coords(tid, r0, cx);
@@ -894,28 +924,11 @@ DVS_HD void stage_gdu(const FusedParams& p, const Tile& t, float* sm, int tid, c
 }
 // ... then the adjoint of the bilinear up-sample restricted to this tile, separably:
 // (a) rows of R0 x coarse columns into tbuf, (b) coarse rows x coarse columns -> atomic add to global.
-struct CoarseBox {
-  int i0, i1, j0, j1;   // inclusive coarse ranges touched by the tile
-  int fy0, fy1, fx0, fx1;  // fine ranges of R0 clipped to the image (inclusive)
-};
-DVS_HD CoarseBox coarse_box(const FusedParams& p, const Tile& t, int s) {
-  CoarseBox c;
-  c.fy0 = t.gy0 + 1; c.fy1 = imin(t.gy0 + TH - 2, p.H - 1);
-  c.fx0 = t.gx0 + 1; c.fx1 = imin(t.gx0 + TW - 2, p.W - 1);
-  int a, b;
-  float l;
-  up_taps(c.fy0, (float)p.dh[s] / (float)p.H, p.dh[s], a, b, l); c.i0 = a;
-  up_taps(c.fy1, (float)p.dh[s] / (float)p.H, p.dh[s], a, b, l); c.i1 = b;
-  up_taps(c.fx0, (float)p.dw[s] / (float)p.W, p.dw[s], a, b, l); c.j0 = a;
-  up_taps(c.fx1, (float)p.dw[s] / (float)p.W, p.dw[s], a, b, l); c.j1 = b;
-  return c;
-}
 // Fine indices whose up-sampling taps can include coarse index J: for an integer ratio f = out/in the hat function
 // around J covers [J f - f/2, J f + 3f/2 - 1] (one spare element on each side for odd f; the border clamps only
 // shrink it); otherwise a generous float bound.
-DVS_HD void fine_range(int J, int out, int in, float inv, int& lo, int& hi) {
-  if (out % in == 0) {
-    int f = out / in;
+DVS_HD void fine_range(int J, int f, float inv, int& lo, int& hi) {
+  if (f > 0) {
     lo = J * f - f / 2 - 1;
     hi = J * f + (3 * f) / 2;
   } else {
@@ -927,20 +940,23 @@ constexpr int kTbufCols = 36;   // >= max coarse columns touched by 30 fine colu
 template <int NS>
 DVS_HD void adjoint_rows(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   SmemLayout L{NS};
-  CoarseBox cb = coarse_box(p, t, s);
-  int ncj = cb.j1 - cb.j0 + 1, nfy = cb.fy1 - cb.fy0 + 1;
-  float scale = (float)p.dw[s] / (float)p.W;
-  float inv = (float)p.W / (float)p.dw[s];
+  const int* a = reinterpret_cast<const int*>(sm + L.consts() + kC_adj + 8 * s);
+  const int j0 = a[2], ncj = a[3] - a[2] + 1, fxi = a[5];
+  const int fy0 = t.gy0 + 1, fx0 = t.gx0 + 1, fx1 = imin(t.gx0 + TW - 2, p.W - 1);
+  const int nfy = imin(t.gy0 + TH - 2, p.H - 1) - fy0 + 1;
+  const float scale = (float)p.dw[s] / (float)p.W, inv = (float)p.W / (float)p.dw[s];
+  const float rn = 1.0f / (float)ncj;
   for (int k = tid; k < nfy * ncj; k += NT) {
-    int y = k / ncj, J = cb.j0 + k % ncj;
+    int y = (int)(((float)k + 0.5f) * rn);              // k / ncj (exact for these small integers)
+    int Jl = k - y * ncj, J = j0 + Jl;
     // fine columns that can touch coarse column J (superset, exact weight inside)
     int xa, xb;
-    fine_range(J, p.W, p.dw[s], inv, xa, xb);
-    xa = imax(xa, cb.fx0); xb = imin(xb, cb.fx1);
+    fine_range(J, fxi, inv, xa, xb);
+    xa = imax(xa, fx0); xb = imin(xb, fx1);
     float acc = 0.f;
-    const float* row = sm + L.du() + pidx(cb.fy0 + y - t.gy0, -t.gx0);
+    const float* row = sm + L.du() + pidx(y + 1, -t.gx0);
     for (int x = xa; x <= xb; ++x) acc = fmaf(tap_weight(x, scale, p.dw[s], J), row[x], acc);
-    sm[L.tbuf() + y * kTbufCols + (J - cb.j0)] = acc;
+    sm[L.tbuf() + y * kTbufCols + Jl] = acc;
   }
 }
 DVS_HD void atomic_add_f32(float* a, float v) {
@@ -953,19 +969,21 @@ DVS_HD void atomic_add_f32(float* a, float v) {
 template <int NS>
 DVS_HD void adjoint_cols(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   SmemLayout L{NS};
-  CoarseBox cb = coarse_box(p, t, s);
-  int ncj = cb.j1 - cb.j0 + 1, nci = cb.i1 - cb.i0 + 1;
-  float scale = (float)p.dh[s] / (float)p.H;
-  float inv = (float)p.H / (float)p.dh[s];
+  const int* a = reinterpret_cast<const int*>(sm + L.consts() + kC_adj + 8 * s);
+  const int i0 = a[0], nci = a[1] - a[0] + 1, j0 = a[2], ncj = a[3] - a[2] + 1, fyi = a[4];
+  const int fy0 = t.gy0 + 1, fy1 = imin(t.gy0 + TH - 2, p.H - 1);
+  const float scale = (float)p.dh[s] / (float)p.H, inv = (float)p.H / (float)p.dh[s];
+  const float rn = 1.0f / (float)ncj;
   for (int k = tid; k < nci * ncj; k += NT) {
-    int I = cb.i0 + k / ncj, Jl = k % ncj;
+    int Il = (int)(((float)k + 0.5f) * rn);
+    int Jl = k - Il * ncj, I = i0 + Il;
     int ya, yb;
-    fine_range(I, p.H, p.dh[s], inv, ya, yb);
-    ya = imax(ya, cb.fy0); yb = imin(yb, cb.fy1);
+    fine_range(I, fyi, inv, ya, yb);
+    ya = imax(ya, fy0); yb = imin(yb, fy1);
     float acc = 0.f;
     for (int y = ya; y <= yb; ++y)
-      acc = fmaf(tap_weight(y, scale, p.dh[s], I), sm[L.tbuf() + (y - cb.fy0) * kTbufCols + Jl], acc);
-    atomic_add_f32(p.gdisp[s] + ((size_t)t.b * p.dh[s] + I) * p.dw[s] + cb.j0 + Jl, acc);
+      acc = fmaf(tap_weight(y, scale, p.dh[s], I), sm[L.tbuf() + (y - fy0) * kTbufCols + Jl], acc);
+    atomic_add_f32(p.gdisp[s] + ((size_t)t.b * p.dh[s] + I) * p.dw[s] + j0 + Jl, acc);
   }
 }
 
