@@ -250,3 +250,47 @@ def test_c_abi_backward_recompute_matches_forward_saved_gradients():
     assert L.dvs_photometric_backward_recompute(C.byref(shape), C.byref(params), fptr_array(disps), ptr(tgt), fptr_array(srcs),
                                                 ptr(K), ptr(iK), fptr_array(Ts), None, 0, 0, None, fptr_array(gd), fptr_array(gT),
                                                 wsp, stream_ptr(dev)) == -1
+
+
+def test_fused_loss_is_cuda_graph_capturable():
+    """the whole loss forward+backward (4 + 1 kernels, 3 memsets, no host sync) replays from a CUDA graph
+    and gives the numbers of the eager call (the reference syncs the host every step, vo/train.py:196-197)."""
+    from dvsloss import view_synthesis_loss
+    from dvsloss.synthetic import pose_matrix
+    dev = torch.device("cuda:0")
+    B = 2
+    p = make_problem(B, 96, 128, 2, 4, seed=21, consistent=True)
+    cut = lambda t: t.to(dev).contiguous()
+    disps = [cut(d).requires_grad_(True) for d in p["disps"]]
+    Ts = [cut(pose_matrix(a.view(B, 3), t.view(B, 3), inv)).requires_grad_(True)
+          for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+    tgt, srcs, K, iK = cut(p["target"]), [cut(s) for s in p["sources"]], cut(p["K"]), cut(p["inv_K"])
+    noise = [cut(n) for n in p["noise"]]
+
+    def step():
+        loss, per_scale = view_synthesis_loss(disps, tgt, srcs, K, iK, Ts, noise=noise)
+        grads = torch.autograd.grad(loss, disps + Ts)
+        return loss.detach(), per_scale.detach(), grads      # keep no autograd graph alive across streams
+
+    ref = step()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                       # warm-up on a side stream, as torch.cuda.graphs requires
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = step()
+    with torch.no_grad():                                # new inputs in the captured buffers
+        for d in disps:
+            d.mul_(0.9).add_(0.01)
+    g.replay()
+    torch.cuda.synchronize()
+    chk = step()
+    assert float(out[0]) == float(chk[0]) and float(out[0]) != float(ref[0])
+    assert torch.equal(out[1], chk[1])
+    for a, b in zip(out[2][4:], chk[2][4:]):
+        assert torch.equal(a, b)                         # pose gradients: fixed-order reductions
+    assert torch.equal(out[2][0], chk[2][0])             # full-resolution disparity gradient: direct stores
+    for a, b in zip(out[2][1:4], chk[2][1:4]):
+        assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())      # coarse scales: atomics reorder the sums
