@@ -25,17 +25,35 @@ __global__ void __launch_bounds__(256) mean_partial_kernel(FusedParams p, float*
   const int h = p.dh[s], w = p.dw[s], n = h * w;
   const float* d = p.disp[s] + (size_t)b * n;
   const bool exact = (p.H % h == 0) && (p.W % w == 0);
-  const float cw = exact ? (float)((p.H / h) * (p.W / w)) : 0.f;
   const int per = (n + kMeanBlocks - 1) / kMeanBlocks;
   const int lo = chunk * per, hi = min(lo + per, n);
   float acc = 0.f;
-  for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
-    float wgt = cw;
-    if (!exact) {
-      int i = e / w, j = e - i * w;
-      wgt = up_weight(i, h, p.H) * up_weight(j, w, p.W);
+  if (exact) {
+    // constant weight: plain sum, 128-bit loads where the chunk is aligned (independent accumulators keep several
+    // loads in flight per thread), scalar head/tail
+    const float cw = (float)((p.H / h) * (p.W / w));
+    int a0 = lo, a1 = hi;
+    if ((((uintptr_t)d) & 15) == 0) {
+      a0 = min((lo + 3) & ~3, hi);
+      a1 = max(a0, hi & ~3);
+      const float4* d4 = reinterpret_cast<const float4*>(d);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int e = a0 / 4 + threadIdx.x; e < a1 / 4; e += blockDim.x) {
+        float4 v = d4[e];
+        s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+      }
+      acc = (s0 + s1) + (s2 + s3);
+      for (int e = lo + threadIdx.x; e < a0; e += blockDim.x) acc += d[e];
+      for (int e = a1 + threadIdx.x; e < hi; e += blockDim.x) acc += d[e];
+    } else {
+      for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) acc += d[e];
     }
-    acc = fmaf(wgt, d[e], acc);
+    acc *= cw;
+  } else {
+    for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+      int i = e / w, j = e - i * w;
+      acc = fmaf(up_weight(i, h, p.H) * up_weight(j, w, p.W), d[e], acc);
+    }
   }
   __shared__ float red[8];
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -188,15 +206,28 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(BackwardParams q) {
     return;
   }
   const int h = q.dh[s], w = q.dw[s];
-  const size_t n = (size_t)q.B * h * w;
+  const size_t hw = (size_t)h * w, n = (size_t)q.B * hw;
   const float gs = q.g[s];
   const bool exact = (q.H % h == 0) && (q.W % w == 0);
   const float cwc = exact ? (float)((q.H / h) * (q.W / w)) : 0.f;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-    int b = (int)(e / ((size_t)h * w));
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (exact && (hw & 3) == 0 && ((((uintptr_t)q.u[s]) | ((uintptr_t)q.out[s])) & 15) == 0) {
+    // constant up-sampling weight and whole float4s inside one image: 128-bit loads and stores
+    const float4* u4 = reinterpret_cast<const float4*>(q.u[s]);
+    float4* o4 = reinterpret_cast<float4*>(q.out[s]);
+    for (size_t e = t0; e < n / 4; e += stride) {
+      const float c = q.coup[s * q.B + (int)((e * 4) / hw)] * cwc;
+      float4 v = u4[e];
+      v.x = gs * (v.x - c); v.y = gs * (v.y - c); v.z = gs * (v.z - c); v.w = gs * (v.w - c);
+      o4[e] = v;
+    }
+    return;
+  }
+  for (size_t e = t0; e < n; e += stride) {
+    int b = (int)(e / hw);
     float wgt = cwc;
     if (!exact) {
-      int r = (int)(e - (size_t)b * h * w);
+      int r = (int)(e - (size_t)b * hw);
       int i = r / w, j = r - i * w;
       wgt = up_weight(i, h, q.H) * up_weight(j, w, q.W);
     }
