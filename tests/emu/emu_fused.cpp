@@ -19,6 +19,8 @@ using namespace dvs;
 
 namespace {
 
+int g_guard_hit = 0;      // 1 + index of a block that wrote past the declared shared-memory extent
+
 template <int NS, bool GRAD>
 void run_block(const FusedParams& p, int blk, std::vector<float>& smv) {
   float* sm = smv.data();
@@ -52,12 +54,16 @@ void run_block(const FusedParams& p, int blk, std::vector<float>& smv) {
 template <int NS>
 void run_all(const FusedParams& p, int nblk) {
   SmemLayout L{NS};
-  std::vector<float> sm(L.total());
+  constexpr int kGuard = 256;                       // canary words after the declared extent (compute-sanitizer stand-in)
+  std::vector<float> sm(L.total() + kGuard);
   for (int blk = 0; blk < nblk; ++blk) {
     // poison shared memory so that reads of never-written words show up as NaN in the results
     for (auto& v : sm) v = __builtin_nanf("");
+    for (int k = 0; k < kGuard; ++k) sm[L.total() + k] = 12345.0f + k;
     if (p.want_grad) run_block<NS, true>(p, blk, sm);
     else run_block<NS, false>(p, blk, sm);
+    for (int k = 0; k < kGuard; ++k)
+      if (sm[L.total() + k] != 12345.0f + k) { g_guard_hit = blk + 1; }
   }
 }
 
@@ -143,6 +149,7 @@ extern "C" int emu_photometric_forward(const DvsShape* sh, const DvsParams* pr, 
     total += l;
   }
   loss_total[0] = total / (float)sh->S;
+  if (g_guard_hit) { g_guard_hit = 0; return -100; }
   return DVS_OK;
 }
 
