@@ -10,8 +10,9 @@ Redwood-shaped geometrically consistent triplets.  One step = one fo
 for one batch.  Metric: warped pixels per second, B*S*N*H*W / t, whole job.  Prints ONE JSON line on rank 0.
 
   value        device-timed (CUDA events), inputs resident in HBM, L2 flushed between steps
-  e2e          same step through the public API from pinned HOST buffers: H2D of every input, D2H of the
-               losses and all gradients, inside the timed region
+  e2e          same step through the public host-resident API (dvsloss.HostLossPipeline) from pinned HOST buffers:
+               H2D of every input, D2H of the losses and all gradients, inside the timed region (batch chunks
+               overlap copy and compute on three streams; PCIe-bound)
   roofline     dominant kernel (fused_tile_kernel) timed with events around its launch inside libdvsloss.so;
                achieved = bytes_alg(B,H,W,N,S) / t   (SURVEY 8d figure, 303.9 B per full-res pixel at N=2,S=4)
   cpu_baseline the oracle port (op-for-op restatement of the reference's PyTorch path) on the host cores, on a
@@ -324,32 +325,19 @@ def run_b200(args):
     t_kernel = sum(tk) / len(tk) / 1e3 if tk else None
 
     # ---- end to end from pinned host buffers
-    d_buf = dict(target=torch.empty_like(d_in["target"]), sources=[torch.empty_like(s) for s in d_in["sources"]],
-                 disps=[torch.empty_like(d).requires_grad_(True) for d in d_in["disps"]], K=torch.empty_like(d_in["K"]),
-                 inv_K=torch.empty_like(d_in["inv_K"]), Ts=[torch.empty_like(T).requires_grad_(True) for T in d_in["Ts"]])
     h_out = dict(loss=torch.empty(1 + NSCALE).pin_memory(), gd=[torch.empty_like(d).pin_memory() for d in h_in["disps"]],
                  gT=[torch.empty_like(T).pin_memory() for T in h_in["Ts"]])
     h2d = sum(t.numel() * 4 for t in [h_in["target"], h_in["K"], h_in["inv_K"]] + h_in["sources"] + h_in["disps"] + h_in["Ts"])
     d2h = sum(t.numel() * 4 for t in [h_out["loss"]] + h_out["gd"] + h_out["gT"])
 
+    from dvsloss import HostLossPipeline
+    pipe = HostLossPipeline(B, H, W, [tuple(d.shape[2:]) for d in h_in["disps"]], NSRC, chunks=args.e2e_chunks, device=dev,
+                            noise="kernel")
+
     def e2e_step():
-        with torch.no_grad():
-            d_buf["target"].copy_(h_in["target"], non_blocking=True)
-            d_buf["K"].copy_(h_in["K"], non_blocking=True)
-            d_buf["inv_K"].copy_(h_in["inv_K"], non_blocking=True)
-            for a, b in zip(d_buf["sources"] + d_buf["disps"] + d_buf["Ts"], h_in["sources"] + h_in["disps"] + h_in["Ts"]):
-                a.copy_(b, non_blocking=True)
-        for t in d_buf["disps"] + d_buf["Ts"]:
-            t.grad = None
-        loss, per_scale = view_synthesis_loss(d_buf["disps"], d_buf["target"], d_buf["sources"], d_buf["K"],
-                                              d_buf["inv_K"], d_buf["Ts"], noise="kernel")
-        loss.backward()
-        with torch.no_grad():
-            h_out["loss"][:1].copy_(loss.detach().view(1), non_blocking=True)
-            h_out["loss"][1:].copy_(per_scale.detach(), non_blocking=True)
-            for a, t in zip(h_out["gd"] + h_out["gT"], d_buf["disps"] + d_buf["Ts"]):
-                a.copy_(t.grad, non_blocking=True)
-        torch.cuda.synchronize()
+        # public host-resident call: chunked H2D -> fused loss fwd+bwd -> D2H of the loss and every gradient, overlapped
+        # on three streams; returns when the results are in the pinned output buffers
+        pipe.run(h_in, h_out)
 
     for _ in range(3):
         e2e_step()
@@ -373,7 +361,7 @@ def run_b200(args):
         torch.cuda.empty_cache()
     train = None
     if not args.no_train:
-        del d_buf, h_out, flush
+        del pipe, h_out, flush
         torch.cuda.empty_cache()
         try:
             train = run_train(args, world, rank, local, dev)
@@ -426,6 +414,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="batch per GPU (BASELINE configs[1]: 16)")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="batch chunks of the host-resident pipeline (e2e leg)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-CUDA reference leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE configs[2])")

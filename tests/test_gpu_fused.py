@@ -294,3 +294,31 @@ def test_fused_loss_is_cuda_graph_capturable():
     assert torch.equal(out[2][0], chk[2][0])             # full-resolution disparity gradient: direct stores
     for a, b in zip(out[2][1:4], chk[2][1:4]):
         assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())      # coarse scales: atomics reorder the sums
+
+
+def test_host_pipeline_matches_device_call():
+    """dvsloss.HostLossPipeline (pinned host buffers, chunked copy/compute overlap) == one device-resident call."""
+    from dvsloss import HostLossPipeline, view_synthesis_loss
+    from dvsloss.synthetic import pose_matrix
+    dev = torch.device("cuda:0")
+    B, H, W = 8, 96, 128
+    p = make_problem(B, H, W, 2, 4, seed=31, consistent=True)
+    Ts = [pose_matrix(a.view(B, 3), t.view(B, 3), inv) for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+    pin = lambda t: t.contiguous().pin_memory()
+    h_in = dict(target=pin(p["target"]), sources=[pin(s) for s in p["sources"]], disps=[pin(d) for d in p["disps"]],
+                K=pin(p["K"]), inv_K=pin(p["inv_K"]), Ts=[pin(T) for T in Ts])
+    h_out = dict(loss=torch.empty(5).pin_memory(), gd=[torch.empty_like(d).pin_memory() for d in h_in["disps"]],
+                 gT=[torch.empty_like(T).pin_memory() for T in h_in["Ts"]])
+    pipe = HostLossPipeline(B, H, W, [tuple(d.shape[2:]) for d in h_in["disps"]], 2, chunks=4, device=dev, noise=None)
+    for _ in range(2):                                   # second run re-uses the double buffers
+        pipe.run(h_in, h_out)
+    disps = [d.to(dev).requires_grad_(True) for d in h_in["disps"]]
+    Td = [T.to(dev).requires_grad_(True) for T in h_in["Ts"]]
+    loss, per_scale = view_synthesis_loss(disps, h_in["target"].to(dev), [s.to(dev) for s in h_in["sources"]],
+                                          h_in["K"].to(dev), h_in["inv_K"].to(dev), Td, noise=None)
+    loss.backward()
+    assert abs(float(h_out["loss"][0]) - float(loss)) <= 2e-6 * abs(float(loss))
+    np.testing.assert_allclose(h_out["loss"][1:].numpy(), per_scale.detach().cpu().numpy(), rtol=2e-6)
+    for a, b in zip(h_out["gd"] + h_out["gT"], disps + Td):
+        ref = b.grad.cpu()
+        assert float((a - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-12
