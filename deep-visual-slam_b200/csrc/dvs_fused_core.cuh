@@ -644,15 +644,30 @@ DVS_HD void phase_warp(const FusedParams& p, const Tile& t, float* sm, int tid, 
     sm[L.du() + k] = du;
     float D = rcp_fast(fmaf(du, p.disp_range, p.min_disp));
     float u = (float)rx, v = (float)ry;
+    // Three explicit stages so that the 12 N tap loads of a pixel are all in flight before the first one is used:
+    // left to itself the compiler finishes source 0 (loads -> lerps -> shared-memory stores) before it starts the
+    // loads of source 1, because it cannot prove that the stores do not alias the images.
+    Proj pr[NS];
+    float tap[NS][3][4];
+    DVS_UNROLL
+    for (int i = 0; i < NS; ++i) project(c + kC_A + 12 * i, u, v, D, p.eps, p.H, p.W, pr[i]);
     DVS_UNROLL
     for (int i = 0; i < NS; ++i) {
-      Proj pr;
-      project(c + kC_A + 12 * i, u, v, D, p.eps, p.H, p.W, pr);
-      const float* im = p.src[i] + (size_t)t.b * 3 * HW;
-      sm[L.x(i, 0) + k] = bilerp(im, p.W, pr);
-      sm[L.x(i, 1) + k] = bilerp(im + HW, p.W, pr);
-      sm[L.x(i, 2) + k] = bilerp(im + 2 * HW, p.W, pr);
+      const float* im = p.src[i] + (size_t)t.b * 3 * HW + pr[i].o;
+      DVS_UNROLL
+      for (int ch = 0; ch < 3; ++ch) {
+        const float* a = im + ch * HW;
+        tap[i][ch][0] = a[0]; tap[i][ch][1] = a[1]; tap[i][ch][2] = a[p.W]; tap[i][ch][3] = a[p.W + 1];
+      }
     }
+    DVS_UNROLL
+    for (int i = 0; i < NS; ++i)
+      DVS_UNROLL
+      for (int ch = 0; ch < 3; ++ch) {
+        const float* q = tap[i][ch];
+        float top = fmaf(pr[i].tx, q[1] - q[0], q[0]), bot = fmaf(pr[i].tx, q[3] - q[2], q[2]);
+        sm[L.x(i, ch) + k] = fmaf(pr[i].ty, bot - top, top);
+      }
   }
 }
 
