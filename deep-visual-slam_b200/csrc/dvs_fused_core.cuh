@@ -613,15 +613,28 @@ DVS_HD void bilerp_slopes(const float* __restrict__ img, int W, const Proj& r, f
   dy = bot - top;
 }
 
-DVS_HD float bilinear_disp(const float* __restrict__ d, int dh, int dw, float sy, float sx, int ry, int rx) {
+// Up-sampled disparity at one fine pixel, split into "issue the loads" and "combine" so that the warp phase can fetch
+// the disparity of its NEXT pixel while it works on the current one.
+struct DispTaps {
+  float a, b, c, e, lx, ly;
+};
+DVS_HD void disp_taps_load(const float* __restrict__ d, int dh, int dw, float sy, float sx, bool direct, int ry, int rx,
+                           DispTaps& q) {
+  if (direct) {
+    q.a = q.b = q.c = q.e = d[ry * dw + rx];
+    q.lx = q.ly = 0.f;
+    return;
+  }
   int y0, y1, x0, x1;
-  float ly, lx;
-  up_taps(ry, sy, dh, y0, y1, ly);
-  up_taps(rx, sx, dw, x0, x1, lx);
-  float a = d[y0 * dw + x0], b = d[y0 * dw + x1], c = d[y1 * dw + x0], e = d[y1 * dw + x1];
-  float top = a * (1.f - lx) + b * lx;
-  float bot = c * (1.f - lx) + e * lx;
-  return top * (1.f - ly) + bot * ly;
+  up_taps(ry, sy, dh, y0, y1, q.ly);
+  up_taps(rx, sx, dw, x0, x1, q.lx);
+  q.a = d[y0 * dw + x0]; q.b = d[y0 * dw + x1]; q.c = d[y1 * dw + x0]; q.e = d[y1 * dw + x1];
+}
+DVS_HD float disp_taps_value(const DispTaps& q, bool direct) {
+  if (direct) return q.a;
+  float top = q.a * (1.f - q.lx) + q.b * q.lx;
+  float bot = q.c * (1.f - q.lx) + q.e * q.lx;
+  return top * (1.f - q.ly) + bot * q.ly;
 }
 
 // ------------------------------------------------------------------------------------------------ phase W
@@ -636,11 +649,17 @@ DVS_HD void phase_warp(const FusedParams& p, const Tile& t, float* sm, int tid, 
   const bool direct = dh == p.H && dw == p.W;
   const float scy = (float)dh / (float)p.H, scx = (float)dw / (float)p.W;
   const int* posp = reinterpret_cast<const int*>(sm + L.pos());
+  int pk = posp[tid];                                   // tid < PLANE always (NT <= PLANE)
+  DispTaps dt;
+  disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
   DVS_NOUNROLL
   for (int k = tid; k < PLANE; k += NT) {
-    int pk = posp[k];
-    int rx = pk & 0xffff, ry = pk >> 16;
-    float du = direct ? d[ry * dw + rx] : bilinear_disp(d, dh, dw, scy, scx, ry, rx);
+    const int rx = pk & 0xffff, ry = pk >> 16;
+    const float du = disp_taps_value(dt, direct);
+    if (k + NT < PLANE) {                                // disparity of the next pixel: in flight during this one
+      pk = posp[k + NT];
+      disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
+    }
     sm[L.du() + k] = du;
     float D = rcp_fast(fmaf(du, p.disp_range, p.min_disp));
     float u = (float)rx, v = (float)ry;
