@@ -352,6 +352,28 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * pix_step * args.steps / float(te.item()) / 1e9
 
+    # ---- same, with the images crossing PCIe in dataset precision (uint8, expanded to x/255 on the device: SURVEY 8f rank 2)
+    q8 = lambda t: (t * 255).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
+    h_u8 = dict(h_in)
+    h_u8["target"], h_u8["sources"] = q8(host["target"]), [q8(s_) for s_ in host["sources"]]
+    pipe8 = HostLossPipeline(B, H, W, [tuple(d.shape[2:]) for d in h_in["disps"]], NSRC, chunks=args.e2e_chunks, device=dev,
+                             noise="kernel", uint8_images=True)
+    for _ in range(3):
+        pipe8.run(h_u8, h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pipe8.run(h_u8, h_out)
+    barrier()
+    t8 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t8, op=dist.ReduceOp.MAX)
+    h2d8 = sum(t.numel() * t.element_size() for t in [h_u8["target"], h_u8["K"], h_u8["inv_K"]] + h_u8["sources"] + h_u8["disps"] + h_u8["Ts"])
+    e2e_u8 = {"value": world * pix_step * args.steps / float(t8.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d8,
+              "d2h_bytes_per_step": d2h, "note": "images quantised to 8 bits and sent as uint8 (the dataset's precision), expanded "
+              "to float32 x/255 on the device; disparities, poses and gradients stay fp32; NOT the headline e2e"}
+    del pipe8
+
     eager = None
     if rank == 0 and world == 1 and not args.no_eager:
         try:
@@ -398,7 +420,7 @@ def run_b200(args):
                            "l2": "256 MB buffer written between timed steps (outside the event pairs)", "sharding": f"batch, {world} independent rank(s), no data-path collective"},
                 "clocks": clocks, "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": 5 * args.steps, "roofline": roof, "cpu_baseline": cpu, "eager_cuda_baseline": eager,
-                "train_step": train}
+                "train_step": train, "e2e_uint8_images": e2e_u8}
         if eager and "value" in eager:
             line["eager_cuda_baseline"]["speedup_device_timed"] = value / eager["value"]
         print(json.dumps(line), flush=True)

@@ -778,3 +778,29 @@ extern "C" int dvs_pose_matrix_bwd(const float* grad_M, const float* axisangle, 
   LAUNCH_CHECK();
   return DVS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ image format
+// ToTensor of the reference's loader (vo/dataset/common.py:77): uint8 [0,255] -> float32 / 255 (IEEE division, so the
+// result is bit-identical to the host-side conversion).  Lets image batches cross PCIe as bytes.
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < n; e += stride) {
+    if (e + 4 <= n && (((uintptr_t)(src + e)) & 3) == 0 && (((uintptr_t)(dst + e)) & 15) == 0) {
+      const uchar4 v = *reinterpret_cast<const uchar4*>(src + e);
+      *reinterpret_cast<float4*>(dst + e) = make_float4(__fdiv_rn((float)v.x, 255.f), __fdiv_rn((float)v.y, 255.f),
+                                                        __fdiv_rn((float)v.z, 255.f), __fdiv_rn((float)v.w, 255.f));
+    } else {
+      for (int64_t k = e; k < n && k < e + 4; ++k) dst[k] = __fdiv_rn((float)src[k], 255.f);
+    }
+  }
+}
+extern "C" int dvs_u8_to_f32(const uint8_t* src, float* dst, int64_t n, void* stream) {
+  if (!src || !dst || n < 0) return DVS_EINVAL;
+  if (n == 0) return DVS_OK;
+  int64_t want = (n / 4 + 255) / 256;
+  int blocks = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+  u8_to_f32_kernel<<<blocks, 256, 0, ST(stream)>>>(src, dst, n);
+  LAUNCH_CHECK();
+  return DVS_OK;
+}
+

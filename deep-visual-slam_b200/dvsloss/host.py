@@ -14,15 +14,17 @@ from typing import Dict, List, Sequence
 import torch
 
 from .functional import view_synthesis_loss
+from .ops import images_u8_to_f32
 
 
 class HostLossPipeline:
     def __init__(self, B: int, H: int, W: int, disp_sizes: Sequence[Sequence[int]], num_sources: int = 2, chunks: int = 4,
-                 device=None, **loss_kwargs):
+                 device=None, uint8_images: bool = False, **loss_kwargs):
         if B % chunks:
             raise ValueError("the batch must split into equal chunks (batch means must stay batch means)")
         self.B, self.Bc, self.chunks, self.N, self.S = B, B // chunks, chunks, num_sources, len(disp_sizes)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.uint8_images = uint8_images        # images arrive as bytes (dataset precision) and are expanded on the device
         self.kw = dict(loss_kwargs)
         self.kw.setdefault("noise", "kernel")
         Bc, d = self.Bc, self.dev
@@ -32,7 +34,8 @@ class HostLossPipeline:
             self.sets.append(dict(
                 target=mk(Bc, 3, H, W), sources=[mk(Bc, 3, H, W) for _ in range(num_sources)],
                 disps=[mk(Bc, 1, h, w).requires_grad_(True) for h, w in disp_sizes], K=mk(Bc, 4, 4), inv_K=mk(Bc, 4, 4),
-                Ts=[mk(Bc, 4, 4).requires_grad_(True) for _ in range(num_sources)], losses=mk(1 + self.S)))
+                Ts=[mk(Bc, 4, 4).requires_grad_(True) for _ in range(num_sources)], losses=mk(1 + self.S),
+                raw=[torch.empty(Bc, 3, H, W, dtype=torch.uint8, device=d) for _ in range(1 + num_sources)] if uint8_images else None))
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(d) for _ in range(3))
         self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
         self.ev_run = [torch.cuda.Event() for _ in range(chunks)]
@@ -53,10 +56,18 @@ class HostLossPipeline:
             with torch.cuda.stream(self.s_in), torch.no_grad():
                 if c >= 2:
                     self.s_in.wait_event(self.ev_out[c - 2])          # the set is free once its gradients left the device
-                S_["target"].copy_(h_in["target"][sl], non_blocking=True)
+                if self.uint8_images:
+                    for a, b in zip(S_["raw"], [h_in["target"]] + h_in["sources"]):
+                        a.copy_(b[sl], non_blocking=True)
+                    for raw, img in zip(S_["raw"], [S_["target"]] + S_["sources"]):
+                        images_u8_to_f32(raw, img)                 # x / 255 on the copy stream, exact
+                else:
+                    S_["target"].copy_(h_in["target"][sl], non_blocking=True)
+                    for a, b in zip(S_["sources"], h_in["sources"]):
+                        a.copy_(b[sl], non_blocking=True)
                 S_["K"].copy_(h_in["K"][sl], non_blocking=True)
                 S_["inv_K"].copy_(h_in["inv_K"][sl], non_blocking=True)
-                for a, b in zip(S_["sources"] + S_["disps"] + S_["Ts"], h_in["sources"] + h_in["disps"] + h_in["Ts"]):
+                for a, b in zip(S_["disps"] + S_["Ts"], h_in["disps"] + h_in["Ts"]):
                     a.copy_(b[sl], non_blocking=True)
                 self.ev_in[c].record(self.s_in)
             with torch.cuda.stream(self.s_run):

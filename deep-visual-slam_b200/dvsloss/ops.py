@@ -333,3 +333,19 @@ class _PoseMatrix(torch.autograd.Function):
 def transformation_from_parameters(axisangle: torch.Tensor, translation: torch.Tensor, invert: bool = False) -> torch.Tensor:
     """vo/learner_func.py:29-46: axisangle, translation [B,1,3] -> 4x4 (inverted when `invert`)."""
     return _PoseMatrix.apply(axisangle, translation, bool(invert))
+
+
+def images_u8_to_f32(src: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """uint8 image batch -> float32 in [0,1], exactly ``ToTensor`` (x / 255) of the reference's loader
+    (vo/dataset/common.py:77), on the device; ``out`` may be a preallocated float32 tensor of the same shape."""
+    if not src.is_cuda or src.dtype != torch.uint8:
+        raise DvsError("images_u8_to_f32 needs a CUDA uint8 tensor (no CPU fallback by design)")
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    if out.shape != src.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != src.device:
+        raise DvsError("out must be a contiguous float32 tensor of the input's shape on the same device")
+    with torch.cuda.device(src.device):
+        check(lib().dvs_u8_to_f32(src.data_ptr(), out.data_ptr(), src.numel(), stream_ptr(src.device)), "dvs_u8_to_f32")
+    return out
+

@@ -186,6 +186,10 @@ int dvs_pose_matrix_fwd(const float* axisangle, const float* translation, float*
 int dvs_pose_matrix_bwd(const float* grad_M, const float* axisangle, const float* translation,
                         float* grad_axisangle, float* grad_translation, int B, int invert, void* stream);
 
+/* ToTensor of the reference's loader (vo/dataset/common.py:77): dst[i] = (float)src[i] / 255 for n bytes; exact
+ * (IEEE division), so uint8 image batches can cross PCIe as bytes and be expanded on the device. */
+int dvs_u8_to_f32(const uint8_t* src, float* dst, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -322,3 +322,32 @@ def test_host_pipeline_matches_device_call():
     for a, b in zip(h_out["gd"] + h_out["gT"], disps + Td):
         ref = b.grad.cpu()
         assert float((a - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-12
+
+
+def test_host_pipeline_uint8_images():
+    """Images crossing PCIe as bytes (dataset precision) and expanded on the device give exactly the result of
+    float images that hold the same 8-bit values."""
+    from dvsloss import HostLossPipeline
+    from dvsloss.synthetic import pose_matrix
+    dev = torch.device("cuda:0")
+    B, H, W = 4, 64, 96
+    p = make_problem(B, H, W, 2, 4, seed=33, consistent=True)
+    Ts = [pose_matrix(a.view(B, 3), t.view(B, 3), inv) for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+    q8 = lambda t: (t * 255).round().clamp(0, 255).to(torch.uint8)
+    pin = lambda t: t.contiguous().pin_memory()
+    u8 = dict(target=pin(q8(p["target"])), sources=[pin(q8(s)) for s in p["sources"]])
+    common = dict(disps=[pin(d) for d in p["disps"]], K=pin(p["K"]), inv_K=pin(p["inv_K"]), Ts=[pin(T) for T in Ts])
+    f32 = dict(target=pin(u8["target"].float().div(255)), sources=[pin(s.float().div(255)) for s in u8["sources"]])
+    outs = []
+    for imgs, flag in ((u8, True), (f32, False)):
+        h_out = dict(loss=torch.empty(5).pin_memory(), gd=[torch.empty_like(d).pin_memory() for d in common["disps"]],
+                     gT=[torch.empty_like(T).pin_memory() for T in common["Ts"]])
+        pipe = HostLossPipeline(B, H, W, [tuple(d.shape[2:]) for d in common["disps"]], 2, chunks=2, device=dev, noise=None,
+                                uint8_images=flag)
+        pipe.run({**common, **imgs}, h_out)
+        outs.append(h_out)
+    assert torch.equal(outs[0]["loss"], outs[1]["loss"])
+    for a, b in zip(outs[0]["gT"], outs[1]["gT"]):
+        assert torch.equal(a, b)
+    assert torch.equal(outs[0]["gd"][0], outs[1]["gd"][0])
+

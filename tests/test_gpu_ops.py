@@ -273,3 +273,17 @@ def test_ops_reject_cpu_tensors():
         disp_to_depth(torch.rand(1, 1, 4, 4), 0.1, 10.0)
     with pytest.raises(DvsError):
         SSIM()(torch.rand(1, 3, 8, 8), torch.rand(1, 3, 8, 8))
+
+
+def test_images_u8_to_f32_is_exactly_totensor():
+    """uint8 -> float32 / 255 on the device equals the host-side ToTensor arithmetic bit for bit (all 256 values, odd sizes)."""
+    from dvsloss.ops import images_u8_to_f32
+    for shape in [(2, 3, 33, 47), (1, 3, 8, 8), (1, 1, 1, 3), (256,)]:
+        n = int(np.prod(shape))
+        src = (torch.arange(n, dtype=torch.int64) * 37 % 256).to(torch.uint8).view(*shape)
+        got = images_u8_to_f32(src.to(DEV))
+        ref = src.to(torch.float32).div(255)
+        assert torch.equal(got.cpu(), ref)
+    with pytest.raises(Exception):
+        images_u8_to_f32(torch.zeros(4, dtype=torch.uint8))
+
