@@ -51,7 +51,6 @@ constexpr int RH2 = TH + 2;            // R2 height
 constexpr int PW = RW2;                // plane row stride (floats)
 constexpr int PLANE = RH2 * PW;        // 1156 floats; plane index of R2 pixel (ly,lx) is (ly+1)*PW + lx+1
 constexpr int NT = 256;                // threads per CTA
-constexpr int NIT = (PLANE + NT - 1) / NT;   // R2 pixels per thread in the load / warp phases (5)
 constexpr int kMeanBlocks = 16;        // partial sums per (scale, batch item) in the disparity-mean pre-pass
 constexpr float kC1 = 0.0001f, kC2 = 0.0009f;
 constexpr float kK1 = 81.0f * 0.0001f, kK2 = 81.0f * 0.0009f;   // SSIM constants on 9-sums
@@ -705,12 +704,15 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
   const int HW = p.H * p.W;
   const int fl = st.flags;
 
+  // N <= 2 with gradients: one statistics pass, target-side sums shared between the sources (quad_reproj_coefs).
+  // N  > 2 with gradients: one source at a time (rolled loop below), its coefficient fields go to F where it takes the lead.
   constexpr bool kSinglePass = GRAD && NS <= 2;
+  constexpr bool kRolled = GRAD && NS > 2;
   const float kF = p.ssim_w / (3.0f * (float)p.B * (float)HW);
   float r[NS][4];
   float hold[3][3][4];
-  if (kSinglePass) quad_reproj_coefs<NS>(sm, L.x(0, 0), L.y(0), L.f(0), base, sw3, lw3, kF, r, hold);
-  else quad_reproj<NS, false>(sm, L.x(0, 0), L.y(0), base, sw3, lw3, r, nullptr, nullptr);
+  if constexpr (kSinglePass) quad_reproj_coefs<NS>(sm, L.x(0, 0), L.y(0), L.f(0), base, sw3, lw3, kF, r, hold);
+  else if constexpr (!kRolled) quad_reproj<NS, false>(sm, L.x(0, 0), L.y(0), base, sw3, lw3, r, nullptr, nullptr);
 
   float best[4];
   int tag[4], chan[4];
@@ -742,10 +744,38 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
       }
   }
   const int off = p.auto_mask ? NS : 0;
-  DVS_UNROLL
-  for (int i = 0; i < NS; ++i)
-    for (int j = 0; j < 4; ++j)
-      if (r[i][j] < best[j]) { best[j] = r[i][j]; chan[j] = off + i; tag[j] = i; }
+  if constexpr (kRolled) {
+    DVS_NOUNROLL
+    for (int i = 0; i < NS; ++i) {
+      float rs[4] = {0.f, 0.f, 0.f, 0.f}, rl[4] = {0.f, 0.f, 0.f, 0.f};
+      DVS_UNROLL
+      for (int c = 0; c < 3; ++c) {
+        YN yn;
+        XS xs;
+        load_yn(sm + L.y(c), base, yn);
+        stats_x(sm + L.x(0, c) + i * 3 * PLANE, base, yn, xs);
+        for (int j = 0; j < 4; ++j) {
+          rs[j] += ssim_coefs(xs.sx[j], xs.sxx[j], xs.sxy[j], yn.sy[j], yn.ysq[j], yn.ty[j], kF, hold[c][0][j], hold[c][1][j],
+                              hold[c][2][j]);
+          rl[j] += fabsf(yn_at(yn, j + 1, 1) - xs.xc[j]);
+        }
+      }
+      for (int j = 0; j < 4; ++j) {
+        const float rij = fmaf(sw3, rs[j], lw3 * rl[j]);
+        if (rij < best[j]) {
+          best[j] = rij; chan[j] = off + i; tag[j] = i;
+          const int o = L.f(0) + base + j * PW;
+          for (int c = 0; c < 3; ++c)
+            for (int f = 0; f < 3; ++f) sm[o + (c * 3 + f) * PLANE] = hold[c][f][j];
+        }
+      }
+    }
+  } else {
+    DVS_UNROLL
+    for (int i = 0; i < NS; ++i)
+      for (int j = 0; j < 4; ++j)
+        if (r[i][j] < best[j]) { best[j] = r[i][j]; chan[j] = off + i; tag[j] = i; }
+  }
 
   // loss sums, selection output, tags
   int tags = 0;
@@ -797,29 +827,6 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
       for (int c = 0; c < 3; ++c)
         for (int f = 0; f < 3; ++f) sm[o + (c * 3 + f) * PLANE] = hold[c][f][j];
     }
-  } else {
-  // more than two sources: coefficient fields of the selected source(s) of these pixels -> F planes (second pass)
-  DVS_UNROLL
-  for (int i = 0; i < NS; ++i) {
-    bool any = false;
-    for (int j = 0; j < 4; ++j) any = any || (tag[j] == i);
-    if (!any) continue;
-    for (int c = 0; c < 3; ++c) {
-      YN yn;
-      XS xs;
-      load_yn(sm + L.y(c), base, yn);
-      stats_x(sm + L.x(i, c), base, yn, xs);
-      for (int j = 0; j < 4; ++j) {
-        if (tag[j] != i) continue;
-        float al, be, ga;
-        ssim_coefs(xs.sx[j], xs.sxx[j], xs.sxy[j], yn.sy[j], yn.ysq[j], yn.ty[j], kF, al, be, ga);
-        int o = base + j * PW;
-        sm[L.f(c * 3 + 0) + o] = al;
-        sm[L.f(c * 3 + 1) + o] = be;
-        sm[L.f(c * 3 + 2) + o] = ga;
-      }
-    }
-  }
   }
 }
 
