@@ -3,6 +3,7 @@
 // Launch sequence of dvs_photometric_forward (all on the caller's stream, no host sync):
 //   1. mean_partial_kernel   partial sums of the up-sampled disparity per (scale, image)      [reads disp once]
 //   2. fused_tile_kernel     one CTA per 30x30 tile x image, all scales, loss sums (+ unit gradients)
+//   2b. gather_gdisp_kernel  unit gradients of the up-sampled scales: fixed-order sum of the tiles' coarse boxes
 //   3. finish_kernel         per (scale, image): fixed-order reduction of the per-CTA partials, pose
 //                            gradient dL/dT = K^T dL/dP, smoothness mean-coupling coefficient
 //   4. final_kernel          loss/s and loss
@@ -11,11 +12,15 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/dvsloss.h"
 #include "dvs_fused_core.cuh"
 #include "dvs_host.h"
 
 namespace dvs {
+
+constexpr int kMaxDevices = 64;
 
 // ------------------------------------------------------------------------------------------------ 1. disparity mean
 // mean(up-sample(d)) is a fixed linear functional of d: sum_ij rw[i] cw[j] d[i,j] / (H W); for the
@@ -103,6 +108,20 @@ __global__ void __launch_bounds__(NT, (NS <= 2 ? 2 : 1)) fused_tile_kernel(const
     // no barrier needed here: the next phase_warp writes only X/DU, which nobody reads any more
     // (adjoint_cols / reduce_stage2 read the F region, next written after the following barrier) ...
     // ... except adjoint_rows' input DU: all threads passed the barrier after adjoint_rows already.
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 2b. coarse gradients
+// unit gradients of the up-sampled scales: one thread per disparity element gathers the tile boxes (gather_gdisp).
+__global__ void __launch_bounds__(256) gather_gdisp_kernel(const __grid_constant__ FusedParams p) {
+  const int s = blockIdx.y;
+  const int dh = p.dh[s], dw = p.dw[s];
+  if (dh == p.H && dw == p.W) return;
+  const int n = p.B * dh * dw;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int b = e / (dh * dw), r = e - b * dh * dw;
+    const int I = r / dw, J = r - I * dw;
+    p.gdisp[s][e] = gather_gdisp(p, s, b, I, J);
   }
 }
 
@@ -239,8 +258,9 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(BackwardParams q) {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t mean_part, part, perimg, uT, coup, lossbuf, total;
+  size_t mean_part, part, perimg, uT, coup, lossbuf, cpart, total;
   int tiles_x, tiles_y, nblk;
+  int cstride, coff[kMaxS], cbw[kMaxS];
 };
 static WsLayout ws_layout(const DvsShape& sh) {
   WsLayout w;
@@ -254,6 +274,14 @@ static WsLayout ws_layout(const DvsShape& sh) {
   w.uT = o;        o = align_up(o + sizeof(float) * sh.S * sh.N * sh.B * 16, 256);   // used by backward_recompute
   w.coup = o;      o = align_up(o + sizeof(float) * sh.S * sh.B, 256);
   w.lossbuf = o;   o = align_up(o + sizeof(float) * 8, 256);
+  w.cstride = 0;
+  for (int s = 0; s < sh.S; ++s) {
+    const bool direct = sh.dh[s] == sh.H && sh.dw[s] == sh.W;
+    w.coff[s] = w.cstride;
+    w.cbw[s] = direct ? 0 : coarse_box_extent(sh.dw[s], sh.W);
+    w.cstride += direct ? 0 : coarse_box_extent(sh.dh[s], sh.H) * w.cbw[s];
+  }
+  w.cpart = o;     o = align_up(o + sizeof(float) * (size_t)w.nblk * w.cstride, 256);
   w.total = o;
   return w;
 }
@@ -273,11 +301,15 @@ template <int NS, bool GRAD>
 static cudaError_t launch_tile(const FusedParams& p, int nblk, cudaStream_t st) {
   SmemLayout L{NS};
   size_t bytes = (size_t)L.total() * sizeof(float);
-  static bool configured = false;   // per instantiation
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fused_tile_kernel<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  // the dynamic shared-memory opt-in is a per-device attribute of the function: one flag per (instantiation, device)
+  static std::atomic<bool> configured[kMaxDevices];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices || !configured[dev].load(std::memory_order_acquire)) {
+    e = cudaFuncSetAttribute(fused_tile_kernel<NS, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < kMaxDevices) configured[dev].store(true, std::memory_order_release);
   }
   fused_tile_kernel<NS, GRAD><<<nblk, NT, bytes, st>>>(p);
   return cudaGetLastError();
@@ -298,9 +330,15 @@ static cudaError_t dispatch_tile(const FusedParams& p, int nblk, cudaStream_t st
 }
 
 // Optional timing of the dominant kernel with events on the caller's stream (bench.py roofline leg).
-static bool g_profile = false;
-static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-static bool g_ev_valid = false;
+// The events belong to the device that was current when they were created: one pair per device, and the read-back
+// reports the pair of the device the last profiled launch ran on.
+static std::atomic<bool> g_profile{false};
+struct ProfileEvents {
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool valid = false;
+};
+static ProfileEvents g_prof[kMaxDevices];
+static std::atomic<int> g_prof_dev{-1};
 
 static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* const* disp, const float* target,
                        const float* const* src, const float* K, const float* inv_K, const float* const* T,
@@ -342,25 +380,42 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
   p.mean_part = reinterpret_cast<float*>(base + w.mean_part);
   p.part = reinterpret_cast<float*>(base + w.part);
   p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y;
-
-  if (want_grad)
-    for (int s = 0; s < sh->S; ++s)
-      if (!(sh->dh[s] == sh->H && sh->dw[s] == sh->W))
-        DVS_CUDA_TRY(cudaMemsetAsync(ugrad_disp[s], 0, sizeof(float) * (size_t)sh->B * sh->dh[s] * sh->dw[s], st));
+  p.cpart = reinterpret_cast<float*>(base + w.cpart);
+  p.cstride = w.cstride;
+  for (int s = 0; s < sh->S; ++s) { p.coff[s] = w.coff[s]; p.cbw[s] = w.cbw[s]; }
 
   mean_partial_kernel<<<dim3(kMeanBlocks, sh->B, sh->S), 256, 0, st>>>(p, reinterpret_cast<float*>(base + w.mean_part));
   DVS_CUDA_TRY(cudaGetLastError());
-  if (g_profile) {
-    if (!g_ev0) {
-      DVS_CUDA_TRY(cudaEventCreate(&g_ev0));
-      DVS_CUDA_TRY(cudaEventCreate(&g_ev1));
+  ProfileEvents* pe = nullptr;
+  if (g_profile.load()) {
+    int dev = 0;
+    DVS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < kMaxDevices) {
+      pe = &g_prof[dev];
+      if (!pe->ev0) {
+        DVS_CUDA_TRY(cudaEventCreate(&pe->ev0));
+        DVS_CUDA_TRY(cudaEventCreate(&pe->ev1));
+      }
+      DVS_CUDA_TRY(cudaEventRecord(pe->ev0, st));
     }
-    DVS_CUDA_TRY(cudaEventRecord(g_ev0, st));
   }
   DVS_CUDA_TRY(dispatch_tile(p, w.nblk, st));
-  if (g_profile) {
-    DVS_CUDA_TRY(cudaEventRecord(g_ev1, st));
-    g_ev_valid = true;
+  if (pe) {
+    DVS_CUDA_TRY(cudaEventRecord(pe->ev1, st));
+    pe->valid = true;
+    int dev = 0;
+    DVS_CUDA_TRY(cudaGetDevice(&dev));
+    g_prof_dev.store(dev);
+  }
+
+  if (want_grad && w.cstride > 0) {
+    size_t nmax = 0;
+    for (int s = 0; s < sh->S; ++s)
+      if (w.cbw[s]) nmax = nmax > (size_t)sh->B * sh->dh[s] * sh->dw[s] ? nmax : (size_t)sh->B * sh->dh[s] * sh->dw[s];
+    int gx = (int)((nmax + 255) / 256);
+    if (gx > 148 * 16) gx = 148 * 16;
+    gather_gdisp_kernel<<<dim3(gx, sh->S), 256, 0, st>>>(p);
+    DVS_CUDA_TRY(cudaGetLastError());
   }
 
   FinishParams f{};
@@ -404,16 +459,18 @@ static int run_backward(const DvsShape* sh, const float* g, const float* const* 
 using namespace dvs;
 
 extern "C" int dvs_set_profiling(int enabled) {
-  g_profile = enabled != 0;
-  g_ev_valid = false;
+  g_profile.store(enabled != 0);
+  for (int d = 0; d < kMaxDevices; ++d) g_prof[d].valid = false;
+  g_prof_dev.store(-1);
   return DVS_OK;
 }
 
 extern "C" int dvs_last_tile_kernel_ms(float* ms) {
   if (!ms) return DVS_EINVAL;
-  if (!g_ev_valid) return DVS_EINVAL;
-  DVS_CUDA_TRY(cudaEventSynchronize(g_ev1));
-  DVS_CUDA_TRY(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+  const int dev = g_prof_dev.load();
+  if (dev < 0 || !g_prof[dev].valid) return DVS_EINVAL;
+  DVS_CUDA_TRY(cudaEventSynchronize(g_prof[dev].ev1));
+  DVS_CUDA_TRY(cudaEventElapsedTime(ms, g_prof[dev].ev0, g_prof[dev].ev1));
   return DVS_OK;
 }
 

@@ -73,13 +73,22 @@ struct FusedParams {
   int auto_mask;
   int want_grad;
   // outputs
-  float* gdisp[kMaxS];             // unit gradients d loss/s / d disp[s] (accumulated; pre-zeroed when up-sampled)
+  float* gdisp[kMaxS];             // unit gradients d loss/s / d disp[s] (written directly when full resolution,
+                                   // else gathered from cpart by gather_gdisp in a fixed order)
   unsigned char* sel[kMaxS];       // optional argmin maps
   // workspace
   const float* mean_part;          // [S][B][kMeanBlocks] partial sums of the up-sampled disparity
   float* part;                     // [nblk][S][3 + 12N] per-block partial sums
+  // up-sampled scales: every tile leaves the adjoint of the bilinear up-sample restricted to its own pixels as a small
+  // coarse box (rows i0..i1 x columns j0..j1 of disp[s], row pitch cbw[s]) at cpart[blk * cstride + coff[s]]
+  float* cpart;
+  int cstride, coff[kMaxS], cbw[kMaxS];
   int tiles_x, tiles_y;
 };
+
+// Upper bound of the coarse rows (columns) touched by the 30 fine rows (columns) of one tile: the clamped source
+// coordinate spans 29 * in/out, plus the two taps.
+DVS_HD int coarse_box_extent(int in, int out) { int e = (29 * in) / out + 3; return e < in ? e : in; }
 
 // per-block partial sums: [0] photometric, [1] smooth-x, [2] smooth-y, then per source 12 pose moments
 //   M[r*4 + 0..2] = sum g_c[r] * D * (u, v, 1),  M[r*4 + 3] = sum g_c[r]      (r = row of the 3x4 projection)
@@ -900,6 +909,9 @@ DVS_HD void phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, 
         float x = X[j * PW], y = Y[j * PW];
         float g = fmaf(2.f * x, pooled[1][j], fmaf(y, pooled[2][j], pooled[0][j]));
         if (tg[j + 1][1] == i) g -= l1k * sgn(y - x);
+#if defined(DVS_FAULT_GRAD_SCALE)
+        g *= DVS_FAULT_GRAD_SCALE;   // fault-injection builds of the tests only: the parity gates must catch a 1 % error
+#endif
         G[c][j] = g;
       }
     }
@@ -1000,13 +1012,6 @@ DVS_HD void adjoint_rows(const FusedParams& p, const Tile& t, float* sm, int tid
     sm[L.tbuf() + y * kTbufCols + Jl] = acc;
   }
 }
-DVS_HD void atomic_add_f32(float* a, float v) {
-#if defined(__CUDA_ARCH__)
-  atomicAdd(a, v);
-#else
-  *a += v;
-#endif
-}
 template <int NS>
 DVS_HD void adjoint_cols(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   SmemLayout L{NS};
@@ -1024,8 +1029,37 @@ DVS_HD void adjoint_cols(const FusedParams& p, const Tile& t, float* sm, int tid
     float acc = 0.f;
     for (int y = ya; y <= yb; ++y)
       acc = fmaf(tap_weight(y, scale, p.dh[s], I), sm[L.tbuf() + (y - fy0) * kTbufCols + Jl], acc);
-    atomic_add_f32(p.gdisp[s] + ((size_t)t.b * p.dh[s] + I) * p.dw[s] + j0 + Jl, acc);
+    p.cpart[(size_t)t.blk * p.cstride + p.coff[s] + Il * p.cbw[s] + Jl] = acc;     // own box slot: no atomics
   }
+}
+
+// d loss/s / d disp[s][b, I, J] of an up-sampled scale: the sum, in a fixed order (tile row, then tile column), of
+// the boxes of the <= 4 (integer ratios; a few more otherwise) tiles whose pixels have a tap on (I, J).  Bit-reproducible.
+DVS_HD float gather_gdisp(const FusedParams& p, int s, int b, int I, int J) {
+  const int dh = p.dh[s], dw = p.dw[s];
+  const float sy = (float)dh / (float)p.H, sx = (float)dw / (float)p.W;
+  int ya, yb, xa, xb;
+  fine_range(I, (p.H % dh == 0) ? p.H / dh : 0, (float)p.H / (float)dh, ya, yb);
+  fine_range(J, (p.W % dw == 0) ? p.W / dw : 0, (float)p.W / (float)dw, xa, xb);
+  const int ty0 = imax(ya, 0) / PITCH_Y, ty1 = imin(imin(yb, p.H - 1) / PITCH_Y, p.tiles_y - 1);
+  const int tx0 = imax(xa, 0) / PITCH_X, tx1 = imin(imin(xb, p.W - 1) / PITCH_X, p.tiles_x - 1);
+  float acc = 0.f;
+  for (int ty = ty0; ty <= ty1; ++ty) {
+    int i0, i1, a, bb;
+    float l;
+    up_taps(ty * PITCH_Y, sy, dh, i0, bb, l);
+    up_taps(imin(ty * PITCH_Y + PITCH_Y - 1, p.H - 1), sy, dh, a, i1, l);
+    if (I < i0 || I > i1) continue;
+    for (int tx = tx0; tx <= tx1; ++tx) {
+      int j0, j1;
+      up_taps(tx * PITCH_X, sx, dw, j0, bb, l);
+      up_taps(imin(tx * PITCH_X + PITCH_X - 1, p.W - 1), sx, dw, a, j1, l);
+      if (J < j0 || J > j1) continue;
+      const size_t blk = ((size_t)b * p.tiles_y + ty) * p.tiles_x + tx;
+      acc += p.cpart[blk * p.cstride + p.coff[s] + (I - i0) * p.cbw[s] + (J - j0)];
+    }
+  }
+  return acc;
 }
 
 // ------------------------------------------------------------------------------------------------ block reduction

@@ -13,7 +13,8 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdvsloss.so")
+# DVSLOSS_LIB selects another build of the same library (kernel experiments, fault-injection builds of the tests)
+LIB_PATH = os.environ.get("DVSLOSS_LIB") or os.path.join(_HERE, "libdvsloss.so")
 
 MAX_SCALES = 4
 MAX_SOURCES = 4

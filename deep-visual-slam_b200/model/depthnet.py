@@ -4,6 +4,8 @@ Same constructor and output dict as the reference (model/depthnet.py:16-90): ``(
 """
 from __future__ import annotations
 
+from collections import OrderedDict
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -22,25 +24,30 @@ class DepthNet(nn.Module):
         self.encoder = ResnetEncoder(num_layers, pretrained, num_input_images)
         self.num_ch_enc = self.encoder.num_ch_enc
         self.num_ch_dec = np.array([16, 32, 64, 128, 256])
-        self.up0, self.up1, self.heads = nn.ModuleDict(), nn.ModuleDict(), nn.ModuleDict()
+        # Registration order and attribute names are the checkpoint format (vo/train.py:83-98 loads
+        # ``depth_net_epoch_N.pth`` with keys ``decoder.<k>.conv.conv.*`` / ``decoder.<k>.conv.*``): the blocks are
+        # registered as ``self.decoder`` in the order (upconv,4,0), (upconv,4,1), ..., (upconv,0,1), dispconv 0..3
+        # (reference: model/depthnet.py:41-60) and looked up through the tuple-keyed ``self.convs``.
+        self.convs = OrderedDict()
         for i in range(4, -1, -1):
             c_in = self.num_ch_enc[-1] if i == 4 else self.num_ch_dec[i + 1]
-            self.up0[str(i)] = ConvBlock(c_in, self.num_ch_dec[i])
+            self.convs[("upconv", i, 0)] = ConvBlock(c_in, self.num_ch_dec[i])
             c_in = self.num_ch_dec[i] + (self.num_ch_enc[i - 1] if use_skips and i > 0 else 0)
-            self.up1[str(i)] = ConvBlock(c_in, self.num_ch_dec[i])
+            self.convs[("upconv", i, 1)] = ConvBlock(c_in, self.num_ch_dec[i])
         for s in self.scales:
-            self.heads[str(s)] = Conv3x3(self.num_ch_dec[s], num_output_channels)
+            self.convs[("dispconv", s)] = Conv3x3(self.num_ch_dec[s], num_output_channels)
+        self.decoder = nn.ModuleList(self.convs.values())
 
     def forward(self, input_data: torch.Tensor) -> dict:
         feats = self.encoder(input_data)
         outputs = {}
         x = feats[-1]
         for i in range(4, -1, -1):
-            x = upsample(self.up0[str(i)](x))
+            x = upsample(self.convs[("upconv", i, 0)](x))
             if self.use_skips and i > 0:
                 x = torch.cat([x, feats[i - 1]], 1)
-            x = self.up1[str(i)](x)
+            x = self.convs[("upconv", i, 1)](x)
             if i in self.scales:
-                outputs[("disp", i)] = torch.sigmoid(self.heads[str(i)](x))
+                outputs[("disp", i)] = torch.sigmoid(self.convs[("dispconv", i)](x))
         self.outputs = outputs
         return outputs

@@ -10,8 +10,10 @@ Constructor and ``process_batch(sample) -> (outputs, losses)`` follow the refere
   * ``outputs``: what DepthNet returns (``("disp", s)``) plus ``("axisangle"|"translation"|"cam_T_cam", 0, f)``
     and ``"identity_selection/s"``.  The full-resolution intermediates the reference materialises on every
     step (``("disp_up", s)``, ``("depth", s)``, ``("sample", f, s)``, ``("color", f, s)``,
-    ``("color_identity", f, s)`` -- 0.94 GB at B=16) are *not* produced on the hot path; callers that plot
-    them (vo/utils/plot_utils.py:40-47, every 1000 steps) call ``materialize_outputs(sample, outputs)``.
+    ``("color_identity", f, s)`` -- 0.94 GB at B=16) are *not* produced on the hot path: ``outputs`` is a
+    ``LazyOutputs`` dict that computes them (granular kernels, ``no_grad``) the first time one of those keys is
+    read, so the plotting call of the unchanged trainer (vo/train.py:268-279 -> vo/utils/plot_utils.py:40-47,
+    step 0 and every 1000th) finds them and ordinary steps pay nothing.
 
 Hot path: DepthNet + PoseNet (stock PyTorch) -> ``dvsloss.view_synthesis_loss`` (one fused launch computing
 every scale and source, the losses and their gradients) instead of the ~2 160 ATen launches of
@@ -34,6 +36,50 @@ if _PKG not in sys.path:
 from dvsloss import view_synthesis_loss  # noqa: E402
 from dvsloss import ops as _ops  # noqa: E402
 from model.layers import BackprojectDepth, Project3D, SSIM  # noqa: E402
+
+
+class LazyOutputs(dict):
+    """``outputs`` of ``process_batch``.  A plain dict for everything the step computed; the full-resolution side
+    products of vo/learner_new.py:142,146,158,165-172 are produced on first access (``d[key]``, ``d.get(key)``,
+    ``key in d``) by the bound filler and then stay in the dict like any other entry."""
+
+    LAZY_KINDS = ("disp_up", "depth", "sample", "color", "color_identity")
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._filler = None
+
+    def bind(self, filler) -> "LazyOutputs":
+        self._filler = filler
+        return self
+
+    def _is_lazy(self, key) -> bool:
+        return self._filler is not None and isinstance(key, tuple) and len(key) > 1 and key[0] in self.LAZY_KINDS
+
+    def __missing__(self, key):
+        if self._is_lazy(key):
+            filler, self._filler = self._filler, None
+            filler(self)
+            if dict.__contains__(self, key):
+                return dict.__getitem__(self, key)
+        raise KeyError(key)
+
+    def __contains__(self, key) -> bool:
+        if dict.__contains__(self, key):
+            return True
+        if self._is_lazy(key):
+            try:
+                self[key]
+            except KeyError:
+                return False
+            return True
+        return False
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
 
 
 class MonodepthTrainer:
@@ -78,10 +124,11 @@ class MonodepthTrainer:
         for key, val in sample.items():
             if isinstance(val, torch.Tensor):
                 sample[key] = val.to(self.device, non_blocking=True)
-        outputs: dict = self.depth_net(sample[("target_image", 0)])
+        outputs = LazyOutputs(self.depth_net(sample[("target_image", 0)]))
         outputs.update(self._predict_poses(sample))
         if self.fused:
             losses = self._view_synthesis(sample, outputs)
+            outputs.bind(lambda out: self.materialize_outputs(sample, out))
         else:
             self._generate_images_pred(sample, outputs)
             losses = self._compute_losses(sample, outputs)
@@ -168,8 +215,9 @@ class MonodepthTrainer:
     @torch.no_grad()
     def materialize_outputs(self, sample: Dict, outputs: Dict) -> Dict:
         """Fill the full-resolution side products the plotting code reads (("depth", s), ("color", f, s), ...)."""
-        det = {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in outputs.items()}
+        det = {k: (v.detach().float() if isinstance(v, torch.Tensor) else v) for k, v in dict.items(outputs)}
         self._generate_images_pred(sample, det)
         for k, v in det.items():
-            outputs.setdefault(k, v)
+            if not dict.__contains__(outputs, k):
+                dict.__setitem__(outputs, k, v)
         return outputs

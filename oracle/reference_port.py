@@ -195,6 +195,9 @@ def view_synthesis_loss(disps: Sequence[torch.Tensor], target: torch.Tensor,
                                                       min_depth, max_depth)
             reproj.append(reprojection_loss(color, target, ssim_ratio))
             if keep:
+                if disp_up.requires_grad:
+                    disp_up.retain_grad()          # test-only: per-pixel gradient of the up-sampled map (summed over i)
+                extras.setdefault(("disp_up_all", s), []).append(disp_up)
                 extras[("depth", s)] = depth
                 extras[("disp_up", s)] = disp_up
                 extras[("sample", i, s)] = grid

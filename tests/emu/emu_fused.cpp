@@ -96,6 +96,16 @@ extern "C" int emu_photometric_forward(const DvsShape* sh, const DvsParams* pr, 
   p.auto_mask = pr->auto_mask ? 1 : 0; p.want_grad = want_grad;
   p.mean_part = mean_part.data(); p.part = part.data();
   p.tiles_x = tiles_x; p.tiles_y = tiles_y;
+  int cstride = 0;
+  for (int s = 0; s < sh->S; ++s) {
+    const bool direct = p.dh[s] == p.H && p.dw[s] == p.W;
+    p.coff[s] = cstride;
+    p.cbw[s] = direct ? 0 : coarse_box_extent(p.dw[s], p.W);
+    cstride += direct ? 0 : coarse_box_extent(p.dh[s], p.H) * p.cbw[s];
+  }
+  p.cstride = cstride;
+  std::vector<float> cpart((size_t)nblk * cstride + 1, __builtin_nanf(""));
+  p.cpart = cpart.data();
 
   // mean_partial_kernel
   for (int s = 0; s < sh->S; ++s)
@@ -108,11 +118,6 @@ extern "C" int emu_photometric_forward(const DvsShape* sh, const DvsParams* pr, 
         mean_part[(s * sh->B + b) * kMeanBlocks + c] = acc;
       }
     }
-  if (want_grad)
-    for (int s = 0; s < sh->S; ++s)
-      if (!(p.dh[s] == p.H && p.dw[s] == p.W))
-        memset(ugrad_disp[s], 0, sizeof(float) * (size_t)sh->B * p.dh[s] * p.dw[s]);
-
   switch (sh->N) {
     case 1: run_all<1>(p, nblk); break;
     case 2: run_all<2>(p, nblk); break;
@@ -120,6 +125,16 @@ extern "C" int emu_photometric_forward(const DvsShape* sh, const DvsParams* pr, 
     case 4: run_all<4>(p, nblk); break;
     default: return DVS_EINVAL;
   }
+
+  // gather_gdisp_kernel
+  if (want_grad)
+    for (int s = 0; s < sh->S; ++s) {
+      if (p.dh[s] == p.H && p.dw[s] == p.W) continue;
+      for (int b = 0; b < sh->B; ++b)
+        for (int I = 0; I < p.dh[s]; ++I)
+          for (int J = 0; J < p.dw[s]; ++J)
+            ugrad_disp[s][((size_t)b * p.dh[s] + I) * p.dw[s] + J] = gather_gdisp(p, s, b, I, J);
+    }
 
   // finish_kernel + final_kernel
   const int tpi = tiles_x * tiles_y;

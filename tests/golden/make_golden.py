@@ -122,6 +122,41 @@ def run_port(prob, auto_mask):
     }
 
 
+def make_process_batch_case(learner_new, name="ref_process_batch_b2_48x64", B=2, H=48, W=64, seed=21):
+    """The reference's whole ``process_batch`` (vo/learner_new.py:76-105) with tiny networks: losses and the gradients
+    that reach the network weights.  The GPU test loads the same weights into the same tiny nets, runs THIS repo's
+    ``MonodepthTrainer.process_batch`` with the same noise and compares."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tiny_nets import TinyDepthNet, TinyPoseNet
+    prob = make_problem(B, H, W, 2, 4, seed=seed, consistent=True)
+    torch.manual_seed(seed)
+    dnet = TinyDepthNet(prob["disps"])
+    pnet = TinyPoseNet(prob["axisangle"], prob["translation"])
+    cfg = {"Train": dict(num_source=2, batch_size=B, img_h=H, img_w=W, smoothness_ratio=0.001, auto_mask=True,
+                         ssim_ratio=0.85, min_depth=0.1, max_depth=10.0, use_compile=False)}
+    trainer = learner_new.MonodepthTrainer(dnet, pnet, cfg, torch.device("cpu"))
+    sample = dict(prob["sample"])
+    with _RandnPatch(prob["noise"]):
+        outputs, losses = trainer.process_batch(sample)
+    losses["loss"].backward()
+    arrays = {f"sample/{k[0]}/{k[1]}": v for k, v in prob["sample"].items()}
+    for s in range(4):
+        arrays[f"noise{s}"] = prob["noise"][s]
+        arrays[f"loss/{s}"] = losses[f"loss/{s}"].detach()
+        arrays[f"identity_selection/{s}"] = outputs[f"identity_selection/{s}"]
+        arrays[f"depth{s}"] = outputs[("depth", s)].detach()
+        arrays[f"color{s}_-1"] = outputs[("color", -1, s)].detach()
+    arrays["loss"] = losses["loss"].detach()
+    for net, tag in ((dnet, "depth_net"), (pnet, "pose_net")):
+        for k, v in net.state_dict().items():
+            arrays[f"{tag}/state/{k}"] = v
+        for k, v in net.named_parameters():
+            arrays[f"{tag}/grad/{k}"] = v.grad
+    frac = [1 - float(outputs[f"identity_selection/{s}"].mean()) for s in range(4)]   # idx > 1  <=>  reprojection won
+    print(f"{name}: loss={float(losses['loss']):.8f} identity-selected={['%.2f' % f for f in frac]}")
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: v.detach().cpu().numpy() for k, v in arrays.items()})
+
+
 def close(a, b, what):
     """Forward values are bit-identical; gradients may differ in the last bits because autograd
     accumulates the (out-of-place vs in-place) graph in a different order."""
@@ -132,6 +167,9 @@ def close(a, b, what):
 def main():
     torch.set_num_threads(8)
     learner_new, learner_func = load_reference()
+    make_process_batch_case(learner_new)
+    if "--process-batch-only" in sys.argv:
+        return
     for name, B, H, W, consistent, auto_mask, seed in CASES:
         kw = {}
         if "bigmotion" in name:

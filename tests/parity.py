@@ -102,20 +102,24 @@ def oracle_eval(prob: Dict[str, object], *, sel_override: Optional[Sequence[np.n
                sel=[s[:, 0].cpu().numpy() for s in out["sel"]],
                combined=[c.cpu().double().numpy() for c in out["combined"]])
     if keep:
-        res["extras"] = {k: v.detach().cpu().double().numpy() for k, v in out["extras"].items()}
+        res["extras"] = {k: v.detach().cpu().double().numpy() for k, v in out["extras"].items()
+                         if not isinstance(v, list)}
     if want_grad:
         g = [1.0 / S] * S if grad_per_scale is None else list(grad_per_scale)
         obj = sum(gi * p for gi, p in zip(g, out["per_scale"]))
         obj.backward()
         res["grad_disp"] = [d.grad.cpu().double().numpy() for d in disps]
         res["grad_T"] = [T.grad.cpu().double().numpy() for T in Ts]
+        if keep:   # d objective / d disp_up[s] per full-resolution pixel: "one pixel's worth" of gradient, see check_parity
+            res["grad_disp_up"] = [sum(t.grad for t in out["extras"][("disp_up_all", s)]).cpu().double().numpy()
+                                   for s in range(S)]
     return res
 
 
 def check_parity(impl: Callable[[Dict[str, object], Optional[Sequence[float]]], Dict[str, object]],
                  prob: Dict[str, object], *, ref32: Optional[Dict[str, object]] = None, device="cpu",
                  grad_per_scale: Optional[Sequence[float]] = None, check_grad: bool = True,
-                 loss_rtol: float = 1e-5, verbose: bool = False) -> Dict[str, float]:
+                 loss_rtol: float = 1e-5, verbose: bool = False, expect_kink_free: bool = False) -> Dict[str, float]:
     """Assert the bounds of the module docstring; returns the measured error figures."""
     S, N = len(prob["disps"]), len(prob["sources"])
     B, _, H, W = prob["target"].shape
@@ -175,27 +179,55 @@ def check_parity(impl: Callable[[Dict[str, object], Optional[Sequence[float]]], 
             g, r, r64 = np.asarray(got["grad_disp"][s], np.float64), refg["grad_disp"][s], refg64["grad_disp"][s]
             assert g.shape == r.shape
             assert np.all(np.isfinite(g)), f"non-finite grad_disp[{s}]"
-            risky = _kink_risk(prob, refg64["extras"], so[s] if so is not None else None, s, N, H, W)
+            kinks = _kink_weight(prob, refg64["extras"], so[s] if so is not None else None, s, N, H, W)
+            risky = kinks > 0
             n_risky += int(risky.sum())
+            stats[f"near_kink_frac/{s}"] = float(risky.mean())
             rmax = max(np.abs(r).max(), 1e-30)
-            noise = 2 * np.abs(r - r64)
+            noise = 2 * np.abs(r - r64)                      # the reference's own fp32 rounding, element by element
             err = np.abs(g - r)
             ok = ~risky
             rel = (err[ok]).max() / rmax if ok.any() else 0.0
             worst = max(worst, rel)
-            assert np.all(err[ok] <= 1e-3 * rmax + noise.max()), \
-                f"grad_disp[{s}]: normalised inf-norm error {rel:.3e} (reference fp32 noise {noise.max() / 2 / rmax:.2e})"
-            lim = 1e-3 * np.abs(r) + 1e-6 * gscale + noise      # north_star: rtol 1e-3 / atol 1e-6 on the raw gradient
+            # (1) kink-free elements, inf-norm: the allowance is the fp32 noise of THOSE elements only
+            assert (not ok.any()) or np.all(err[ok] <= 1e-3 * rmax + noise[ok].max()), \
+                f"grad_disp[{s}]: normalised inf-norm error {rel:.3e} (reference fp32 noise {noise[ok].max() / 2 / rmax:.2e})"
+            # (2) kink-free elements, element-wise: north_star's rtol 1e-3 / atol 1e-6 on the raw gradient
+            lim = 1e-3 * np.abs(r) + 1e-6 * gscale + noise
             bad = err[ok] > lim[ok]
             # stragglers: at most 2 in 100 000 elements (kinks the float64 locator above missed by a hair) may sit
             # outside the element-wise bound, and then by no more than 10x; the inf-norm bound above has no exception
             assert bad.size == 0 or (bad.mean() <= 2e-5 and np.all(err[ok] <= 10 * lim[ok])), \
                 f"grad_disp[{s}]: {int(bad.sum())} of {bad.size} elements outside rtol 1e-3 / atol 1e-6"
             stats["grad_disp_stragglers"] = stats.get("grad_disp_stragglers", 0) + int(bad.sum())
-            assert np.all(err[risky] <= 0.25 * rmax), f"grad_disp[{s}]: near-kink elements off by {err[risky].max() / rmax:.3e}"
+            # (3) elements with kink pixels in their footprint: the same element-wise bound plus what those pixels can
+            # move -- a pixel on a kink may take either one-sided derivative, i.e. change by up to twice one pixel's worth
+            # of gradient (gpix: the largest per-pixel |d objective / d disp_up| of this scale, float64 oracle), weighted
+            # by its up-sampling tap weight into the element.  One kink pixel under a scale-3 element (256-pixel
+            # footprint) therefore opens the gate by ~1/256 of the element's typical size, not by 0.25 * max.
+            gpix = float(np.abs(refg64["grad_disp_up"][s]).max())
+            lim_k = lim + 2.0 * kinks * gpix
+            badk = err[risky] > lim_k[risky]
+            assert not badk.any(), (f"grad_disp[{s}]: {int(badk.sum())} near-kink elements outside the footprint-scaled bound, "
+                                    f"worst excess {(err[risky] / lim_k[risky]).max():.2f}x")
+            # (4) every element, no exclusion: the implementation must be as close to the float64 evaluation as the
+            # reference's own fp32 evaluation is (within 2x, plus a floor of a few fp32 ulps of the largest element) at
+            # the median and the 90th percentile -- and further into the tail (p99, p99.9) where the map has enough
+            # elements that the handful of kink pixels, which either evaluation may resolve the other way, stay above
+            # the quantile.  A systematic error of 1 % in the photometric gradient moves the median by
+            # ~1e-2 * median|g| / max|g| ~ 1e-4, two orders above the fp32 noise (~2e-6): this is the gate that fails on it.
+            e_impl, e_ref = np.abs(g - r64).ravel() / rmax, np.abs(r - r64).ravel() / rmax
+            levels = [0.5, 0.9] + ([0.99] if e_impl.size >= 10000 else []) + ([0.999] if e_impl.size >= 1000000 else [])
+            qi, qr = np.quantile(e_impl, levels), np.quantile(e_ref, levels)
+            stats[f"dist_ratio_p50/{s}"] = float(qi[0] / max(qr[0], 1e-30))
+            stats[f"dist_ratio_p90/{s}"] = float(qi[1] / max(qr[1], 1e-30))
+            assert np.all(qi <= 2 * qr + 2e-7), \
+                f"grad_disp[{s}]: quantiles {levels} of |g - g64| / max = {qi} vs the reference's own fp32 evaluation {qr}"
             assert risky.mean() < 0.20 or g.shape[2:] != (H, W), f"grad_disp[{s}]: {risky.mean():.1%} of the elements excluded as near-kink"
         stats["grad_disp_relinf_max"] = worst
         stats["near_kink_elements"] = n_risky
+        if expect_kink_free:      # the strict gates (1), (2) above then covered every element of every scale
+            assert n_risky == 0 and stats.get("grad_disp_stragglers", 0) == 0, (n_risky, stats.get("grad_disp_stragglers"))
         worst = 0.0
         for i in range(N):
             g, r, r64 = np.asarray(got["grad_T"][i], np.float64), refg["grad_T"][i], refg64["grad_T"][i]
@@ -220,9 +252,10 @@ def _dilate3(m: np.ndarray) -> np.ndarray:
     return out
 
 
-def _kink_risk(prob, extras, sel, s: int, N: int, H: int, W: int) -> np.ndarray:
-    """Boolean mask over disp[s] elements whose footprint holds a pixel within round-off of a kink of the
-    loss (see module docstring).  `extras` are the float64 oracle's intermediates, `sel` the selection in force."""
+def _kink_weight(prob, extras, sel, s: int, N: int, H: int, W: int) -> np.ndarray:
+    """For every disp[s] element: the sum of up-sampling tap weights of the full-resolution pixels in its footprint that
+    sit within round-off of a kink of the loss (see module docstring); 0 = kink-free.  `extras` are the float64
+    oracle's intermediates, `sel` the selection in force."""
     from oracle.closed_form import ssim_terms, upsample_taps
     B, _, h, w = prob["disps"][s].shape
     tgt = np.asarray(prob["target"], np.float64)
@@ -249,11 +282,54 @@ def _kink_risk(prob, extras, sel, s: int, N: int, H: int, W: int) -> np.ndarray:
     pix[:, :, 1:] |= kx
     pix[:, :-1, :] |= ky
     pix[:, 1:, :] |= ky
-    out = np.zeros((B, 1, h, w), bool)
-    y0, y1, _ = upsample_taps(H, h, np.float64)
-    x0, x1, _ = upsample_taps(W, w, np.float64)
+    out = np.zeros((B, 1, h, w), np.float64)
+    y0, y1, ly = upsample_taps(H, h, np.float64)
+    x0, x1, lx = upsample_taps(W, w, np.float64)
     bb, yy, xx = np.nonzero(pix)
-    for ya in (y0, y1):
-        for xa in (x0, x1):
-            out[bb, 0, ya[yy], xa[xx]] = True
+    for ya, wy in ((y0, 1 - ly), (y1, ly)):
+        for xa, wx in ((x0, 1 - lx), (x1, lx)):
+            # a tap of weight 0 still marks the element (round-off can put the kink on either side of a tap boundary)
+            np.add.at(out, (bb, 0, ya[yy], xa[xx]), np.maximum(wy[yy] * wx[xx], 1e-3))
     return out
+
+
+def kink_free_problem(B: int = 1, H: int = 64, W: int = 96, seed: int = 0) -> Dict[str, object]:
+    """A problem on which the loss is smooth at every pixel, so the strict element-wise gradient gates apply to 100 %
+    of the elements of every scale (no near-kink exemption): low-contrast smooth textures well inside (0,1) (no clipping,
+    SSIM far from its clamp), sources = independent smooth textures offset in brightness (|target - warped| never near 0),
+    fronto-parallel translations with ramp disparities so that every sampling coordinate stays a fixed sub-pixel distance
+    (0.2 .. 0.8 px) from the integer grid, monotone disparity ramps (|delta n| is either exactly 0 on the border clamp or
+    far above 1e-6), no automask.  ``check_parity`` asserts ``near_kink_elements == 0`` when asked to (``expect_kink_free``)."""
+    import torch.nn.functional as F
+    from dvsloss.synthetic import redwood_intrinsics
+    gen = torch.Generator().manual_seed(seed)
+
+    def tex(lo, hi):
+        low = torch.rand(B, 3, 6, 8, generator=gen)
+        img = F.interpolate(low, size=(H, W), mode="bicubic", align_corners=False)
+        img = (img - img.amin()) / (img.amax() - img.amin())
+        return lo + (hi - lo) * img
+
+    target = tex(0.35, 0.60)
+    sources = [tex(0.62, 0.80), tex(0.15, 0.33)]
+    intr = redwood_intrinsics(B, H, W)
+    K, inv_K = intr[("K", 0)], intr[("inv_K", 0)]
+    fx, fy = float(K[0, 0, 0]), float(K[0, 1, 1])
+    v, u = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+    disps = []
+    for s in range(4):
+        ramp = 0.30 + (0.10 + 0.01 * s) * u + (0.08 - 0.01 * s) * v            # in [0.30, 0.49]
+        d = F.interpolate(ramp[None, None], size=(H >> s, W >> s), mode="bilinear", align_corners=False)
+        disps.append(d.repeat(B, 1, 1, 1).contiguous())
+    sd_lo, sd_hi = 0.1 + 9.9 * 0.30, 0.1 + 9.9 * 0.49                            # scaled disparity = 1 / depth
+    Ts = []
+    for sign in (1.0, -1.0):
+        # flow = f * t / depth in [0.27, 0.45] px (x) and [0.3, 0.5] px (y), away from the integer grid
+        T = torch.eye(4).repeat(B, 1, 1)
+        T[:, 0, 3] = sign * 0.27 / (fx * sd_lo)
+        T[:, 1, 3] = -sign * 0.30 / (fy * sd_lo)
+        Ts.append(T)
+    assert 0.45 * sd_hi / sd_lo < 0.8
+    n = lambda t: t.detach().cpu().numpy().astype(np.float32)
+    return dict(disps=[n(d) for d in disps], target=n(target), sources=[n(s_) for s_ in sources], K=n(K), inv_K=n(inv_K),
+                Ts=[n(T) for T in Ts], noise=None, auto_mask=False)

@@ -52,3 +52,24 @@ def test_emulator_non_pyramid_disparity_sizes():
     prob["disps"] = [rng.uniform(0.05, 0.9, (1, 1, 20, 27)).astype(np.float32),
                      rng.uniform(0.05, 0.9, (1, 1, 7, 64)).astype(np.float32)]
     parity.check_parity(emu_impl, prob, verbose=True)
+
+
+@pytest.mark.parametrize("name", ["ref_b2_48x64_consistent.npz", "ref_b1_96x128_consistent.npz"])
+def test_parity_gates_catch_a_one_percent_gradient_error(name):
+    """The gates must be able to fail: the same tile code built with a 1 % error injected into d loss / d warped colour
+    (``-DDVS_FAULT_GRAD_SCALE=1.01f`` in phase_grad) has to be rejected by check_parity."""
+    def faulty(prob, gps):
+        return emu_harness.run(prob["disps"], prob["target"], prob["sources"], prob["K"], prob["inv_K"], prob["Ts"],
+                               prob["noise"], auto_mask=prob["auto_mask"], grad_per_scale=gps,
+                               defines=("DVS_FAULT_GRAD_SCALE=1.01f",))
+    g = parity.load_golden(name)
+    with pytest.raises(AssertionError, match="grad_"):
+        parity.check_parity(faulty, g["prob"], ref32=dict(g["ref"]))
+
+
+@pytest.mark.parametrize("B,H,W,seed", [(1, 64, 96, 0), (2, 96, 128, 1)])
+def test_emulator_kink_free_every_element_strict(B, H, W, seed):
+    """No near-kink exemption: every element of every scale under rtol 1e-3 / atol 1e-6 and the 1e-3 inf-norm bound."""
+    prob = parity.kink_free_problem(B, H, W, seed)
+    stats = parity.check_parity(emu_impl, prob, verbose=True, expect_kink_free=True)
+    assert stats["grad_disp_relinf_max"] < 1e-3

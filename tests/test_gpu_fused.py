@@ -71,6 +71,19 @@ def test_fused_non_pyramid_disparity_sizes():
     parity.check_parity(cuda_impl, prob, verbose=True)
 
 
+# Share of disparity elements with a kink pixel in their footprint on the 640x480 consistent problems (measured on the
+# float64 oracle: 4.9 % / 13.7 % / 37.3 % / 80.2 % at scales 0..3 -- a scale-3 element gathers 256 pixels).  Stored so
+# that a locator that silently starts excluding more shows up; those elements are still held to the footprint-scaled
+# element-wise bound and to the all-element distribution gate of tests/parity.py.
+NEAR_KINK_FRAC_MAX = (0.07, 0.18, 0.45, 0.88)
+
+
+def _check_kink_fractions(stats):
+    fr = [stats[f"near_kink_frac/{s}"] for s in range(4)]
+    print("near-kink share per scale:", ["%.3f" % f for f in fr])
+    assert all(f <= m for f, m in zip(fr, NEAR_KINK_FRAC_MAX)), fr
+
+
 def test_fused_full_resolution_parity():
     """BASELINE config-2 frame size (640x480, 2 sources, 4 scales) against the oracle run with torch ops on
     the same GPU (the reference's eager-CUDA op sequence), batch 2."""
@@ -78,17 +91,45 @@ def test_fused_full_resolution_parity():
     prob = parity.problem_from_synthetic(p, True)
     stats = parity.check_parity(cuda_impl, prob, device="cuda", verbose=True)
     assert stats["loss_rel"] < 1e-5
+    _check_kink_fractions(stats)
 
 
-def test_fused_deterministic():
-    """Fixed-order reductions: two runs on the same inputs give bit-identical losses and pose gradients."""
-    g = parity.load_golden("ref_b1_96x128_consistent.npz")
-    a, b = cuda_impl(g["prob"], None), cuda_impl(g["prob"], None)
+def test_fused_config2_full_batch_parity():
+    """The whole BASELINE configs[1] problem (batch 16, 640x480, 2 sources, 4 scales) against the oracle evaluated on
+    the GPU in fp32 and float64: losses, selection, every gradient."""
+    p = make_problem(16, 480, 640, 2, 4, seed=16, consistent=True)
+    prob = parity.problem_from_synthetic(p, True)
+    stats = parity.check_parity(cuda_impl, prob, device="cuda", verbose=True)
+    assert stats["loss_rel"] < 1e-5
+    _check_kink_fractions(stats)
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("B,H,W,seed", [(1, 64, 96, 0), (2, 96, 128, 1), (1, 240, 320, 2)])
+def test_fused_kink_free_every_element_strict(B, H, W, seed):
+    """No exemption anywhere: on a problem without kinks (tests/parity.py: kink_free_problem) every element of every
+    scale is held to rtol 1e-3 / atol 1e-6 and to the 1e-3 inf-norm bound -- this is the case that checks the in-tile
+    up-sample adjoint element by element at the coarse scales."""
+    prob = parity.kink_free_problem(B, H, W, seed)
+    stats = parity.check_parity(cuda_impl, prob, verbose=True, expect_kink_free=True)
+    assert stats["grad_disp_relinf_max"] < 1e-3
+
+
+@pytest.mark.parametrize("shape", [None, (2, 240, 320)])
+def test_fused_deterministic(shape):
+    """Fixed-order reductions everywhere (no float atomics): two runs on the same inputs give bit-identical losses, pose
+    gradients and disparity gradients at EVERY scale."""
+    if shape is None:
+        prob = parity.load_golden("ref_b1_96x128_consistent.npz")["prob"]
+    else:
+        prob = parity.problem_from_synthetic(make_problem(*shape, 2, 4, seed=9, consistent=True), True)
+    a, b = cuda_impl(prob, None), cuda_impl(prob, None)
     assert a["loss"] == b["loss"]
     assert np.array_equal(a["per_scale"], b["per_scale"])
     for x, y in zip(a["grad_T"], b["grad_T"]):
         assert np.array_equal(x, y)
-    assert np.array_equal(a["grad_disp"][0], b["grad_disp"][0])      # full-res map: direct stores
+    for s in range(4):
+        assert np.array_equal(a["grad_disp"][s], b["grad_disp"][s]), s
 
 
 def test_fused_kernel_noise_statistics():
@@ -243,7 +284,7 @@ def test_c_abi_backward_recompute_matches_forward_saved_gradients():
     torch.cuda.synchronize()
     for s in range(4):
         a, b = gd[s].cpu().numpy(), ref["grad_disp"][s]
-        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max() + 1e-12, s      # same kernels; atomics may reorder the coarse sums
+        assert np.array_equal(a, b), s                    # same kernels, fixed-order sums everywhere
     for i in range(2):
         assert np.array_equal(gT[i].cpu().numpy(), ref["grad_T"][i])
     # misuse is reported, not executed
@@ -253,7 +294,7 @@ def test_c_abi_backward_recompute_matches_forward_saved_gradients():
 
 
 def test_fused_loss_is_cuda_graph_capturable():
-    """the whole loss forward+backward (4 + 1 kernels, 3 memsets, no host sync) replays from a CUDA graph
+    """the whole loss forward+backward (5 + 1 kernels, no memsets, no host sync) replays from a CUDA graph
     and gives the numbers of the eager call (the reference syncs the host every step, vo/train.py:196-197)."""
     from dvsloss import view_synthesis_loss
     from dvsloss.synthetic import pose_matrix
@@ -291,9 +332,8 @@ def test_fused_loss_is_cuda_graph_capturable():
     assert torch.equal(out[1], chk[1])
     for a, b in zip(out[2][4:], chk[2][4:]):
         assert torch.equal(a, b)                         # pose gradients: fixed-order reductions
-    assert torch.equal(out[2][0], chk[2][0])             # full-resolution disparity gradient: direct stores
-    for a, b in zip(out[2][1:4], chk[2][1:4]):
-        assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())      # coarse scales: atomics reorder the sums
+    for a, b in zip(out[2][:4], chk[2][:4]):
+        assert torch.equal(a, b)                         # disparity gradients of every scale: direct stores / fixed-order gather
 
 
 def test_host_pipeline_matches_device_call():
