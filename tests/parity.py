@@ -26,15 +26,24 @@ Tolerances (BASELINE.json north_star):
   * discontinuities: the loss is only piecewise smooth.  At a pixel that sits within fp32 round-off of a kink,
     either one-sided derivative is a correct answer and two fp32 evaluations (the reference on CPU vs on CUDA
     included) may disagree by O(1) *at that pixel*.  The kinks are: a sampling coordinate within ~3e-4 px of an
-    integer (bilinear cell change; covers the border clip at 0 and W-1), |target - warped| < 1e-5 in a channel
-    (sign of the L1 term), an SSIM value within 5e-5 of the clamp bounds (its fp32 evaluation carries ~2e-5 of cancellation noise), and 0 < |delta n| < 1e-6 in the
+    integer (bilinear cell change; covers the border clip at 0 and W-1), |target - warped| < 5e-5 in a channel
+    (sign of the L1 term: the warped colour inherits the ~6e-5 px fp32 uncertainty of its sampling coordinate times the image slope), an SSIM value within 5e-5 of the clamp bounds (its fp32 evaluation carries ~2e-5 of cancellation noise), and 0 < |delta n| < 1e-6 in the
     smoothness term -- the synthetic textures are clipped to [0,1], so saturated patches where warped == target
     make the L1 and clamp kinks common.  They are located with the float64 oracle for the source(s) selected
-    around the pixel; disparity elements whose footprint (SSIM 3x3 window, then the bilinear up-sampling taps)
-    contains such a pixel are checked against the loose bound 0.25 * ||g_ref||_inf instead, and at full
-    resolution they must stay below 20 % of the elements (a coarse element gathers up to 256 pixels, so the
-    share is not bounded there; the pose gradient, which sums every pixel, is always checked strictly).
-    At the multi-hundred-thousand-element sizes a couple of elements per 100 000 that the locator misses may exceed the
+    around the pixel.  A disparity element whose footprint (SSIM 3x3 window, then the bilinear up-sampling taps) holds
+    such pixels is NOT exempt: it is held to the same element-wise bound widened by what those pixels can move,
+    2 * (sum of their tap weights) * (largest per-pixel |d objective / d disp_up| of that scale) -- one kink pixel under
+    a scale-3 element opens the gate by ~1/256 of the element's typical size.  The inf-norm bound over the kink-free
+    elements uses the fp32 noise of those elements only.  At full resolution the kink share must stay below 20 %
+    (the GPU tests also pin the share of every scale at 640x480 against stored values).
+  * every element, no exclusion: at the median and the 90th percentile (and p99 / p99.9 where the map is large
+    enough that the few kink pixels stay above the quantile) |g - g64| / max|g| of the implementation must be within
+    2x of the reference's own fp32 evaluation against float64.  This is the gate a systematic error trips:
+    tests/test_emulator.py::test_parity_gates_catch_a_one_percent_gradient_error builds the tile code with a 1 % error
+    injected in phase_grad and requires check_parity to fail.
+  * ``kink_free_problem`` builds inputs without any kink; there ``expect_kink_free`` asserts that the strict
+    element-wise and inf-norm gates covered 100 % of the elements of every scale.
+  * At the multi-hundred-thousand-element sizes a couple of elements per 100 000 that the locator misses may exceed the
     element-wise bound (by < 10x); they are counted in ``grad_disp_stragglers`` and never exempt from the inf-norm bound.
 """
 from __future__ import annotations
@@ -270,7 +279,7 @@ def _kink_weight(prob, extras, sel, s: int, N: int, H: int, W: int) -> np.ndarra
         iy = (g[..., 1] + 1) / 2 * (H - 1)
         k = (np.abs(ix - np.round(ix)) < thr) | (np.abs(iy - np.round(iy)) < thr)
         col = extras[("color", i, s)]
-        k |= (np.abs(tgt - col) < 1e-5).any(1) & chosen
+        k |= (np.abs(tgt - col) < 5e-5).any(1) & chosen
         S = ssim_terms(col, tgt)[0]
         k |= _dilate3((((S < 5e-5) | (S > 1 - 5e-5)).any(1)) & chosen)
         pix |= k & active
