@@ -11,11 +11,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
 #include "../../include/dvsloss.h"
 #include "dvs_fused_core.cuh"
+#include "dvs_pair_core.cuh"
 #include "dvs_host.h"
 
 namespace dvs {
@@ -108,6 +110,45 @@ __global__ void __launch_bounds__(NT, (NS <= 2 ? 2 : 1)) fused_tile_kernel(const
     // no barrier needed here: the next phase_warp writes only X/DU, which nobody reads any more
     // (adjoint_cols / reduce_stage2 read the F region, next written after the following barrier) ...
     // ... except adjoint_rows' input DU: all threads passed the barrier after adjoint_rows already.
+  }
+}
+
+// Two-source specialisation (dvs_pair_core.cuh): per-source arithmetic on (source 0, source 1) pairs, packed fp32.
+template <bool GRAD>
+__global__ void __launch_bounds__(NT, 2) fused_pair_kernel(const __grid_constant__ FusedParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x;
+  const Tile t = make_tile(p, blockIdx.x);
+  PairLayout P;
+  PairState st;
+
+  phase_consts<2>(p, t, sm, tid, sm + P.a2());
+  pair_phase_load(p, t, sm, tid, st);
+  __syncthreads();
+  pair_phase_identity(p, t, sm, tid, st);
+  __syncthreads();
+
+  for (int s = 0; s < p.S; ++s) {
+    pair_reset_scale_state(st);
+    pair_phase_warp(p, t, sm, tid, s);
+    __syncthreads();
+    pair_phase_stats<GRAD>(p, t, sm, tid, s, st);
+    __syncthreads();
+    const bool direct = (p.dh[s] == p.H && p.dw[s] == p.W);
+    if (GRAD) {
+      pair_phase_grad(p, t, sm, tid, s, st);
+      __syncthreads();
+      if (direct) pair_store_gdu_direct(p, t, tid, s, st);
+      else pair_stage_gdu(sm, tid, st);
+    }
+    pair_reduce_write(sm, tid, st);
+    __syncthreads();
+    if (GRAD && !direct) adjoint_rows<2>(p, t, sm, tid, s);
+    reduce_stage1<2>(p, sm, tid);
+    __syncthreads();
+    if (GRAD && !direct) adjoint_cols<2>(p, t, sm, tid, s);
+    reduce_stage2<2>(p, t, sm, tid, s);
+    // as in fused_tile_kernel: the next warp phase writes only X / DU, which nobody reads any more
   }
 }
 
@@ -315,7 +356,31 @@ static cudaError_t launch_tile(const FusedParams& p, int nblk, cudaStream_t st) 
   return cudaGetLastError();
 }
 
+template <bool GRAD>
+static cudaError_t launch_pair(const FusedParams& p, int nblk, cudaStream_t st) {
+  PairLayout P;
+  size_t bytes = (size_t)P.total() * sizeof(float);
+  static std::atomic<bool> configured[kMaxDevices];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices || !configured[dev].load(std::memory_order_acquire)) {
+    e = cudaFuncSetAttribute(fused_pair_kernel<GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < kMaxDevices) configured[dev].store(true, std::memory_order_release);
+  }
+  fused_pair_kernel<GRAD><<<nblk, NT, bytes, st>>>(p);
+  return cudaGetLastError();
+}
+
+// DVS_GENERIC_KERNEL=1 routes two-source problems through the generic kernel (A/B measurements, regression tests).
+static bool use_generic_kernel() {
+  static const bool v = [] { const char* e = getenv("DVS_GENERIC_KERNEL"); return e && e[0] == '1'; }();
+  return v;
+}
+
 static cudaError_t dispatch_tile(const FusedParams& p, int nblk, cudaStream_t st) {
+  if (p.N == 2 && !use_generic_kernel()) return p.want_grad ? launch_pair<true>(p, nblk, st) : launch_pair<false>(p, nblk, st);
   switch (p.N * 2 + (p.want_grad ? 1 : 0)) {
     case 2: return launch_tile<1, false>(p, nblk, st);
     case 3: return launch_tile<1, true>(p, nblk, st);

@@ -297,8 +297,9 @@ DVS_HD CoarseBox coarse_box(const FusedParams& p, const Tile& t, int s) {
 
 // ------------------------------------------------------------------------------------------------ phase 0
 // constants of the tile: A_i = (K T_i)[:3,:3] inv_K[:3,:3], p_i = (K T_i)[:3,3], 1/(clamp(mean disp)+1e-7) per scale.
+// `a2` (two-source kernel): additionally the same numbers interleaved per source, a2[2 e + i] = (A_i | p_i)[e].
 template <int NS>
-DVS_HD void phase_consts(const FusedParams& p, const Tile& t, float* sm, int tid) {
+DVS_HD void phase_consts(const FusedParams& p, const Tile& t, float* sm, int tid, float* a2 = nullptr) {
   SmemLayout L{NS};
   float* c = sm + L.consts();
   if (tid < 12 * NS) {
@@ -317,11 +318,13 @@ DVS_HD void phase_consts(const FusedParams& p, const Tile& t, float* sm, int tid
         a += P * (double)iK[m * 4 + k];
       }
       c[kC_A + 12 * i + e] = (float)a;
+      if (a2) a2[2 * e + i] = (float)a;
     } else {
       int r = e - 9;
       double P = 0.0;
       for (int n = 0; n < 4; ++n) P += (double)Kb[r * 4 + n] * (double)Tb[n * 4 + 3];
       c[kC_A + 12 * i + e] = (float)P;
+      if (a2) a2[2 * e + i] = (float)P;
     }
   } else if (tid >= 64 && tid < 64 + p.S) {
     int s = tid - 64;
@@ -1016,13 +1019,13 @@ template <int NS>
 DVS_HD void adjoint_cols(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   SmemLayout L{NS};
   const int* a = reinterpret_cast<const int*>(sm + L.consts() + kC_adj + 8 * s);
-  const int i0 = a[0], nci = a[1] - a[0] + 1, j0 = a[2], ncj = a[3] - a[2] + 1, fyi = a[4];
+  const int nci = a[1] - a[0] + 1, ncj = a[3] - a[2] + 1, fyi = a[4], I0 = a[0];
   const int fy0 = t.gy0 + 1, fy1 = imin(t.gy0 + TH - 2, p.H - 1);
   const float scale = (float)p.dh[s] / (float)p.H, inv = (float)p.H / (float)p.dh[s];
   const float rn = 1.0f / (float)ncj;
   for (int k = tid; k < nci * ncj; k += NT) {
     int Il = (int)(((float)k + 0.5f) * rn);
-    int Jl = k - Il * ncj, I = i0 + Il;
+    int Jl = k - Il * ncj, I = I0 + Il;
     int ya, yb;
     fine_range(I, fyi, inv, ya, yb);
     ya = imax(ya, fy0); yb = imin(yb, fy1);

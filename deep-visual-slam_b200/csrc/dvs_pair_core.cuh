@@ -1,0 +1,580 @@
+// Fused view-synthesis loss, two-source specialisation ("pair" kernel): per-tile phase functions.
+//
+// Same tile geometry, shared-memory planes, reductions and up-sample adjoint as dvs_fused_core.cuh (one CTA per 30x30
+// block of target pixels, lane == column, a thread owns four vertically adjacent pixels).  What changes is the
+// arithmetic layout: the reference's configuration has exactly two source frames (vo/learner_new.py:148,206,214 hard-code
+// [-1, +1]), and everything that is computed "per source" -- projection, bilinear taps, 3x3 sums of x, x^2, xy, the SSIM
+// algebra, the gradient chain, the pose moments -- is carried as a PAIR (source 0, source 1) in one 64-bit register and
+// issued as Blackwell packed fp32 instructions (FADD2 / FMUL2 / FFMA2: two lanes per issue slot).  The kernel is
+// issue-slot bound (profiles/r01d_*), so halving the slots of the per-source arithmetic is the lever; the warped colours
+// of the two sources are interleaved in shared memory (float2 per pixel: one 64-bit load feeds both lanes).
+//
+//   * statistics: two pixels at a time (rolled loop over the halves of the quad): 4 rows of horizontal sums for 2
+//     pixels; keeps the live state small (no spills at 128 registers) and the loop body short (instruction cache)
+//   * coefficient pooling: F holds the fields of the selected source and exact zeros elsewhere, so one sweep yields
+//     the pooled fields of source 0 (masked) and of both (unmasked, same operation order); source 1 = difference
+//   * gradient chain: both sources of a pixel at once, taps re-gathered (L1 resident)
+//
+// Reference arithmetic: vo/learner_new.py:60-74,132-258; formulas as in oracle/closed_form.py.  Operation order
+// follows dvs_fused_core.cuh so that the two kernels agree to the last bit wherever the algorithm is the same.
+#pragma once
+#include "dvs_fused_core.cuh"
+
+namespace dvs {
+
+constexpr int kPairIdent = 8 * NT;   // identity terms parked in shared memory: [2 j + i][tid]
+
+struct PairLayout {
+  SmemLayout L{2};
+  DVS_HD int x2(int c) const { return L.x(0, 0) + 2 * c * PLANE; }                 // float2 plane of channel c
+  DVS_HD int ident() const { return (L.total() + 1) & ~1; }
+  DVS_HD int a2() const { return ident() + kPairIdent; }                           // 12 float2: (A_0[e], A_1[e]); 8-byte aligned
+  DVS_HD int total() const { return a2() + 24; }
+};
+
+DVS_HD f2 ld2(const float* p) {
+#if defined(__CUDA_ARCH__)
+  float2 v = *reinterpret_cast<const float2*>(p);
+  return f2{v.x, v.y};
+#else
+  return f2{p[0], p[1]};
+#endif
+}
+DVS_HD void st2(float* p, f2 v) {
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y);
+#else
+  p[0] = v.x; p[1] = v.y;
+#endif
+}
+DVS_HD f2 bc2(float a) { return f2{a, a}; }
+
+struct PairState {
+  int flags;               // bit j: pixel j inside the image; bit 4+j: pixel j belongs to R0 (own)
+  float acc[3];            // photometric sum, smooth-x sum, smooth-y sum of the current scale
+  f2 M[12];                // pose-gradient moments of the current scale, (source 0, source 1)
+  float gdu[4];            // d loss / d disp_up of the own pixels, current scale
+  int tags;                // selected source of the 4 pixels, one byte each (kSelNone: identity / outside)
+};
+
+// ------------------------------------------------------------------------------------------------ load
+// target -> Y, sources interleaved -> X2 (for the identity terms), zero F, selection plane, pixel flags.
+DVS_HD void pair_phase_load(const FusedParams& p, const Tile& t, float* sm, int tid, PairState& st) {
+  PairLayout P;
+  const SmemLayout& L = P.L;
+  const int HW = p.H * p.W;
+  int* posp = reinterpret_cast<int*>(sm + L.pos());
+  DVS_NOUNROLL
+  for (int k = tid; k < PLANE; k += NT) {
+    int ly = k / PW - 1, lx = k % PW - 1;
+    int gy = reflect_clamp(t.gy0 + ly, p.H), gx = reflect_clamp(t.gx0 + lx, p.W);
+    posp[k] = (gy << 16) | gx;
+    int o = gy * p.W + gx;
+    const float* tg = p.target + (size_t)t.b * 3 * HW + o;
+    sm[L.y(0) + k] = tg[0];
+    sm[L.y(1) + k] = tg[HW];
+    sm[L.y(2) + k] = tg[2 * HW];
+    if (p.auto_mask) {
+      const float* s0 = p.src[0] + (size_t)t.b * 3 * HW + o;
+      const float* s1 = p.src[1] + (size_t)t.b * 3 * HW + o;
+      st2(sm + P.x2(0) + 2 * k, f2{s0[0], s1[0]});
+      st2(sm + P.x2(1) + 2 * k, f2{s0[HW], s1[HW]});
+      st2(sm + P.x2(2) + 2 * k, f2{s0[2 * HW], s1[2 * HW]});
+    }
+  }
+#if defined(__CUDA_ARCH__)
+  float4* f4 = reinterpret_cast<float4*>(sm + L.f(0));
+  for (int k = tid; k < 9 * PLANE / 4; k += NT) f4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
+  for (int k = tid; k < 9 * PLANE; k += NT) sm[L.f(0) + k] = 0.f;
+#endif
+  for (int k = tid; k < PLANE / 4; k += NT) reinterpret_cast<unsigned int*>(sm + L.sel())[k] = 0xffffffffu;   // kSelNone
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  int fl = 0;
+  const int gx = t.gx0 + cx;
+  for (int j = 0; j < 4; ++j) {
+    int gy = t.gy0 + r0 + j;
+    bool in = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+    bool own = in && (r0 + j) >= 1 && (r0 + j) <= TH - 2 && cx >= 1 && cx <= TW - 2;
+    fl |= (in ? 1 : 0) << j;
+    fl |= (own ? 1 : 0) << (4 + j);
+  }
+  st.flags = fl;
+}
+
+// ------------------------------------------------------------------------------------------------ statistics of two pixels
+// SSIM from 9-sums for both sources of one pixel; same operation order as ssim_terms / ssim_coefs.
+struct SsimPair {
+  f2 N1, N2, D1, D2, R, rd;
+};
+DVS_HD void ssim_terms2(f2 sx, f2 sxx, f2 sxy, float sy, float ysq, float ty, SsimPair& t) {
+  const f2 pr = mul2(sx, bc2(sy));
+  const f2 e = fma2(sx, sx, bc2(ysq));
+  t.N1 = fma2(bc2(2.f), pr, bc2(kK1));
+  t.N2 = fma2(bc2(-2.f), pr, fma2(bc2(18.f), sxy, bc2(kK2)));
+  t.D1 = add2(e, bc2(kK1));
+  t.D2 = sub2(fma2(bc2(9.f), sxx, bc2(ty)), e);
+  const f2 dd = mul2(t.D1, t.D2);
+  t.rd = f2{rcp_fast(dd.x), rcp_fast(dd.y)};
+  t.R = mul2(mul2(t.N1, t.N2), t.rd);
+}
+DVS_HD f2 ssim_value2(const SsimPair& t) {
+  return f2{sat01(fmaf(-0.5f, t.R.x, 0.5f)), sat01(fmaf(-0.5f, t.R.y, 0.5f))};
+}
+DVS_HD void ssim_coefs2(const SsimPair& t, f2 sx, float sy, float scale, f2& al, f2& be, f2& ga) {
+  const f2 rk = f2{(t.R.x >= -1.f && t.R.x <= 1.f) ? t.rd.x * scale : 0.f, (t.R.y >= -1.f && t.R.y <= 1.f) ? t.rd.y * scale : 0.f};
+  const f2 nrk = f2{-rk.x, -rk.y};
+  // w = -(R sx) (D2 - D1) + sy (N2 - N1)   (the sign moved onto the difference: exact)
+  const f2 w = fma2(mul2(t.R, sx), sub2(t.D1, t.D2), mul2(bc2(sy), sub2(t.N2, t.N1)));
+  al = mul2(w, nrk);
+  be = mul2(mul2(bc2(4.5f), mul2(t.R, t.D1)), rk);
+  ga = mul2(mul2(bc2(-9.f), t.N1), rk);
+}
+
+// Reprojection terms r = ssim_w3 * sum_c SSIM + l1_w3 * sum_c |y - x| of both sources for the two pixels at R1 rows
+// (ra, ra + 1), column cx (base = pidx(ra, cx)); X2 holds what is compared with the target (warped colours, or the raw
+// sources for the identity terms).  COEFS: the SSIM coefficient fields of source 0 go to F, those of source 1 to `hold`.
+// EDGES: accumulate the |dy| sums of the smoothness edge weights.
+template <bool COEFS, bool EDGES>
+DVS_HD void pair_half(float* sm, int base, float ssim_w3, float l1_w3, float kF, f2* r, float (*hold)[3][2], float* ax,
+                      float* ay) {
+  PairLayout P;
+  const SmemLayout& L = P.L;
+  f2 rs[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}}, rl[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}};
+  DVS_UNROLL
+  for (int c = 0; c < 3; ++c) {
+    const float* Y = sm + L.y(c) + base;
+    const float* X = sm + P.x2(c) + 2 * base;
+    f2 hx[4], hxx[4], hxy[4], xc[2];
+    float hy[4], hyy[4], yc[4];
+    DVS_UNROLL
+    for (int m = 0; m < 4; ++m) {
+      const float* yr = Y + (m - 1) * PW;
+      const float* xr = X + 2 * (m - 1) * PW;
+      const float a = yr[-1], b = yr[0], d = yr[1];
+      const f2 xa = ld2(xr - 2), xb = ld2(xr), xd = ld2(xr + 2);
+      hy[m] = (a + b) + d;
+      hyy[m] = fmaf(d, d, fmaf(b, b, a * a));
+      hx[m] = add2(add2(xa, xb), xd);
+      hxx[m] = fma2(xd, xd, fma2(xb, xb, mul2(xa, xa)));
+      hxy[m] = fma2(xd, bc2(d), fma2(xb, bc2(b), mul2(xa, bc2(a))));
+      yc[m] = b;
+      if (m == 1) xc[0] = xb;
+      if (m == 2) xc[1] = xb;
+      if (EDGES && (m == 1 || m == 2)) ax[m - 1] += fabsf(b - d);
+    }
+    if (EDGES) {
+      ay[0] += fabsf(yc[1] - yc[2]);
+      ay[1] += fabsf(yc[2] - yc[3]);
+    }
+    // vertical 3-sums, shared middle partial (same order as vsum4)
+    const float uy = hy[1] + hy[2], uyy = hyy[1] + hyy[2];
+    const f2 ux = add2(hx[1], hx[2]), uxx = add2(hxx[1], hxx[2]), uxy = add2(hxy[1], hxy[2]);
+    DVS_UNROLL
+    for (int j = 0; j < 2; ++j) {
+      const float sy = j ? uy + hy[3] : hy[0] + uy;
+      const float syy = j ? uyy + hyy[3] : hyy[0] + uyy;
+      const f2 sx = j ? add2(ux, hx[3]) : add2(hx[0], ux);
+      const f2 sxx = j ? add2(uxx, hxx[3]) : add2(hxx[0], uxx);
+      const f2 sxy = j ? add2(uxy, hxy[3]) : add2(hxy[0], uxy);
+      const float ysq = sy * sy, ty = fmaf(9.f, syy, kK2);
+      SsimPair t;
+      ssim_terms2(sx, sxx, sxy, sy, ysq, ty, t);
+      rs[j] = add2(rs[j], ssim_value2(t));
+      const f2 d = sub2(bc2(yc[j + 1]), xc[j]);
+      rl[j] = f2{rl[j].x + fabsf(d.x), rl[j].y + fabsf(d.y)};
+      if (COEFS) {
+        f2 al, be, ga;
+        ssim_coefs2(t, sx, sy, kF, al, be, ga);
+        float* F = sm + L.f(c * 3) + base + j * PW;
+        F[0] = al.x; F[PLANE] = be.x; F[2 * PLANE] = ga.x;
+        hold[c][0][j] = al.y; hold[c][1][j] = be.y; hold[c][2][j] = ga.y;
+      }
+    }
+  }
+  DVS_UNROLL
+  for (int j = 0; j < 2; ++j) r[j] = fma2(bc2(ssim_w3), rs[j], mul2(bc2(l1_w3), rl[j]));
+}
+
+// ------------------------------------------------------------------------------------------------ identity
+// identity terms (parked in shared memory) + smoothness edge weights of the own pixels (scale independent).
+DVS_HD void pair_phase_identity(const FusedParams& p, const Tile& t, float* sm, int tid, PairState& st) {
+  PairLayout P;
+  const SmemLayout& L = P.L;
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  const int base0 = pidx(r0, cx);
+  const float sw3 = p.ssim_w * (1.f / 3.f), lw3 = p.l1_w * (1.f / 3.f);
+  const int gx = t.gx0 + cx;
+  float* idp = sm + P.ident() + tid;
+  DVS_NOUNROLL
+  for (int h = 0; h < 2; ++h) {
+    const int base = base0 + 2 * h * PW;
+    float ax[2] = {0.f, 0.f}, ay[2] = {0.f, 0.f};
+    f2 r[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}};
+    if (p.auto_mask) {
+      pair_half<false, true>(sm, base, sw3, lw3, 0.f, r, nullptr, ax, ay);
+    } else {
+      for (int c = 0; c < 3; ++c)
+        for (int j = 0; j < 2; ++j) {
+          int o = base + j * PW;
+          float y0 = sm[L.y(c) + o];
+          ax[j] += fabsf(y0 - sm[L.y(c) + o + 1]);
+          ay[j] += fabsf(y0 - sm[L.y(c) + o + PW]);
+        }
+    }
+    for (int j = 0; j < 2; ++j) {
+      const int jj = 2 * h + j;
+      idp[(2 * jj) * NT] = r[j].x;
+      idp[(2 * jj + 1) * NT] = r[j].y;
+      const int gy = t.gy0 + r0 + jj, o = base + j * PW;
+      const bool in = (st.flags >> jj) & 1;
+      sm[L.wx() + o] = (in && gx < p.W - 1) ? exp_fast(-ax[j] * (1.f / 3.f)) : 0.f;
+      sm[L.wy() + o] = (in && gy < p.H - 1) ? exp_fast(-ay[j] * (1.f / 3.f)) : 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ geometry (pairs)
+struct Proj2 {
+  f2 q[3];             // A (u,v,1) = d c / d D
+  f2 px, py, rz;       // un-clipped pixel coordinates, 1/(z+eps)
+  f2 tx, ty;
+  int o0, o1;          // offsets of the north-west taps inside a plane
+};
+DVS_HD void project2(const float* A2, float u, float v, float D, float eps, int H, int W, Proj2& r) {
+  const f2 u2 = bc2(u), v2 = bc2(v), D2 = bc2(D);
+  r.q[0] = fma2(ld2(A2 + 0), u2, fma2(ld2(A2 + 2), v2, ld2(A2 + 4)));
+  r.q[1] = fma2(ld2(A2 + 6), u2, fma2(ld2(A2 + 8), v2, ld2(A2 + 10)));
+  r.q[2] = fma2(ld2(A2 + 12), u2, fma2(ld2(A2 + 14), v2, ld2(A2 + 16)));
+  const f2 c0 = fma2(D2, r.q[0], ld2(A2 + 18)), c1 = fma2(D2, r.q[1], ld2(A2 + 20)), c2 = fma2(D2, r.q[2], ld2(A2 + 22));
+  r.rz = f2{rcp_fast(c2.x + eps), rcp_fast(c2.y + eps)};
+  r.px = mul2(c0, r.rz);
+  r.py = mul2(c1, r.rz);
+  const float wm = (float)(W - 1), hm = (float)(H - 1);
+  const f2 ix = f2{fminf(fmaxf(r.px.x, 0.f), wm), fminf(fmaxf(r.px.y, 0.f), wm)};
+  const f2 iy = f2{fminf(fmaxf(r.py.x, 0.f), hm), fminf(fmaxf(r.py.y, 0.f), hm)};
+  const int x0 = imin((int)ix.x, W - 2), x1 = imin((int)ix.y, W - 2);
+  const int y0 = imin((int)iy.x, H - 2), y1 = imin((int)iy.y, H - 2);
+  r.tx = sub2(ix, f2{(float)x0, (float)x1});
+  r.ty = sub2(iy, f2{(float)y0, (float)y1});
+  r.o0 = y0 * W + x0;
+  r.o1 = y1 * W + x1;
+}
+
+// ------------------------------------------------------------------------------------------------ phase W
+// warp both sources onto R2 for scale s (interleaved float2 planes); store the up-sampled disparity.
+DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
+  PairLayout P;
+  const SmemLayout& L = P.L;
+  const float* A2 = sm + P.a2();
+  const int HW = p.H * p.W;
+  const int dh = p.dh[s], dw = p.dw[s];
+  const float* d = p.disp[s] + (size_t)t.b * dh * dw;
+  const bool direct = dh == p.H && dw == p.W;
+  const float scy = (float)dh / (float)p.H, scx = (float)dw / (float)p.W;
+  const int* posp = reinterpret_cast<const int*>(sm + L.pos());
+  const float* im0 = p.src[0] + (size_t)t.b * 3 * HW;
+  const float* im1 = p.src[1] + (size_t)t.b * 3 * HW;
+  int pk = posp[tid];
+  DispTaps dt;
+  disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
+  DVS_NOUNROLL
+  for (int k = tid; k < PLANE; k += NT) {
+    const int rx = pk & 0xffff, ry = pk >> 16;
+    const float du = disp_taps_value(dt, direct);
+    if (k + NT < PLANE) {                                // disparity of the next pixel: in flight during this one
+      pk = posp[k + NT];
+      disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
+    }
+    sm[L.du() + k] = du;
+    const float D = rcp_fast(fmaf(du, p.disp_range, p.min_disp));
+    Proj2 pr;
+    project2(A2, (float)rx, (float)ry, D, p.eps, p.H, p.W, pr);
+    // all 24 tap loads of the pixel before the first use
+    f2 tap[3][4];
+    const float* a0 = im0 + pr.o0;
+    const float* a1 = im1 + pr.o1;
+    DVS_UNROLL
+    for (int ch = 0; ch < 3; ++ch) {
+      const float* q0 = a0 + ch * HW;
+      const float* q1 = a1 + ch * HW;
+      tap[ch][0] = f2{q0[0], q1[0]};
+      tap[ch][1] = f2{q0[1], q1[1]};
+      tap[ch][2] = f2{q0[p.W], q1[p.W]};
+      tap[ch][3] = f2{q0[p.W + 1], q1[p.W + 1]};
+    }
+    DVS_UNROLL
+    for (int ch = 0; ch < 3; ++ch) {
+      const f2 top = fma2(pr.tx, sub2(tap[ch][1], tap[ch][0]), tap[ch][0]);
+      const f2 bot = fma2(pr.tx, sub2(tap[ch][3], tap[ch][2]), tap[ch][2]);
+      st2(sm + P.x2(ch) + 2 * k, fma2(pr.ty, sub2(bot, top), top));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ phase S
+template <bool GRAD>
+DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid, int s, PairState& st) {
+  PairLayout P;
+  const SmemLayout& L = P.L;
+  const float* cst = sm + L.consts();
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  const int base0 = pidx(r0, cx);
+  const int gx = t.gx0 + cx, gyb = t.gy0 + r0;
+  const float sw3 = p.ssim_w * (1.f / 3.f), lw3 = p.l1_w * (1.f / 3.f);
+  const int HW = p.H * p.W;
+  const int fl = st.flags;
+  const float kF = p.ssim_w / (3.0f * (float)p.B * (float)HW);
+  const float* idp = sm + P.ident() + tid;
+  unsigned char* selp = reinterpret_cast<unsigned char*>(sm + L.sel());
+  const int off = p.auto_mask ? 2 : 0;
+  int tags = 0;
+  float photo = 0.f;
+
+  DVS_NOUNROLL
+  for (int h = 0; h < 2; ++h) {
+    const int base = base0 + 2 * h * PW;
+    f2 r[2];
+    float hold[3][3][2];
+    pair_half<GRAD, false>(sm, base, sw3, lw3, kF, r, hold, nullptr, nullptr);
+    DVS_UNROLL
+    for (int j = 0; j < 2; ++j) {
+      const int jj = 2 * h + j;
+      const bool in = (fl >> jj) & 1;
+      float best = 3.0e38f;
+      int tag = kSelNone, chan = 0;
+      if (p.auto_mask) {
+        float n0 = 0.f, n1 = 0.f;
+        if (in) {
+          const int gy = gyb + jj;
+          if (p.noise[s]) {
+            n0 = p.noise[s][((size_t)(t.b * 2) * p.H + gy) * p.W + gx];
+            n1 = p.noise[s][((size_t)(t.b * 2 + 1) * p.H + gy) * p.W + gx];
+          } else {
+            hash_normal2(p.seed, p.offset, (unsigned)((t.b * p.H + gy) * p.W + gx), (unsigned)(s * kMaxN), n0, n1);
+          }
+        }
+        const float v0 = fmaf(n0, 0.00001f, idp[(2 * jj) * NT]);
+        const float v1 = fmaf(n1, 0.00001f, idp[(2 * jj + 1) * NT]);
+        if (v0 < best) { best = v0; chan = 0; }
+        if (v1 < best) { best = v1; chan = 1; }
+      }
+      if (r[j].x < best) { best = r[j].x; chan = off; tag = 0; }
+      if (r[j].y < best) { best = r[j].y; chan = off + 1; tag = 1; }
+      if (!in) tag = kSelNone;
+      tags |= tag << (8 * jj);
+      selp[base + j * PW] = (unsigned char)tag;
+      if ((fl >> (4 + jj)) & 1) {
+        photo += best;
+        if (p.sel[s]) p.sel[s][((size_t)t.b * p.H + gyb + jj) * p.W + gx] = (unsigned char)chan;
+      }
+      if (GRAD && tag != 0) {
+        // F holds source 0's fields: replace them by source 1's where it won, by exact zeros where neither did
+        float* F = sm + L.f(0) + base + j * PW;
+        DVS_UNROLL
+        for (int c = 0; c < 3; ++c)
+          DVS_UNROLL
+          for (int f = 0; f < 3; ++f) F[(c * 3 + f) * PLANE] = tag == 1 ? hold[c][f][j] : 0.f;
+      }
+    }
+  }
+  st.tags = tags;
+  st.acc[0] += photo;
+
+  // smoothness on the normalised up-sampled disparity (own pixels)
+  const float inv_mu = cst[kC_invmu + s];
+  const float kap = p.smooth_w / (float)(1 << s);
+  const float kx = kap / ((float)p.B * (float)p.H * (float)(p.W - 1));
+  const float ky = kap / ((float)p.B * (float)(p.H - 1) * (float)p.W);
+  const float* DU = sm + L.du();
+  const float* WX = sm + L.wx();
+  const float* WY = sm + L.wy();
+  for (int j = 0; j < 4; ++j) {
+    st.gdu[j] = 0.f;
+    if (!((fl >> (4 + j)) & 1)) continue;
+    int o = base0 + j * PW;
+    // difference first, then normalise (see phase_stats)
+    float d0 = DU[o];
+    float dxr = (d0 - DU[o + 1]) * inv_mu, dxl = (DU[o - 1] - d0) * inv_mu;
+    float dyd = (d0 - DU[o + PW]) * inv_mu, dyu = (DU[o - PW] - d0) * inv_mu;
+    float wxr = WX[o], wxl = WX[o - 1], wyd = WY[o], wyu = WY[o - PW];
+    st.acc[1] += fabsf(dxr) * wxr;
+    st.acc[2] += fabsf(dyd) * wyd;
+    if (GRAD) {
+      float gn = kx * (sgn(dxr) * wxr - sgn(dxl) * wxl) + ky * (sgn(dyd) * wyd - sgn(dyu) * wyu);
+      st.gdu[j] = gn * inv_mu;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ phase G
+// own pixels: pooled adjoint of the coefficient fields for both sources in one sweep -> d loss / d warped colour ->
+// sampling coordinates -> depth / pose moments.  Accumulates st.gdu and st.M.
+DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, int s, PairState& st) {
+  PairLayout P;
+  const SmemLayout& L = P.L;
+  if (!(st.flags >> 4)) return;                       // no own pixel
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  const int base = pidx(r0, cx);
+  const int gx = t.gx0 + cx, gyb = t.gy0 + r0;
+  const int HW = p.H * p.W;
+  const unsigned char* selp = reinterpret_cast<const unsigned char*>(sm + L.sel());
+  const float l1k = p.l1_w / (3.0f * (float)p.B * (float)HW);
+  // reflection adjoint: the pad ring mirrors row/column 1 (and H-2 / W-2)
+  const float wl = (gx == 1) ? 2.f : 1.f, wr = (gx == p.W - 2) ? 2.f : 1.f;
+  const bool edge_rows = (gyb <= 1 && gyb + 3 >= 1) || (gyb <= p.H - 2 && gyb + 3 >= p.H - 2);
+  const float u = (float)gx;
+
+  // masks of source 0 on row pairs (2 m2, 2 m2 + 1), and "any reprojection selected in the neighbourhood"
+  f2 mk[3][3];
+  bool any = false;
+  for (int m = 0; m < 6; ++m)
+    for (int k = 0; k < 3; ++k) {
+      const int tg = selp[base + (m - 1) * PW + k - 1];
+      any = any || tg != kSelNone;
+      const float w = (tg == 0) ? (k == 0 ? wl : (k == 2 ? wr : 1.f)) : 0.f;
+      if (m & 1) mk[m >> 1][k].y = w; else mk[m >> 1][k].x = w;
+    }
+  if (!any) return;                                    // F is all zero around the own pixels: no photometric gradient
+  const f2 wl2 = bc2(wl), wr2 = bc2(wr), one2 = bc2(1.f);
+
+  f2 G[3][4];
+  DVS_UNROLL
+  for (int c = 0; c < 3; ++c) {
+    f2 pooled[3][4];                                    // (source 0, source 1) per field and pixel
+    DVS_UNROLL
+    for (int f = 0; f < 3; ++f) {
+      const float* F = sm + L.f(c * 3 + f) + base;
+      f2 hT[3], h0[3];
+      for (int m2 = 0; m2 < 3; ++m2) {
+        const float* ra = F + (2 * m2 - 1) * PW;
+        const float* rb = ra + PW;
+        const f2 lft{ra[-1], rb[-1]}, mid{ra[0], rb[0]}, rgt{ra[1], rb[1]};
+        // same operation order in both sums: where every selected neighbour chose source 0 they are bit-equal
+        hT[m2] = fma2(rgt, wr2, fma2(mid, one2, mul2(lft, wl2)));
+        h0[m2] = fma2(rgt, mk[m2][2], fma2(mid, mk[m2][1], mul2(lft, mk[m2][0])));
+      }
+      float pT[4], p0[4];
+      vsum4(hT, pT);
+      vsum4(h0, p0);
+      if (edge_rows) {
+        const float hsT[6] = {hT[0].x, hT[0].y, hT[1].x, hT[1].y, hT[2].x, hT[2].y};
+        const float hs0[6] = {h0[0].x, h0[0].y, h0[1].x, h0[1].y, h0[2].x, h0[2].y};
+        for (int j = 0; j < 4; ++j) {
+          if (gyb + j == 1) { pT[j] += hsT[j]; p0[j] += hs0[j]; }
+          if (gyb + j == p.H - 2) { pT[j] += hsT[j + 2]; p0[j] += hs0[j + 2]; }
+        }
+      }
+      for (int j = 0; j < 4; ++j) pooled[f][j] = f2{p0[j], pT[j] - p0[j]};
+    }
+    const float* X = sm + P.x2(c) + 2 * base;
+    const float* Y = sm + L.y(c) + base;
+    for (int j = 0; j < 4; ++j) {
+      const f2 x = ld2(X + 2 * j * PW);
+      const float y = Y[j * PW];
+      f2 g = fma2(add2(x, x), pooled[1][j], fma2(bc2(y), pooled[2][j], pooled[0][j]));
+      const int tg = (st.tags >> (8 * j)) & 0xff;
+      if (tg == 0) g.x -= l1k * sgn(y - x.x);
+      if (tg == 1) g.y -= l1k * sgn(y - x.y);
+#if defined(DVS_FAULT_GRAD_SCALE)
+      g = mul2(g, bc2(DVS_FAULT_GRAD_SCALE));
+#endif
+      G[c][j] = g;
+    }
+  }
+
+  // chain through the bilinear gather and the projection (taps re-read; they are L1/L2 resident)
+  const float* A2 = sm + P.a2();
+  const float* im0 = p.src[0] + (size_t)t.b * 3 * HW;
+  const float* im1 = p.src[1] + (size_t)t.b * 3 * HW;
+  DVS_NOUNROLL
+  for (int j = 0; j < 4; ++j) {
+    const f2 g0 = j == 0 ? G[0][0] : (j == 1 ? G[0][1] : (j == 2 ? G[0][2] : G[0][3]));
+    const f2 g1 = j == 0 ? G[1][0] : (j == 1 ? G[1][1] : (j == 2 ? G[1][2] : G[1][3]));
+    const f2 g2 = j == 0 ? G[2][0] : (j == 1 ? G[2][1] : (j == 2 ? G[2][2] : G[2][3]));
+    if (!((st.flags >> (4 + j)) & 1)) continue;
+    if (g0.x == 0.f && g1.x == 0.f && g2.x == 0.f && g0.y == 0.f && g1.y == 0.f && g2.y == 0.f) continue;
+    const float v = (float)(gyb + j);
+    const float D = rcp_fast(fmaf(sm[L.du() + base + j * PW], p.disp_range, p.min_disp));
+    Proj2 pr;
+    project2(A2, u, v, D, p.eps, p.H, p.W, pr);
+    f2 tap[3][4];
+    const float* a0 = im0 + pr.o0;
+    const float* a1 = im1 + pr.o1;
+    DVS_UNROLL
+    for (int ch = 0; ch < 3; ++ch) {
+      const float* q0 = a0 + ch * HW;
+      const float* q1 = a1 + ch * HW;
+      tap[ch][0] = f2{q0[0], q1[0]};
+      tap[ch][1] = f2{q0[1], q1[1]};
+      tap[ch][2] = f2{q0[p.W], q1[p.W]};
+      tap[ch][3] = f2{q0[p.W + 1], q1[p.W + 1]};
+    }
+    f2 gix = f2{0.f, 0.f}, giy = f2{0.f, 0.f};
+    DVS_UNROLL
+    for (int ch = 0; ch < 3; ++ch) {
+      const f2 gc = ch == 0 ? g0 : (ch == 1 ? g1 : g2);
+      const f2 dtp = sub2(tap[ch][1], tap[ch][0]), dbt = sub2(tap[ch][3], tap[ch][2]);
+      const f2 dx = fma2(pr.ty, sub2(dbt, dtp), dtp);
+      const f2 top = fma2(pr.tx, dtp, tap[ch][0]), bot = fma2(pr.tx, dbt, tap[ch][2]);
+      const f2 dy = sub2(bot, top);
+      if (ch == 0) { gix = mul2(gc, dx); giy = mul2(gc, dy); }
+      else { gix = fma2(gc, dx, gix); giy = fma2(gc, dy, giy); }
+    }
+    // ATen clip_coordinates_set_grad: zero gradient when the coordinate was clipped (border included)
+    const float wm = (float)(p.W - 1), hm = (float)(p.H - 1);
+    if (!(pr.px.x > 0.f && pr.px.x < wm)) gix.x = 0.f;
+    if (!(pr.px.y > 0.f && pr.px.y < wm)) gix.y = 0.f;
+    if (!(pr.py.x > 0.f && pr.py.x < hm)) giy.x = 0.f;
+    if (!(pr.py.y > 0.f && pr.py.y < hm)) giy.y = 0.f;
+    const f2 gc0 = mul2(gix, pr.rz), gc1 = mul2(giy, pr.rz);
+    const f2 sneg = fma2(gc0, pr.px, mul2(gc1, pr.py));
+    const f2 gc2 = f2{-sneg.x, -sneg.y};
+    const f2 gD = fma2(gc0, pr.q[0], fma2(gc1, pr.q[1], mul2(gc2, pr.q[2])));
+    const f2 gd = mul2(mul2(gD, bc2(-p.disp_range)), bc2(D * D));
+    const float gsum = gd.x + gd.y;
+    st.gdu[0] += j == 0 ? gsum : 0.f; st.gdu[1] += j == 1 ? gsum : 0.f;
+    st.gdu[2] += j == 2 ? gsum : 0.f; st.gdu[3] += j == 3 ? gsum : 0.f;
+    const f2 D2 = bc2(D), u2 = bc2(u), v2 = bc2(v);
+    const f2 w0 = mul2(gc0, D2), w1 = mul2(gc1, D2), w2 = mul2(gc2, D2);
+    st.M[0] = fma2(w0, u2, st.M[0]); st.M[1] = fma2(w0, v2, st.M[1]); st.M[2] = add2(st.M[2], w0); st.M[3] = add2(st.M[3], gc0);
+    st.M[4] = fma2(w1, u2, st.M[4]); st.M[5] = fma2(w1, v2, st.M[5]); st.M[6] = add2(st.M[6], w1); st.M[7] = add2(st.M[7], gc1);
+    st.M[8] = fma2(w2, u2, st.M[8]); st.M[9] = fma2(w2, v2, st.M[9]); st.M[10] = add2(st.M[10], w2); st.M[11] = add2(st.M[11], gc2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ glue to the shared tail
+DVS_HD void pair_store_gdu_direct(const FusedParams& p, const Tile& t, int tid, int s, const PairState& st) {
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  for (int j = 0; j < 4; ++j)
+    if ((st.flags >> (4 + j)) & 1) p.gdisp[s][((size_t)t.b * p.H + t.gy0 + r0 + j) * p.W + t.gx0 + cx] = st.gdu[j];
+}
+DVS_HD void pair_stage_gdu(float* sm, int tid, const PairState& st) {
+  SmemLayout L{2};
+  int r0, cx;
+  quad_coords(tid, r0, cx);
+  for (int j = 0; j < 4; ++j) sm[L.du() + pidx(r0 + j, cx)] = ((st.flags >> (4 + j)) & 1) ? st.gdu[j] : 0.f;
+}
+DVS_HD void pair_reduce_write(float* sm, int tid, const PairState& st) {
+  SmemLayout L{2};
+  constexpr int nv = 3 + 12 * 2;
+  float* sc = sm + L.scratch() + tid * nv;
+  sc[0] = st.acc[0]; sc[1] = st.acc[1]; sc[2] = st.acc[2];
+  DVS_UNROLL
+  for (int k = 0; k < 12; ++k) {
+    sc[3 + k] = st.M[k].x;
+    sc[15 + k] = st.M[k].y;
+  }
+}
+DVS_HD void pair_reset_scale_state(PairState& st) {
+  st.acc[0] = st.acc[1] = st.acc[2] = 0.f;
+  DVS_UNROLL
+  for (int k = 0; k < 12; ++k) st.M[k] = f2{0.f, 0.f};
+}
+
+}  // namespace dvs

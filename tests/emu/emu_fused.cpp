@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../deep-visual-slam_b200/csrc/dvs_fused_core.cuh"
+#include "../../deep-visual-slam_b200/csrc/dvs_pair_core.cuh"
 #include "../../include/dvsloss.h"
 
 using namespace dvs;
@@ -51,6 +52,54 @@ void run_block(const FusedParams& p, int blk, std::vector<float>& smv) {
   }
 }
 
+// the two-source kernel (fused_pair_kernel), same barrier structure
+template <bool GRAD>
+void run_block_pair(const FusedParams& p, int blk, std::vector<float>& smv) {
+  float* sm = smv.data();
+  Tile t = make_tile(p, blk);
+  PairLayout P;
+  std::vector<PairState> st(NT);
+  for (int tid = 0; tid < NT; ++tid) { phase_consts<2>(p, t, sm, tid, sm + P.a2()); pair_phase_load(p, t, sm, tid, st[tid]); }
+  for (int tid = 0; tid < NT; ++tid) pair_phase_identity(p, t, sm, tid, st[tid]);
+  for (int s = 0; s < p.S; ++s) {
+    for (int tid = 0; tid < NT; ++tid) { pair_reset_scale_state(st[tid]); pair_phase_warp(p, t, sm, tid, s); }
+    for (int tid = 0; tid < NT; ++tid) pair_phase_stats<GRAD>(p, t, sm, tid, s, st[tid]);
+    const bool direct = (p.dh[s] == p.H && p.dw[s] == p.W);
+    if (GRAD) {
+      for (int tid = 0; tid < NT; ++tid) pair_phase_grad(p, t, sm, tid, s, st[tid]);
+      for (int tid = 0; tid < NT; ++tid) {
+        if (direct) pair_store_gdu_direct(p, t, tid, s, st[tid]);
+        else pair_stage_gdu(sm, tid, st[tid]);
+      }
+    }
+    for (int tid = 0; tid < NT; ++tid) pair_reduce_write(sm, tid, st[tid]);
+    for (int tid = 0; tid < NT; ++tid) {
+      if (GRAD && !direct) adjoint_rows<2>(p, t, sm, tid, s);
+      reduce_stage1<2>(p, sm, tid);
+    }
+    for (int tid = 0; tid < NT; ++tid) {
+      if (GRAD && !direct) adjoint_cols<2>(p, t, sm, tid, s);
+      reduce_stage2<2>(p, t, sm, tid, s);
+    }
+  }
+}
+
+int g_generic = 0;        // 1: run two-source problems through the generic kernel code (as DVS_GENERIC_KERNEL=1 does)
+
+void run_all_pair(const FusedParams& p, int nblk) {
+  PairLayout P;
+  constexpr int kGuard = 256;
+  std::vector<float> sm(P.total() + kGuard);
+  for (int blk = 0; blk < nblk; ++blk) {
+    for (auto& v : sm) v = __builtin_nanf("");
+    for (int k = 0; k < kGuard; ++k) sm[P.total() + k] = 12345.0f + k;
+    if (p.want_grad) run_block_pair<true>(p, blk, sm);
+    else run_block_pair<false>(p, blk, sm);
+    for (int k = 0; k < kGuard; ++k)
+      if (sm[P.total() + k] != 12345.0f + k) { g_guard_hit = blk + 1; }
+  }
+}
+
 template <int NS>
 void run_all(const FusedParams& p, int nblk) {
   SmemLayout L{NS};
@@ -68,6 +117,8 @@ void run_all(const FusedParams& p, int nblk) {
 }
 
 }  // namespace
+
+extern "C" void emu_set_generic(int v) { g_generic = v; }
 
 extern "C" int emu_photometric_forward(const DvsShape* sh, const DvsParams* pr, const float* const* disp,
                                        const float* target, const float* const* src, const float* K,
@@ -120,7 +171,7 @@ extern "C" int emu_photometric_forward(const DvsShape* sh, const DvsParams* pr, 
     }
   switch (sh->N) {
     case 1: run_all<1>(p, nblk); break;
-    case 2: run_all<2>(p, nblk); break;
+    case 2: if (g_generic) run_all<2>(p, nblk); else run_all_pair(p, nblk); break;
     case 3: run_all<3>(p, nblk); break;
     case 4: run_all<4>(p, nblk); break;
     default: return DVS_EINVAL;

@@ -32,7 +32,7 @@ def build(defines=()) -> str:
     """``defines``: extra -D macros (fault-injection builds); each set of macros gets its own library file."""
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     out = OUT if not defines else OUT.replace(".so", "_" + "_".join(d.split("=")[0].lower() for d in defines) + ".so")
-    newest = max(os.path.getmtime(SRC), os.path.getmtime(CORE))
+    newest = max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(CORE.replace("dvs_fused_core", "dvs_pair_core")))
     if not os.path.exists(out) or os.path.getmtime(out) < newest:
         subprocess.check_call(["g++", "-O2", "-march=native", "-std=c++17", "-shared", "-fPIC", *[f"-D{d}" for d in defines],
                                "-o", out, SRC])
@@ -49,9 +49,12 @@ def _arr(ptrs, typ=C.c_float):
 
 
 def run(disps, target, sources, K, inv_K, Ts, noise=None, *, auto_mask=True, want_grad=True, grad_per_scale=None,
-        min_depth=0.1, max_depth=10.0, ssim_ratio=0.85, smoothness_ratio=1e-3, seed=0, offset=0, defines=()):
-    """All inputs numpy float32 (contiguous).  Returns dict like oracle.closed_form.loss_and_grads."""
+        min_depth=0.1, max_depth=10.0, ssim_ratio=0.85, smoothness_ratio=1e-3, seed=0, offset=0, defines=(),
+        generic=False):
+    """All inputs numpy float32 (contiguous).  Returns dict like oracle.closed_form.loss_and_grads.
+    ``generic``: run a two-source problem through the generic tile code instead of the two-source specialisation."""
     lib = C.CDLL(build(defines))
+    lib.emu_set_generic(int(bool(generic)))
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     disps = [f32(d) for d in disps]
     target, K, inv_K = f32(target), f32(K), f32(inv_K)

@@ -80,12 +80,15 @@ def test_process_batch_matches_live_reference(fused):
         got, ref = outputs[f"identity_selection/{s}"].cpu().numpy(), z[f"identity_selection/{s}"]
         assert got.shape == ref.shape and (got != ref).mean() < 0.01, s
     # gradients that reach the network weights: sums over every pixel of the loss's disparity / pose gradients
+    # (a bias gradient is a plain sum of per-pixel gradients of both signs: its rounding error scales with the size of the
+    # terms, not of the sum, hence the second term relative to the largest gradient of the same network)
     for net, tag in ((dnet, "depth_net"), (pnet, "pose_net")):
+        net_scale = max(np.abs(z[f"{tag}/grad/{name}"]).max() for name, _ in net.named_parameters())
         for name, q in net.named_parameters():
             ref = z[f"{tag}/grad/{name}"]
             got = q.grad.cpu().numpy()
             scale = np.abs(ref).max()
-            assert np.abs(got - ref).max() <= 2e-3 * scale + 1e-9, (tag, name, np.abs(got - ref).max() / scale)
+            assert np.abs(got - ref).max() <= 2e-3 * scale + 2e-4 * net_scale, (tag, name, np.abs(got - ref).max() / scale)
 
 
 def test_outputs_fill_lazily_for_the_unchanged_plot_call():
