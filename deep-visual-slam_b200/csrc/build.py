@@ -43,15 +43,18 @@ def _newest_dep() -> float:
     return max(os.path.getmtime(d) for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """``variant`` / ``defines``: experiment builds (``libdvsloss_<variant>.so`` with extra -D macros, selected at run time
+    with DVSLOSS_LIB=...); the default build has neither."""
     os.makedirs(OBJ_DIR, exist_ok=True)
     dep_t = _newest_dep()
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines]
+    out = OUT if not variant else OUT.replace(".so", f"_{variant}.so")
     jobs = []
     objs = []
     for src in SOURCES:
         s = os.path.join(HERE, src)
-        o = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        o = os.path.join(OBJ_DIR, src.replace(".cu", (f"_{variant}" if variant else "") + ".o"))
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), dep_t):
             jobs.append([nvcc(), *NVCC_FLAGS, *extra, "-c", s, "-o", o])
@@ -66,18 +69,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {cmd[-3]}")
-    if jobs or force or not os.path.exists(OUT):
-        cmd = [nvcc(), "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    if jobs or force or not os.path.exists(out):
+        cmd = [nvcc(), "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--variant", default="")
+    ap.add_argument("-D", dest="defines", action="append", default=[])
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    print(build(a.force, a.verbose, a.variant, a.defines))

@@ -29,6 +29,7 @@ constexpr int kMaxDevices = 64;
 // exact power-of-two pyramids of the reference the weights are the constant (H/h)(W/w).
 __global__ void __launch_bounds__(256) mean_partial_kernel(FusedParams p, float* mean_part) {
   const int chunk = blockIdx.x, b = blockIdx.y, s = blockIdx.z;
+  if (p.tile_counter && (chunk | b | s) == 0 && threadIdx.x == 0) *p.tile_counter = 0;   // for the tile kernel that follows
   const int h = p.dh[s], w = p.dw[s], n = h * w;
   const float* d = p.disp[s] + (size_t)b * n;
   const bool exact = (p.H % h == 0) && (p.W % w == 0);
@@ -117,38 +118,55 @@ __global__ void __launch_bounds__(NT, (NS <= 2 ? 2 : 1)) fused_tile_kernel(const
 template <bool GRAD>
 __global__ void __launch_bounds__(NT, 2) fused_pair_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ __align__(16) float sm[];
+  __shared__ int next_tile;
   const int tid = threadIdx.x;
-  const Tile t = make_tile(p, blockIdx.x);
   PairLayout P;
   PairState st;
 
-  phase_consts<2>(p, t, sm, tid, sm + P.a2());
-  pair_phase_load(p, t, sm, tid, st);
-  __syncthreads();
-  pair_phase_identity(p, t, sm, tid, st);
-  __syncthreads();
+  // One tile per CTA.  -DDVS_PERSISTENT switches to persistent CTAs (2 per SM) that pull tiles from a global counter;
+  // measured 4 % SLOWER at config 2 (1.650 vs 1.589 ms, gpurun_out/r2_ab2.log): CTAs launched together stay phase-locked,
+  // so the two CTAs of an SM sit in the latency-bound gather phase at the same time, whereas CTAs of a plain grid retire
+  // and start at different times and overlap gather with arithmetic.
+#if !defined(DVS_PERSISTENT)
+  for (int round = 0;; ++round) {          // one tile per CTA, grid = number of tiles
+    if (tid == 0) next_tile = round == 0 ? (int)blockIdx.x : p.nblk;
+#else
+  for (;;) {
+    if (tid == 0) next_tile = atomicAdd(p.tile_counter, 1);
+#endif
+    __syncthreads();                       // also fences the previous tile's last shared-memory reads (tbuf / rbuf)
+    const int blk = next_tile;
+    if (blk >= p.nblk) break;
+    const Tile t = make_tile(p, blk);
 
-  for (int s = 0; s < p.S; ++s) {
-    pair_reset_scale_state(st);
-    pair_phase_warp(p, t, sm, tid, s);
+    phase_consts<2>(p, t, sm, tid, sm + P.a2());
+    pair_phase_load(p, t, sm, tid, st);
     __syncthreads();
-    pair_phase_stats<GRAD>(p, t, sm, tid, s, st);
+    pair_phase_identity(p, t, sm, tid, st);
     __syncthreads();
-    const bool direct = (p.dh[s] == p.H && p.dw[s] == p.W);
-    if (GRAD) {
-      pair_phase_grad(p, t, sm, tid, s, st);
+
+    for (int s = 0; s < p.S; ++s) {
+      pair_reset_scale_state(st);
+      pair_phase_warp(p, t, sm, tid, s);
       __syncthreads();
-      if (direct) pair_store_gdu_direct(p, t, tid, s, st);
-      else pair_stage_gdu(sm, tid, st);
+      pair_phase_stats<GRAD>(p, t, sm, tid, s, st);
+      __syncthreads();
+      const bool direct = (p.dh[s] == p.H && p.dw[s] == p.W);
+      if (GRAD) {
+        pair_phase_grad(p, t, sm, tid, s, st);
+        __syncthreads();
+        if (direct) pair_store_gdu_direct(p, t, tid, s, st);
+        else pair_stage_gdu(sm, tid, st);
+      }
+      pair_reduce_write(sm, tid, st);
+      __syncthreads();
+      if (GRAD && !direct) adjoint_rows<2>(p, t, sm, tid, s);
+      reduce_stage1<2>(p, sm, tid);
+      __syncthreads();
+      if (GRAD && !direct) adjoint_cols<2>(p, t, sm, tid, s);
+      reduce_stage2<2>(p, t, sm, tid, s);
+      // as in fused_tile_kernel: the next warp phase writes only X / DU, which nobody reads any more
     }
-    pair_reduce_write(sm, tid, st);
-    __syncthreads();
-    if (GRAD && !direct) adjoint_rows<2>(p, t, sm, tid, s);
-    reduce_stage1<2>(p, sm, tid);
-    __syncthreads();
-    if (GRAD && !direct) adjoint_cols<2>(p, t, sm, tid, s);
-    reduce_stage2<2>(p, t, sm, tid, s);
-    // as in fused_tile_kernel: the next warp phase writes only X / DU, which nobody reads any more
   }
 }
 
@@ -299,7 +317,7 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(BackwardParams q) {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t mean_part, part, perimg, uT, coup, lossbuf, cpart, total;
+  size_t mean_part, part, perimg, uT, coup, lossbuf, counter, cpart, total;
   int tiles_x, tiles_y, nblk;
   int cstride, coff[kMaxS], cbw[kMaxS];
 };
@@ -315,6 +333,7 @@ static WsLayout ws_layout(const DvsShape& sh) {
   w.uT = o;        o = align_up(o + sizeof(float) * sh.S * sh.N * sh.B * 16, 256);   // used by backward_recompute
   w.coup = o;      o = align_up(o + sizeof(float) * sh.S * sh.B, 256);
   w.lossbuf = o;   o = align_up(o + sizeof(float) * 8, 256);
+  w.counter = o;   o = align_up(o + sizeof(int), 256);
   w.cstride = 0;
   for (int s = 0; s < sh.S; ++s) {
     const bool direct = sh.dh[s] == sh.H && sh.dw[s] == sh.W;
@@ -369,7 +388,19 @@ static cudaError_t launch_pair(const FusedParams& p, int nblk, cudaStream_t st) 
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < kMaxDevices) configured[dev].store(true, std::memory_order_release);
   }
-  fused_pair_kernel<GRAD><<<nblk, NT, bytes, st>>>(p);
+  static std::atomic<int> sm_count[kMaxDevices];
+  int sms = (dev >= 0 && dev < kMaxDevices) ? sm_count[dev].load(std::memory_order_relaxed) : 0;
+  if (sms <= 0) {
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < kMaxDevices) sm_count[dev].store(sms, std::memory_order_relaxed);
+  }
+#if !defined(DVS_PERSISTENT)
+  const int grid = nblk;
+#else
+  const int grid = nblk < 2 * sms ? nblk : 2 * sms;      // two resident CTAs per SM (shared memory and registers)
+#endif
+  fused_pair_kernel<GRAD><<<grid, NT, bytes, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -446,6 +477,18 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
   p.part = reinterpret_cast<float*>(base + w.part);
   p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y;
   p.cpart = reinterpret_cast<float*>(base + w.cpart);
+  p.tile_counter = reinterpret_cast<int*>(base + w.counter);
+  {
+    const float npix = 3.0f * (float)sh->B * (float)(sh->H * sh->W);
+    p.kF = p.ssim_w / npix;
+    p.l1k = p.l1_w / npix;
+    for (int s = 0; s < sh->S; ++s) {
+      const float kap = p.smooth_w / (float)(1 << s);
+      p.kxs[s] = kap / ((float)sh->B * (float)sh->H * (float)(sh->W - 1));
+      p.kys[s] = kap / ((float)sh->B * (float)(sh->H - 1) * (float)sh->W);
+    }
+  }
+  p.nblk = w.nblk;
   p.cstride = w.cstride;
   for (int s = 0; s < sh->S; ++s) { p.coff[s] = w.coff[s]; p.cbw[s] = w.cbw[s]; }
 

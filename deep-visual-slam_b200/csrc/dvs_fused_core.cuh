@@ -84,6 +84,12 @@ struct FusedParams {
   float* cpart;
   int cstride, coff[kMaxS], cbw[kMaxS];
   int tiles_x, tiles_y;
+  // persistent two-source kernel: tiles are handed out through this counter (zeroed by the disparity-mean pre-pass)
+  int* tile_counter;
+  int nblk;
+  // loop-invariant scalars of the two-source kernel, divided once on the host (IEEE, same values as on the device):
+  // kF = ssim_w / (3 B H W), l1k = l1_w / (3 B H W), kxs[s] / kys[s] = smooth_w / 2^s / (B H (W-1)) resp. (B (H-1) W)
+  float kF, l1k, kxs[kMaxS], kys[kMaxS];
 };
 
 // Upper bound of the coarse rows (columns) touched by the 30 fine rows (columns) of one tile: the clamped source

@@ -64,6 +64,43 @@ DVS_HD void pair_phase_load(const FusedParams& p, const Tile& t, float* sm, int 
   const SmemLayout& L = P.L;
   const int HW = p.H * p.W;
   int* posp = reinterpret_cast<int*>(sm + L.pos());
+#if defined(DVS_LOAD2)
+  // two pixels per iteration: 18 loads in flight before the first store (the tile load is pure latency)
+  DVS_NOUNROLL
+  for (int k = tid; k < PLANE; k += 2 * NT) {
+    const int kb = k + NT < PLANE ? k + NT : k;          // the tail repeats pixel k (same values stored twice)
+    int o[2];
+    DVS_UNROLL
+    for (int h = 0; h < 2; ++h) {
+      const int kk = h ? kb : k;
+      const int ly = kk / PW - 1, lx = kk % PW - 1;
+      const int gy = reflect_clamp(t.gy0 + ly, p.H), gx = reflect_clamp(t.gx0 + lx, p.W);
+      posp[kk] = (gy << 16) | gx;
+      o[h] = gy * p.W + gx;
+    }
+    float ty_[2][3];
+    f2 sx_[2][3];
+    DVS_UNROLL
+    for (int h = 0; h < 2; ++h) {
+      const float* tg = p.target + (size_t)t.b * 3 * HW + o[h];
+      ty_[h][0] = tg[0]; ty_[h][1] = tg[HW]; ty_[h][2] = tg[2 * HW];
+      if (p.auto_mask) {
+        const float* s0 = p.src[0] + (size_t)t.b * 3 * HW + o[h];
+        const float* s1 = p.src[1] + (size_t)t.b * 3 * HW + o[h];
+        sx_[h][0] = f2{s0[0], s1[0]}; sx_[h][1] = f2{s0[HW], s1[HW]}; sx_[h][2] = f2{s0[2 * HW], s1[2 * HW]};
+      }
+    }
+    DVS_UNROLL
+    for (int h = 0; h < 2; ++h) {
+      const int kk = h ? kb : k;
+      DVS_UNROLL
+      for (int c = 0; c < 3; ++c) {
+        sm[L.y(c) + kk] = ty_[h][c];
+        if (p.auto_mask) st2(sm + P.x2(c) + 2 * kk, sx_[h][c]);
+      }
+    }
+  }
+#else
   DVS_NOUNROLL
   for (int k = tid; k < PLANE; k += NT) {
     int ly = k / PW - 1, lx = k % PW - 1;
@@ -82,6 +119,7 @@ DVS_HD void pair_phase_load(const FusedParams& p, const Tile& t, float* sm, int 
       st2(sm + P.x2(2) + 2 * k, f2{s0[2 * HW], s1[2 * HW]});
     }
   }
+#endif
 #if defined(__CUDA_ARCH__)
   float4* f4 = reinterpret_cast<float4*>(sm + L.f(0));
   for (int k = tid; k < 9 * PLANE / 4; k += NT) f4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -123,7 +161,7 @@ DVS_HD f2 ssim_value2(const SsimPair& t) {
   return f2{sat01(fmaf(-0.5f, t.R.x, 0.5f)), sat01(fmaf(-0.5f, t.R.y, 0.5f))};
 }
 DVS_HD void ssim_coefs2(const SsimPair& t, f2 sx, float sy, float scale, f2& al, f2& be, f2& ga) {
-  const f2 rk = f2{(t.R.x >= -1.f && t.R.x <= 1.f) ? t.rd.x * scale : 0.f, (t.R.y >= -1.f && t.R.y <= 1.f) ? t.rd.y * scale : 0.f};
+  const f2 rk = f2{fabsf(t.R.x) <= 1.f ? t.rd.x * scale : 0.f, fabsf(t.R.y) <= 1.f ? t.rd.y * scale : 0.f};
   const f2 nrk = f2{-rk.x, -rk.y};
   // w = -(R sx) (D2 - D1) + sy (N2 - N1)   (the sign moved onto the difference: exact)
   const f2 w = fma2(mul2(t.R, sx), sub2(t.D1, t.D2), mul2(bc2(sy), sub2(t.N2, t.N1)));
@@ -148,14 +186,25 @@ DVS_HD void pair_half(float* sm, int base, float ssim_w3, float l1_w3, float kF,
     const float* X = sm + P.x2(c) + 2 * base;
     f2 hx[4], hxx[4], hxy[4], xc[2];
     float hy[4], hyy[4], yc[4];
+    float yv[4][3];
     DVS_UNROLL
     for (int m = 0; m < 4; ++m) {
       const float* yr = Y + (m - 1) * PW;
+      yv[m][0] = yr[-1]; yv[m][1] = yr[0]; yv[m][2] = yr[1];
+    }
+    // target-side row sums on row pairs (0,1), (2,3): packed, same operation order as the scalar form
+    DVS_UNROLL
+    for (int m2 = 0; m2 < 2; ++m2) {
+      const f2 a{yv[2 * m2][0], yv[2 * m2 + 1][0]}, b{yv[2 * m2][1], yv[2 * m2 + 1][1]}, d{yv[2 * m2][2], yv[2 * m2 + 1][2]};
+      const f2 s1 = add2(add2(a, b), d), s2 = fma2(d, d, fma2(b, b, mul2(a, a)));
+      hy[2 * m2] = s1.x; hy[2 * m2 + 1] = s1.y;
+      hyy[2 * m2] = s2.x; hyy[2 * m2 + 1] = s2.y;
+    }
+    DVS_UNROLL
+    for (int m = 0; m < 4; ++m) {
       const float* xr = X + 2 * (m - 1) * PW;
-      const float a = yr[-1], b = yr[0], d = yr[1];
+      const float a = yv[m][0], b = yv[m][1], d = yv[m][2];
       const f2 xa = ld2(xr - 2), xb = ld2(xr), xd = ld2(xr + 2);
-      hy[m] = (a + b) + d;
-      hyy[m] = fmaf(d, d, fmaf(b, b, a * a));
       hx[m] = add2(add2(xa, xb), xd);
       hxx[m] = fma2(xd, xd, fma2(xb, xb, mul2(xa, xa)));
       hxy[m] = fma2(xd, bc2(d), fma2(xb, bc2(b), mul2(xa, bc2(a))));
@@ -243,12 +292,13 @@ struct Proj2 {
   f2 tx, ty;
   int o0, o1;          // offsets of the north-west taps inside a plane
 };
-DVS_HD void project2(const float* A2, float u, float v, float D, float eps, int H, int W, Proj2& r) {
+// A: the 12 (A_0[e], A_1[e]) pairs (registers in the warp phase, re-read from shared memory in the gradient phase)
+DVS_HD void project2(const f2* A, float u, float v, float D, float eps, int H, int W, Proj2& r) {
   const f2 u2 = bc2(u), v2 = bc2(v), D2 = bc2(D);
-  r.q[0] = fma2(ld2(A2 + 0), u2, fma2(ld2(A2 + 2), v2, ld2(A2 + 4)));
-  r.q[1] = fma2(ld2(A2 + 6), u2, fma2(ld2(A2 + 8), v2, ld2(A2 + 10)));
-  r.q[2] = fma2(ld2(A2 + 12), u2, fma2(ld2(A2 + 14), v2, ld2(A2 + 16)));
-  const f2 c0 = fma2(D2, r.q[0], ld2(A2 + 18)), c1 = fma2(D2, r.q[1], ld2(A2 + 20)), c2 = fma2(D2, r.q[2], ld2(A2 + 22));
+  r.q[0] = fma2(A[0], u2, fma2(A[1], v2, A[2]));
+  r.q[1] = fma2(A[3], u2, fma2(A[4], v2, A[5]));
+  r.q[2] = fma2(A[6], u2, fma2(A[7], v2, A[8]));
+  const f2 c0 = fma2(D2, r.q[0], A[9]), c1 = fma2(D2, r.q[1], A[10]), c2 = fma2(D2, r.q[2], A[11]);
   r.rz = f2{rcp_fast(c2.x + eps), rcp_fast(c2.y + eps)};
   r.px = mul2(c0, r.rz);
   r.py = mul2(c1, r.rz);
@@ -262,13 +312,36 @@ DVS_HD void project2(const float* A2, float u, float v, float D, float eps, int 
   r.o0 = y0 * W + x0;
   r.o1 = y1 * W + x1;
 }
+// the 24 taps of one pixel (both sources, three channels): issue only
+DVS_HD void gather_taps2(const float* im0, const float* im1, int o0, int o1, int HW, int W, f2 (*tap)[4]) {
+  const float* a0 = im0 + o0;
+  const float* a1 = im1 + o1;
+  DVS_UNROLL
+  for (int ch = 0; ch < 3; ++ch) {
+    const float* q0 = a0 + ch * HW;
+    const float* q1 = a1 + ch * HW;
+    tap[ch][0] = f2{q0[0], q1[0]};
+    tap[ch][1] = f2{q0[1], q1[1]};
+    tap[ch][2] = f2{q0[W], q1[W]};
+    tap[ch][3] = f2{q0[W + 1], q1[W + 1]};
+  }
+}
+DVS_HD void lerp_store2(float* sm, int x2off, int k, f2 tx, f2 ty, const f2 (*tap)[4]) {
+  DVS_UNROLL
+  for (int ch = 0; ch < 3; ++ch) {
+    const f2 top = fma2(tx, sub2(tap[ch][1], tap[ch][0]), tap[ch][0]);
+    const f2 bot = fma2(tx, sub2(tap[ch][3], tap[ch][2]), tap[ch][2]);
+    st2(sm + x2off + 2 * ch * PLANE + 2 * k, fma2(ty, sub2(bot, top), top));
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ phase W
 // warp both sources onto R2 for scale s (interleaved float2 planes); store the up-sampled disparity.
+// Two pixels per iteration: their eight disparity taps are fetched together, then the 48 image taps of both are in flight
+// before the first interpolation (the phase is bound by the latency of the gather, not by its bandwidth).
 DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   PairLayout P;
   const SmemLayout& L = P.L;
-  const float* A2 = sm + P.a2();
   const int HW = p.H * p.W;
   const int dh = p.dh[s], dw = p.dw[s];
   const float* d = p.disp[s] + (size_t)t.b * dh * dw;
@@ -277,6 +350,90 @@ DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int 
   const int* posp = reinterpret_cast<const int*>(sm + L.pos());
   const float* im0 = p.src[0] + (size_t)t.b * 3 * HW;
   const float* im1 = p.src[1] + (size_t)t.b * 3 * HW;
+  const int x2off = P.x2(0);
+
+#if defined(DVS_WSPLIT)
+  // pass 1 (arithmetic): up-sampled disparity, projection of both sources; the bilinear weights and tap offsets are parked
+  // in the pixel's own X2 slots.  pass 2 (gather): the loop body is only "fetch weights, 24 taps, interpolate", so two
+  // pixels' taps fit in registers and the loads of the next pixel are issued before the current one is interpolated.
+  {
+    int pk = posp[tid];
+    DispTaps dt;
+    disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
+    DVS_NOUNROLL
+    for (int k = tid; k < PLANE; k += NT) {
+      const int rx = pk & 0xffff, ry = pk >> 16;
+      const float du = disp_taps_value(dt, direct);
+      if (k + NT < PLANE) {
+        pk = posp[k + NT];
+        disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
+      }
+      sm[L.du() + k] = du;
+      f2 A[12];
+      DVS_UNROLL
+      for (int e = 0; e < 12; ++e) A[e] = ld2(sm + P.a2() + 2 * e);
+      Proj2 pr;
+      project2(A, (float)rx, (float)ry, rcp_fast(fmaf(du, p.disp_range, p.min_disp)), p.eps, p.H, p.W, pr);
+      st2(sm + x2off + 2 * k, pr.tx);
+      st2(sm + x2off + 2 * PLANE + 2 * k, pr.ty);
+      reinterpret_cast<int*>(sm)[x2off + 4 * PLANE + 2 * k] = pr.o0;
+      reinterpret_cast<int*>(sm)[x2off + 4 * PLANE + 2 * k + 1] = pr.o1;
+    }
+  }
+  {
+    f2 txc = ld2(sm + x2off + 2 * tid), tyc = ld2(sm + x2off + 2 * PLANE + 2 * tid);
+    f2 tapc[3][4];
+    gather_taps2(im0, im1, reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * tid],
+                 reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * tid + 1], HW, p.W, tapc);
+    DVS_NOUNROLL
+    for (int k = tid; k < PLANE; k += 2 * NT) {
+      // pixel k is in flight in (txc, tyc, tapc); fetch k + NT, interpolate k, fetch k + 2 NT, interpolate k + NT
+      const int k1 = k + NT, k2 = k + 2 * NT;
+      f2 txn, tyn, tapn[3][4];
+      if (k1 < PLANE) {
+        txn = ld2(sm + x2off + 2 * k1); tyn = ld2(sm + x2off + 2 * PLANE + 2 * k1);
+        gather_taps2(im0, im1, reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * k1],
+                     reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * k1 + 1], HW, p.W, tapn);
+      }
+      lerp_store2(sm, x2off, k, txc, tyc, tapc);
+      if (k1 < PLANE) {
+        if (k2 < PLANE) {
+          txc = ld2(sm + x2off + 2 * k2); tyc = ld2(sm + x2off + 2 * PLANE + 2 * k2);
+          gather_taps2(im0, im1, reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * k2],
+                       reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * k2 + 1], HW, p.W, tapc);
+        }
+        lerp_store2(sm, x2off, k1, txn, tyn, tapn);
+      }
+    }
+  }
+#elif defined(DVS_W2PX)
+  DVS_NOUNROLL
+  for (int k = tid; k < PLANE; k += 2 * NT) {
+    const bool hasb = k + NT < PLANE;
+    const int kb = hasb ? k + NT : k;
+    const int pka = posp[k], pkb = posp[kb];
+    const int rxa = pka & 0xffff, rya = pka >> 16, rxb = pkb & 0xffff, ryb = pkb >> 16;
+    DispTaps dta, dtb;
+    disp_taps_load(d, dh, dw, scy, scx, direct, rya, rxa, dta);
+    disp_taps_load(d, dh, dw, scy, scx, direct, ryb, rxb, dtb);
+    f2 A[12];                                            // projection constants: re-read per iteration (registers are short here)
+    DVS_UNROLL
+    for (int e = 0; e < 12; ++e) A[e] = ld2(sm + P.a2() + 2 * e);
+    const float dua = disp_taps_value(dta, direct), dub = disp_taps_value(dtb, direct);
+    Proj2 pa, pb;
+    f2 tapa[3][4], tapb[3][4];
+    sm[L.du() + k] = dua;
+    project2(A, (float)rxa, (float)rya, rcp_fast(fmaf(dua, p.disp_range, p.min_disp)), p.eps, p.H, p.W, pa);
+    gather_taps2(im0, im1, pa.o0, pa.o1, HW, p.W, tapa);
+    if (hasb) {
+      sm[L.du() + kb] = dub;
+      project2(A, (float)rxb, (float)ryb, rcp_fast(fmaf(dub, p.disp_range, p.min_disp)), p.eps, p.H, p.W, pb);
+      gather_taps2(im0, im1, pb.o0, pb.o1, HW, p.W, tapb);
+    }
+    lerp_store2(sm, x2off, k, pa.tx, pa.ty, tapa);
+    if (hasb) lerp_store2(sm, x2off, kb, pb.tx, pb.ty, tapb);
+  }
+#else
   int pk = posp[tid];
   DispTaps dt;
   disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
@@ -289,29 +446,16 @@ DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int 
       disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
     }
     sm[L.du() + k] = du;
-    const float D = rcp_fast(fmaf(du, p.disp_range, p.min_disp));
+    f2 A[12];
+    DVS_UNROLL
+    for (int e = 0; e < 12; ++e) A[e] = ld2(sm + P.a2() + 2 * e);
     Proj2 pr;
-    project2(A2, (float)rx, (float)ry, D, p.eps, p.H, p.W, pr);
-    // all 24 tap loads of the pixel before the first use
+    project2(A, (float)rx, (float)ry, rcp_fast(fmaf(du, p.disp_range, p.min_disp)), p.eps, p.H, p.W, pr);
     f2 tap[3][4];
-    const float* a0 = im0 + pr.o0;
-    const float* a1 = im1 + pr.o1;
-    DVS_UNROLL
-    for (int ch = 0; ch < 3; ++ch) {
-      const float* q0 = a0 + ch * HW;
-      const float* q1 = a1 + ch * HW;
-      tap[ch][0] = f2{q0[0], q1[0]};
-      tap[ch][1] = f2{q0[1], q1[1]};
-      tap[ch][2] = f2{q0[p.W], q1[p.W]};
-      tap[ch][3] = f2{q0[p.W + 1], q1[p.W + 1]};
-    }
-    DVS_UNROLL
-    for (int ch = 0; ch < 3; ++ch) {
-      const f2 top = fma2(pr.tx, sub2(tap[ch][1], tap[ch][0]), tap[ch][0]);
-      const f2 bot = fma2(pr.tx, sub2(tap[ch][3], tap[ch][2]), tap[ch][2]);
-      st2(sm + P.x2(ch) + 2 * k, fma2(pr.ty, sub2(bot, top), top));
-    }
+    gather_taps2(im0, im1, pr.o0, pr.o1, HW, p.W, tap);   // all 24 tap loads of the pixel before the first use
+    lerp_store2(sm, x2off, k, pr.tx, pr.ty, tap);
   }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ phase S
@@ -327,7 +471,7 @@ DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int
   const float sw3 = p.ssim_w * (1.f / 3.f), lw3 = p.l1_w * (1.f / 3.f);
   const int HW = p.H * p.W;
   const int fl = st.flags;
-  const float kF = p.ssim_w / (3.0f * (float)p.B * (float)HW);
+  const float kF = p.kF;
   const float* idp = sm + P.ident() + tid;
   unsigned char* selp = reinterpret_cast<unsigned char*>(sm + L.sel());
   const int off = p.auto_mask ? 2 : 0;
@@ -348,7 +492,16 @@ DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int
       int tag = kSelNone, chan = 0;
       if (p.auto_mask) {
         float n0 = 0.f, n1 = 0.f;
-        if (in) {
+        const float id0 = idp[(2 * jj) * NT], id1 = idp[(2 * jj + 1) * NT];
+        // The in-kernel generator is bounded (|n| <= sqrt(48 ln 2) = 5.77, i.e. 5.77e-5 after scaling): where a
+        // reprojection term beats both identity terms by more than that, no draw can change the outcome (minimum,
+        // argmin and loss value are the reprojection's), so the draw is skipped.  Given noise tensors are always read.
+#if defined(DVS_NO_NOISE_SKIP)
+        const bool need = true;
+#else
+        const bool need = p.noise[s] != nullptr || !(fminf(r[j].x, r[j].y) < fminf(id0, id1) - 6.0e-5f);
+#endif
+        if (in && need) {
           const int gy = gyb + jj;
           if (p.noise[s]) {
             n0 = p.noise[s][((size_t)(t.b * 2) * p.H + gy) * p.W + gx];
@@ -357,8 +510,8 @@ DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int
             hash_normal2(p.seed, p.offset, (unsigned)((t.b * p.H + gy) * p.W + gx), (unsigned)(s * kMaxN), n0, n1);
           }
         }
-        const float v0 = fmaf(n0, 0.00001f, idp[(2 * jj) * NT]);
-        const float v1 = fmaf(n1, 0.00001f, idp[(2 * jj + 1) * NT]);
+        const float v0 = fmaf(n0, 0.00001f, id0);
+        const float v1 = fmaf(n1, 0.00001f, id1);
         if (v0 < best) { best = v0; chan = 0; }
         if (v1 < best) { best = v1; chan = 1; }
       }
@@ -386,9 +539,7 @@ DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int
 
   // smoothness on the normalised up-sampled disparity (own pixels)
   const float inv_mu = cst[kC_invmu + s];
-  const float kap = p.smooth_w / (float)(1 << s);
-  const float kx = kap / ((float)p.B * (float)p.H * (float)(p.W - 1));
-  const float ky = kap / ((float)p.B * (float)(p.H - 1) * (float)p.W);
+  const float kx = p.kxs[s], ky = p.kys[s];
   const float* DU = sm + L.du();
   const float* WX = sm + L.wx();
   const float* WY = sm + L.wy();
@@ -423,7 +574,7 @@ DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int 
   const int gx = t.gx0 + cx, gyb = t.gy0 + r0;
   const int HW = p.H * p.W;
   const unsigned char* selp = reinterpret_cast<const unsigned char*>(sm + L.sel());
-  const float l1k = p.l1_w / (3.0f * (float)p.B * (float)HW);
+  const float l1k = p.l1k;
   // reflection adjoint: the pad ring mirrors row/column 1 (and H-2 / W-2)
   const float wl = (gx == 1) ? 2.f : 1.f, wr = (gx == p.W - 2) ? 2.f : 1.f;
   const bool edge_rows = (gyb <= 1 && gyb + 3 >= 1) || (gyb <= p.H - 2 && gyb + 3 >= p.H - 2);
@@ -442,7 +593,10 @@ DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int 
   if (!any) return;                                    // F is all zero around the own pixels: no photometric gradient
   const f2 wl2 = bc2(wl), wr2 = bc2(wr), one2 = bc2(1.f);
 
+  // d loss / d warped colour of the own pixels, (source 0, source 1)
+#if defined(DVS_GREGS)
   f2 G[3][4];
+#endif
   DVS_UNROLL
   for (int c = 0; c < 3; ++c) {
     f2 pooled[3][4];                                    // (source 0, source 1) per field and pixel
@@ -471,7 +625,7 @@ DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int 
       }
       for (int j = 0; j < 4; ++j) pooled[f][j] = f2{p0[j], pT[j] - p0[j]};
     }
-    const float* X = sm + P.x2(c) + 2 * base;
+    float* X = sm + P.x2(c) + 2 * base;
     const float* Y = sm + L.y(c) + base;
     for (int j = 0; j < 4; ++j) {
       const f2 x = ld2(X + 2 * j * PW);
@@ -483,37 +637,40 @@ DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int 
 #if defined(DVS_FAULT_GRAD_SCALE)
       g = mul2(g, bc2(DVS_FAULT_GRAD_SCALE));
 #endif
+#if !defined(DVS_GREGS)
+      st2(X + 2 * j * PW, g);      // over the warped colour itself: only this thread reads its own pixels' X2 entries here
+#else
       G[c][j] = g;
+#endif
     }
   }
 
   // chain through the bilinear gather and the projection (taps re-read; they are L1/L2 resident)
-  const float* A2 = sm + P.a2();
   const float* im0 = p.src[0] + (size_t)t.b * 3 * HW;
   const float* im1 = p.src[1] + (size_t)t.b * 3 * HW;
   DVS_NOUNROLL
   for (int j = 0; j < 4; ++j) {
+#if !defined(DVS_GREGS)
+    if (!((st.flags >> (4 + j)) & 1)) continue;
+    const f2 g0 = ld2(sm + P.x2(0) + 2 * (base + j * PW));
+    const f2 g1 = ld2(sm + P.x2(1) + 2 * (base + j * PW));
+    const f2 g2 = ld2(sm + P.x2(2) + 2 * (base + j * PW));
+#else
     const f2 g0 = j == 0 ? G[0][0] : (j == 1 ? G[0][1] : (j == 2 ? G[0][2] : G[0][3]));
     const f2 g1 = j == 0 ? G[1][0] : (j == 1 ? G[1][1] : (j == 2 ? G[1][2] : G[1][3]));
     const f2 g2 = j == 0 ? G[2][0] : (j == 1 ? G[2][1] : (j == 2 ? G[2][2] : G[2][3]));
     if (!((st.flags >> (4 + j)) & 1)) continue;
+#endif
     if (g0.x == 0.f && g1.x == 0.f && g2.x == 0.f && g0.y == 0.f && g1.y == 0.f && g2.y == 0.f) continue;
     const float v = (float)(gyb + j);
     const float D = rcp_fast(fmaf(sm[L.du() + base + j * PW], p.disp_range, p.min_disp));
-    Proj2 pr;
-    project2(A2, u, v, D, p.eps, p.H, p.W, pr);
-    f2 tap[3][4];
-    const float* a0 = im0 + pr.o0;
-    const float* a1 = im1 + pr.o1;
+    f2 A[12];
     DVS_UNROLL
-    for (int ch = 0; ch < 3; ++ch) {
-      const float* q0 = a0 + ch * HW;
-      const float* q1 = a1 + ch * HW;
-      tap[ch][0] = f2{q0[0], q1[0]};
-      tap[ch][1] = f2{q0[1], q1[1]};
-      tap[ch][2] = f2{q0[p.W], q1[p.W]};
-      tap[ch][3] = f2{q0[p.W + 1], q1[p.W + 1]};
-    }
+    for (int e = 0; e < 12; ++e) A[e] = ld2(sm + P.a2() + 2 * e);
+    Proj2 pr;
+    project2(A, u, v, D, p.eps, p.H, p.W, pr);
+    f2 tap[3][4];
+    gather_taps2(im0, im1, pr.o0, pr.o1, HW, p.W, tap);
     f2 gix = f2{0.f, 0.f}, giy = f2{0.f, 0.f};
     DVS_UNROLL
     for (int ch = 0; ch < 3; ++ch) {

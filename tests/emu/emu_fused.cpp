@@ -155,6 +155,16 @@ extern "C" int emu_photometric_forward(const DvsShape* sh, const DvsParams* pr, 
     cstride += direct ? 0 : coarse_box_extent(p.dh[s], p.H) * p.cbw[s];
   }
   p.cstride = cstride;
+  {
+    const float npix = 3.0f * (float)sh->B * (float)(sh->H * sh->W);
+    p.kF = p.ssim_w / npix;
+    p.l1k = p.l1_w / npix;
+    for (int s = 0; s < sh->S; ++s) {
+      const float kap = p.smooth_w / (float)(1 << s);
+      p.kxs[s] = kap / ((float)sh->B * (float)sh->H * (float)(sh->W - 1));
+      p.kys[s] = kap / ((float)sh->B * (float)(sh->H - 1) * (float)sh->W);
+    }
+  }
   std::vector<float> cpart((size_t)nblk * cstride + 1, __builtin_nanf(""));
   p.cpart = cpart.data();
 
