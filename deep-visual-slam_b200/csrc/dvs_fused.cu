@@ -16,8 +16,9 @@
 #include <atomic>
 
 #include "../../include/dvsloss.h"
+#include <cuda_bf16.h>
+
 #include "dvs_fused_core.cuh"
-#include "dvs_pair_core.cuh"
 #include "dvs_host.h"
 
 namespace dvs {
@@ -29,14 +30,23 @@ constexpr int kMaxDevices = 64;
 // exact power-of-two pyramids of the reference the weights are the constant (H/h)(W/w).
 __global__ void __launch_bounds__(256) mean_partial_kernel(FusedParams p, float* mean_part) {
   const int chunk = blockIdx.x, b = blockIdx.y, s = blockIdx.z;
-  if (p.tile_counter && (chunk | b | s) == 0 && threadIdx.x == 0) *p.tile_counter = 0;   // for the tile kernel that follows
   const int h = p.dh[s], w = p.dw[s], n = h * w;
   const float* d = p.disp[s] + (size_t)b * n;
   const bool exact = (p.H % h == 0) && (p.W % w == 0);
   const int per = (n + kMeanBlocks - 1) / kMeanBlocks;
   const int lo = chunk * per, hi = min(lo + per, n);
   float acc = 0.f;
-  if (exact) {
+  if (p.io_flags & 1) {
+    // bf16 disparities (two-source kernel only): widened on load; same summation weights
+    const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(p.disp[s]) + (size_t)b * n;
+    const float cw = exact ? (float)((p.H / h) * (p.W / w)) : 0.f;
+    for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+      const float v = __bfloat162float(db[e]);
+      if (exact) acc += v;
+      else acc = fmaf(up_weight(e / w, h, p.H) * up_weight(e % w, w, p.W), v, acc);
+    }
+    if (exact) acc *= cw;
+  } else if (exact) {
     // constant weight: plain sum, 128-bit loads where the chunk is aligned (independent accumulators keep several
     // loads in flight per thread), scalar head/tail
     const float cw = (float)((p.H / h) * (p.W / w));
@@ -111,62 +121,6 @@ __global__ void __launch_bounds__(NT, (NS <= 2 ? 2 : 1)) fused_tile_kernel(const
     // no barrier needed here: the next phase_warp writes only X/DU, which nobody reads any more
     // (adjoint_cols / reduce_stage2 read the F region, next written after the following barrier) ...
     // ... except adjoint_rows' input DU: all threads passed the barrier after adjoint_rows already.
-  }
-}
-
-// Two-source specialisation (dvs_pair_core.cuh): per-source arithmetic on (source 0, source 1) pairs, packed fp32.
-template <bool GRAD>
-__global__ void __launch_bounds__(NT, 2) fused_pair_kernel(const __grid_constant__ FusedParams p) {
-  extern __shared__ __align__(16) float sm[];
-  __shared__ int next_tile;
-  const int tid = threadIdx.x;
-  PairLayout P;
-  PairState st;
-
-  // One tile per CTA.  -DDVS_PERSISTENT switches to persistent CTAs (2 per SM) that pull tiles from a global counter;
-  // measured 4 % SLOWER at config 2 (1.650 vs 1.589 ms, gpurun_out/r2_ab2.log): CTAs launched together stay phase-locked,
-  // so the two CTAs of an SM sit in the latency-bound gather phase at the same time, whereas CTAs of a plain grid retire
-  // and start at different times and overlap gather with arithmetic.
-#if !defined(DVS_PERSISTENT)
-  for (int round = 0;; ++round) {          // one tile per CTA, grid = number of tiles
-    if (tid == 0) next_tile = round == 0 ? (int)blockIdx.x : p.nblk;
-#else
-  for (;;) {
-    if (tid == 0) next_tile = atomicAdd(p.tile_counter, 1);
-#endif
-    __syncthreads();                       // also fences the previous tile's last shared-memory reads (tbuf / rbuf)
-    const int blk = next_tile;
-    if (blk >= p.nblk) break;
-    const Tile t = make_tile(p, blk);
-
-    phase_consts<2>(p, t, sm, tid, sm + P.a2());
-    pair_phase_load(p, t, sm, tid, st);
-    __syncthreads();
-    pair_phase_identity(p, t, sm, tid, st);
-    __syncthreads();
-
-    for (int s = 0; s < p.S; ++s) {
-      pair_reset_scale_state(st);
-      pair_phase_warp(p, t, sm, tid, s);
-      __syncthreads();
-      pair_phase_stats<GRAD>(p, t, sm, tid, s, st);
-      __syncthreads();
-      const bool direct = (p.dh[s] == p.H && p.dw[s] == p.W);
-      if (GRAD) {
-        pair_phase_grad(p, t, sm, tid, s, st);
-        __syncthreads();
-        if (direct) pair_store_gdu_direct(p, t, tid, s, st);
-        else pair_stage_gdu(sm, tid, st);
-      }
-      pair_reduce_write(sm, tid, st);
-      __syncthreads();
-      if (GRAD && !direct) adjoint_rows<2>(p, t, sm, tid, s);
-      reduce_stage1<2>(p, sm, tid);
-      __syncthreads();
-      if (GRAD && !direct) adjoint_cols<2>(p, t, sm, tid, s);
-      reduce_stage2<2>(p, t, sm, tid, s);
-      // as in fused_tile_kernel: the next warp phase writes only X / DU, which nobody reads any more
-    }
   }
 }
 
@@ -270,6 +224,7 @@ struct BackwardParams {
   const float* uT;                // [S][N][B][16]
   const float* coup;              // [S][B]
   float* gT[kMaxN];
+  int out_bf16;                   // grad_disp tensors are bf16 (disparities were bf16)
 };
 __global__ void __launch_bounds__(256) backward_scale_kernel(BackwardParams q) {
   const int s = blockIdx.y;
@@ -289,6 +244,19 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(BackwardParams q) {
   const bool exact = (q.H % h == 0) && (q.W % w == 0);
   const float cwc = exact ? (float)((q.H / h) * (q.W / w)) : 0.f;
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q.out_bf16) {
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(q.out[s]);
+    for (size_t e = t0; e < n; e += stride) {
+      const int b = (int)(e / hw);
+      float wgt = cwc;
+      if (!exact) {
+        const int r = (int)(e - (size_t)b * hw);
+        wgt = up_weight(r / w, h, q.H) * up_weight(r - (r / w) * w, w, q.W);
+      }
+      ob[e] = __float2bfloat16_rn(gs * (q.u[s][e] - q.coup[s * q.B + b] * wgt));
+    }
+    return;
+  }
   if (exact && (hw & 3) == 0 && ((((uintptr_t)q.u[s]) | ((uintptr_t)q.out[s])) & 15) == 0) {
     // constant up-sampling weight and whole float4s inside one image: 128-bit loads and stores
     const float4* u4 = reinterpret_cast<const float4*>(q.u[s]);
@@ -317,7 +285,7 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(BackwardParams q) {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t mean_part, part, perimg, uT, coup, lossbuf, counter, cpart, total;
+  size_t mean_part, part, perimg, uT, coup, lossbuf, cpart, total;
   int tiles_x, tiles_y, nblk;
   int cstride, coff[kMaxS], cbw[kMaxS];
 };
@@ -333,7 +301,6 @@ static WsLayout ws_layout(const DvsShape& sh) {
   w.uT = o;        o = align_up(o + sizeof(float) * sh.S * sh.N * sh.B * 16, 256);   // used by backward_recompute
   w.coup = o;      o = align_up(o + sizeof(float) * sh.S * sh.B, 256);
   w.lossbuf = o;   o = align_up(o + sizeof(float) * 8, 256);
-  w.counter = o;   o = align_up(o + sizeof(int), 256);
   w.cstride = 0;
   for (int s = 0; s < sh.S; ++s) {
     const bool direct = sh.dh[s] == sh.H && sh.dw[s] == sh.W;
@@ -375,35 +342,6 @@ static cudaError_t launch_tile(const FusedParams& p, int nblk, cudaStream_t st) 
   return cudaGetLastError();
 }
 
-template <bool GRAD>
-static cudaError_t launch_pair(const FusedParams& p, int nblk, cudaStream_t st) {
-  PairLayout P;
-  size_t bytes = (size_t)P.total() * sizeof(float);
-  static std::atomic<bool> configured[kMaxDevices];
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= kMaxDevices || !configured[dev].load(std::memory_order_acquire)) {
-    e = cudaFuncSetAttribute(fused_pair_kernel<GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < kMaxDevices) configured[dev].store(true, std::memory_order_release);
-  }
-  static std::atomic<int> sm_count[kMaxDevices];
-  int sms = (dev >= 0 && dev < kMaxDevices) ? sm_count[dev].load(std::memory_order_relaxed) : 0;
-  if (sms <= 0) {
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < kMaxDevices) sm_count[dev].store(sms, std::memory_order_relaxed);
-  }
-#if !defined(DVS_PERSISTENT)
-  const int grid = nblk;
-#else
-  const int grid = nblk < 2 * sms ? nblk : 2 * sms;      // two resident CTAs per SM (shared memory and registers)
-#endif
-  fused_pair_kernel<GRAD><<<grid, NT, bytes, st>>>(p);
-  return cudaGetLastError();
-}
-
 // DVS_GENERIC_KERNEL=1 routes two-source problems through the generic kernel (A/B measurements, regression tests).
 static bool use_generic_kernel() {
   static const bool v = [] { const char* e = getenv("DVS_GENERIC_KERNEL"); return e && e[0] == '1'; }();
@@ -411,7 +349,8 @@ static bool use_generic_kernel() {
 }
 
 static cudaError_t dispatch_tile(const FusedParams& p, int nblk, cudaStream_t st) {
-  if (p.N == 2 && !use_generic_kernel()) return p.want_grad ? launch_pair<true>(p, nblk, st) : launch_pair<false>(p, nblk, st);
+  if (p.N == 2 && (!use_generic_kernel() || p.io_flags)) return launch_pair_kernel(p, nblk, st);
+  if (p.io_flags) return cudaErrorNotSupported;     // bf16 / uint8 inputs: two-source kernel only (run_forward rejects it earlier)
   switch (p.N * 2 + (p.want_grad ? 1 : 0)) {
     case 2: return launch_tile<1, false>(p, nblk, st);
     case 3: return launch_tile<1, true>(p, nblk, st);
@@ -440,9 +379,10 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
                        const float* const* src, const float* K, const float* inv_K, const float* const* T,
                        const float* const* noise, uint64_t seed, uint64_t offset, float* loss_per_scale,
                        float* loss_total, uint8_t* const* sel, float* const* ugrad_disp, float* uT, float* coup,
-                       void* workspace, cudaStream_t st) {
+                       void* workspace, cudaStream_t st, int io_flags = 0) {
   int rc = check_shape(sh);
   if (rc) return rc;
+  if (io_flags && sh->N != 2) return DVS_EINVAL;      // bf16 / uint8 inputs are read by the two-source kernel only
   if (!pr || !disp || !target || !src || !K || !inv_K || !T || !loss_per_scale || !loss_total) return DVS_EINVAL;
   if (!workspace || ((uintptr_t)workspace & 255)) return DVS_EWORKSPACE;
   const bool want_grad = ugrad_disp != nullptr;
@@ -477,7 +417,6 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
   p.part = reinterpret_cast<float*>(base + w.part);
   p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y;
   p.cpart = reinterpret_cast<float*>(base + w.cpart);
-  p.tile_counter = reinterpret_cast<int*>(base + w.counter);
   {
     const float npix = 3.0f * (float)sh->B * (float)(sh->H * sh->W);
     p.kF = p.ssim_w / npix;
@@ -489,6 +428,7 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
     }
   }
   p.nblk = w.nblk;
+  p.io_flags = io_flags;
   p.cstride = w.cstride;
   for (int s = 0; s < sh->S; ++s) { p.coff[s] = w.coff[s]; p.cbw[s] = w.cbw[s]; }
 
@@ -540,8 +480,9 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
 }
 
 static int run_backward(const DvsShape* sh, const float* g, const float* const* u, const float* uT, const float* coup,
-                        float* const* grad_disp, float* const* grad_T, cudaStream_t st) {
+                        float* const* grad_disp, float* const* grad_T, cudaStream_t st, int out_bf16 = 0) {
   BackwardParams q{};
+  q.out_bf16 = out_bf16;
   q.B = sh->B; q.H = sh->H; q.W = sh->W; q.N = sh->N; q.S = sh->S;
   q.g = g; q.uT = uT; q.coup = coup;
   for (int s = 0; s < sh->S; ++s) {
@@ -605,6 +546,43 @@ extern "C" int dvs_photometric_forward(const DvsShape* shape, const DvsParams* p
   float* coup = ugrad_T ? ugrad_T + ut_floats(shape) : nullptr;
   return run_forward(shape, params, disp, target, src, K, inv_K, T, noise, seed, offset, loss_per_scale, loss_total,
                      sel, ugrad_disp, ugrad_T, coup, workspace, static_cast<cudaStream_t>(stream));
+}
+
+static int dtype_flags(int disp_dtype, int image_dtype, int* io) {
+  if ((disp_dtype != DVS_DTYPE_F32 && disp_dtype != DVS_DTYPE_BF16) || (image_dtype != DVS_DTYPE_F32 && image_dtype != DVS_DTYPE_U8))
+    return DVS_EINVAL;
+  *io = (disp_dtype == DVS_DTYPE_BF16 ? 1 : 0) | (image_dtype == DVS_DTYPE_U8 ? 2 : 0);
+  return DVS_OK;
+}
+
+extern "C" int dvs_photometric_forward_ex(const DvsShape* shape, const DvsParams* params, const void* const* disp,
+                                          int disp_dtype, const void* target, const void* const* src, int image_dtype,
+                                          const float* K, const float* inv_K, const float* const* T,
+                                          const float* const* noise, uint64_t seed, uint64_t offset,
+                                          float* loss_per_scale, float* loss_total, uint8_t* const* sel,
+                                          float* const* ugrad_disp, float* ugrad_T, void* workspace, void* stream) {
+  if ((ugrad_disp == nullptr) != (ugrad_T == nullptr)) return DVS_EINVAL;
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  int io = 0;
+  rc = dtype_flags(disp_dtype, image_dtype, &io);
+  if (rc) return rc;
+  float* coup = ugrad_T ? ugrad_T + ut_floats(shape) : nullptr;
+  return run_forward(shape, params, reinterpret_cast<const float* const*>(disp), static_cast<const float*>(target),
+                     reinterpret_cast<const float* const*>(src), K, inv_K, T, noise, seed, offset, loss_per_scale,
+                     loss_total, sel, ugrad_disp, ugrad_T, coup, workspace, static_cast<cudaStream_t>(stream), io);
+}
+
+extern "C" int dvs_photometric_backward_ex(const DvsShape* shape, const float* grad_per_scale,
+                                           const float* const* ugrad_disp, const float* ugrad_T,
+                                           void* const* grad_disp, int grad_dtype, float* const* grad_T, void* stream) {
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  if (!grad_per_scale || !ugrad_disp || !ugrad_T || !grad_disp || !grad_T) return DVS_EINVAL;
+  if (grad_dtype != DVS_DTYPE_F32 && grad_dtype != DVS_DTYPE_BF16) return DVS_EINVAL;
+  return run_backward(shape, grad_per_scale, ugrad_disp, ugrad_T, ugrad_T + ut_floats(shape),
+                      reinterpret_cast<float* const*>(grad_disp), grad_T, static_cast<cudaStream_t>(stream),
+                      grad_dtype == DVS_DTYPE_BF16 ? 1 : 0);
 }
 
 extern "C" int dvs_photometric_backward(const DvsShape* shape, const float* grad_per_scale,

@@ -84,9 +84,10 @@ struct FusedParams {
   float* cpart;
   int cstride, coff[kMaxS], cbw[kMaxS];
   int tiles_x, tiles_y;
-  // persistent two-source kernel: tiles are handed out through this counter (zeroed by the disparity-mean pre-pass)
-  int* tile_counter;
   int nblk;
+  // input formats (two-source kernel, dvs_pair_core.cuh): bit 0 = disparities are bf16, bit 1 = images are uint8; the
+  // pointers above are then to be read as unsigned short / unsigned char with the same element offsets
+  int io_flags;
   // loop-invariant scalars of the two-source kernel, divided once on the host (IEEE, same values as on the device):
   // kF = ssim_w / (3 B H W), l1k = l1_w / (3 B H W), kxs[s] / kys[s] = smooth_w / 2^s / (B H (W-1)) resp. (B (H-1) W)
   float kF, l1k, kxs[kMaxS], kys[kMaxS];

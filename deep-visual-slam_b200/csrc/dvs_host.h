@@ -7,6 +7,9 @@
 namespace dvs {
 // cudaError_t of the last failing CUDA call made by this library on the calling host thread.
 int& last_cuda_error();
+struct FusedParams;
+// dvs_pair.cu: the two-source tile kernel, dispatched on (want_grad, io_flags)
+cudaError_t launch_pair_kernel(const FusedParams& p, int nblk, cudaStream_t st);
 }  // namespace dvs
 
 #define DVS_CUDA_TRY(expr)                          \

@@ -49,6 +49,59 @@ DVS_HD void st2(float* p, f2 v) {
 }
 DVS_HD f2 bc2(float a) { return f2{a, a}; }
 
+// ------------------------------------------------------------------------------------------------ input formats
+// IO bit 0: disparities are bf16 (what DepthNet emits under bf16 autocast, vo/train.py:177-181); bit 1: images are uint8
+// (what the loader decodes, vo/dataset/common.py:39-46,77).  Both are converted on load: bf16 -> fp32 is exact, and
+// x / 255 is the correctly rounded quotient ToTensor computes (one multiply + one FMA correction step; checked for all
+// 256 inputs in tests/test_abi.py), so the results are bit-identical to running on the fp32-expanded tensors.
+constexpr int kIoDispBf16 = 1, kIoImgU8 = 2;
+
+DVS_HD float u8_to_unit(unsigned char v) {
+  const float x = (float)v, r = 1.0f / 255.0f;
+  const float q = x * r;
+  return fmaf(fmaf(-q, 255.0f, x), r, q);
+}
+DVS_HD float bf16_bits_to_float(unsigned short h) {
+  union { unsigned int u; float f; } c;
+  c.u = (unsigned int)h << 16;
+  return c.f;
+}
+template <bool U8>
+struct ImgPtr {
+  const void* p;
+  DVS_HD float at(int i) const {
+    if (U8) return u8_to_unit(static_cast<const unsigned char*>(p)[i]);
+    return static_cast<const float*>(p)[i];
+  }
+  DVS_HD ImgPtr off(size_t e) const {
+    if (U8) return ImgPtr{static_cast<const unsigned char*>(p) + e};
+    return ImgPtr{static_cast<const float*>(p) + e};
+  }
+};
+template <bool BF16>
+DVS_HD float ld_disp(const float* d, int i) {
+  if (BF16) return bf16_bits_to_float(reinterpret_cast<const unsigned short*>(d)[i]);
+  return d[i];
+}
+template <bool BF16>
+DVS_HD const float* disp_image(const float* d, size_t e) {       // start of image b of a disparity map
+  if (BF16) return reinterpret_cast<const float*>(reinterpret_cast<const unsigned short*>(d) + e);
+  return d + e;
+}
+template <bool BF16>
+DVS_HD void disp_taps_load_t(const float* d, int dh, int dw, float sy, float sx, bool direct, int ry, int rx, DispTaps& q) {
+  if (direct) {
+    q.a = q.b = q.c = q.e = ld_disp<BF16>(d, ry * dw + rx);
+    q.lx = q.ly = 0.f;
+    return;
+  }
+  int y0, y1, x0, x1;
+  up_taps(ry, sy, dh, y0, y1, q.ly);
+  up_taps(rx, sx, dw, x0, x1, q.lx);
+  q.a = ld_disp<BF16>(d, y0 * dw + x0); q.b = ld_disp<BF16>(d, y0 * dw + x1);
+  q.c = ld_disp<BF16>(d, y1 * dw + x0); q.e = ld_disp<BF16>(d, y1 * dw + x1);
+}
+
 struct PairState {
   int flags;               // bit j: pixel j inside the image; bit 4+j: pixel j belongs to R0 (own)
   float acc[3];            // photometric sum, smooth-x sum, smooth-y sum of the current scale
@@ -59,67 +112,30 @@ struct PairState {
 
 // ------------------------------------------------------------------------------------------------ load
 // target -> Y, sources interleaved -> X2 (for the identity terms), zero F, selection plane, pixel flags.
+template <int IO>
 DVS_HD void pair_phase_load(const FusedParams& p, const Tile& t, float* sm, int tid, PairState& st) {
   PairLayout P;
   const SmemLayout& L = P.L;
   const int HW = p.H * p.W;
+  constexpr bool U8 = (IO & kIoImgU8) != 0;
+  const ImgPtr<U8> tgt = ImgPtr<U8>{p.target}.off((size_t)t.b * 3 * HW);
+  const ImgPtr<U8> sr0 = ImgPtr<U8>{p.src[0]}.off((size_t)t.b * 3 * HW), sr1 = ImgPtr<U8>{p.src[1]}.off((size_t)t.b * 3 * HW);
   int* posp = reinterpret_cast<int*>(sm + L.pos());
-#if defined(DVS_LOAD2)
-  // two pixels per iteration: 18 loads in flight before the first store (the tile load is pure latency)
-  DVS_NOUNROLL
-  for (int k = tid; k < PLANE; k += 2 * NT) {
-    const int kb = k + NT < PLANE ? k + NT : k;          // the tail repeats pixel k (same values stored twice)
-    int o[2];
-    DVS_UNROLL
-    for (int h = 0; h < 2; ++h) {
-      const int kk = h ? kb : k;
-      const int ly = kk / PW - 1, lx = kk % PW - 1;
-      const int gy = reflect_clamp(t.gy0 + ly, p.H), gx = reflect_clamp(t.gx0 + lx, p.W);
-      posp[kk] = (gy << 16) | gx;
-      o[h] = gy * p.W + gx;
-    }
-    float ty_[2][3];
-    f2 sx_[2][3];
-    DVS_UNROLL
-    for (int h = 0; h < 2; ++h) {
-      const float* tg = p.target + (size_t)t.b * 3 * HW + o[h];
-      ty_[h][0] = tg[0]; ty_[h][1] = tg[HW]; ty_[h][2] = tg[2 * HW];
-      if (p.auto_mask) {
-        const float* s0 = p.src[0] + (size_t)t.b * 3 * HW + o[h];
-        const float* s1 = p.src[1] + (size_t)t.b * 3 * HW + o[h];
-        sx_[h][0] = f2{s0[0], s1[0]}; sx_[h][1] = f2{s0[HW], s1[HW]}; sx_[h][2] = f2{s0[2 * HW], s1[2 * HW]};
-      }
-    }
-    DVS_UNROLL
-    for (int h = 0; h < 2; ++h) {
-      const int kk = h ? kb : k;
-      DVS_UNROLL
-      for (int c = 0; c < 3; ++c) {
-        sm[L.y(c) + kk] = ty_[h][c];
-        if (p.auto_mask) st2(sm + P.x2(c) + 2 * kk, sx_[h][c]);
-      }
-    }
-  }
-#else
   DVS_NOUNROLL
   for (int k = tid; k < PLANE; k += NT) {
     int ly = k / PW - 1, lx = k % PW - 1;
     int gy = reflect_clamp(t.gy0 + ly, p.H), gx = reflect_clamp(t.gx0 + lx, p.W);
     posp[k] = (gy << 16) | gx;
     int o = gy * p.W + gx;
-    const float* tg = p.target + (size_t)t.b * 3 * HW + o;
-    sm[L.y(0) + k] = tg[0];
-    sm[L.y(1) + k] = tg[HW];
-    sm[L.y(2) + k] = tg[2 * HW];
+    sm[L.y(0) + k] = tgt.at(o);
+    sm[L.y(1) + k] = tgt.at(o + HW);
+    sm[L.y(2) + k] = tgt.at(o + 2 * HW);
     if (p.auto_mask) {
-      const float* s0 = p.src[0] + (size_t)t.b * 3 * HW + o;
-      const float* s1 = p.src[1] + (size_t)t.b * 3 * HW + o;
-      st2(sm + P.x2(0) + 2 * k, f2{s0[0], s1[0]});
-      st2(sm + P.x2(1) + 2 * k, f2{s0[HW], s1[HW]});
-      st2(sm + P.x2(2) + 2 * k, f2{s0[2 * HW], s1[2 * HW]});
+      st2(sm + P.x2(0) + 2 * k, f2{sr0.at(o), sr1.at(o)});
+      st2(sm + P.x2(1) + 2 * k, f2{sr0.at(o + HW), sr1.at(o + HW)});
+      st2(sm + P.x2(2) + 2 * k, f2{sr0.at(o + 2 * HW), sr1.at(o + 2 * HW)});
     }
   }
-#endif
 #if defined(__CUDA_ARCH__)
   float4* f4 = reinterpret_cast<float4*>(sm + L.f(0));
   for (int k = tid; k < 9 * PLANE / 4; k += NT) f4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -313,17 +329,15 @@ DVS_HD void project2(const f2* A, float u, float v, float D, float eps, int H, i
   r.o1 = y1 * W + x1;
 }
 // the 24 taps of one pixel (both sources, three channels): issue only
-DVS_HD void gather_taps2(const float* im0, const float* im1, int o0, int o1, int HW, int W, f2 (*tap)[4]) {
-  const float* a0 = im0 + o0;
-  const float* a1 = im1 + o1;
+template <bool U8>
+DVS_HD void gather_taps2(ImgPtr<U8> im0, ImgPtr<U8> im1, int o0, int o1, int HW, int W, f2 (*tap)[4]) {
   DVS_UNROLL
   for (int ch = 0; ch < 3; ++ch) {
-    const float* q0 = a0 + ch * HW;
-    const float* q1 = a1 + ch * HW;
-    tap[ch][0] = f2{q0[0], q1[0]};
-    tap[ch][1] = f2{q0[1], q1[1]};
-    tap[ch][2] = f2{q0[W], q1[W]};
-    tap[ch][3] = f2{q0[W + 1], q1[W + 1]};
+    const ImgPtr<U8> q0 = im0.off((size_t)(o0 + ch * HW)), q1 = im1.off((size_t)(o1 + ch * HW));
+    tap[ch][0] = f2{q0.at(0), q1.at(0)};
+    tap[ch][1] = f2{q0.at(1), q1.at(1)};
+    tap[ch][2] = f2{q0.at(W), q1.at(W)};
+    tap[ch][3] = f2{q0.at(W + 1), q1.at(W + 1)};
   }
 }
 DVS_HD void lerp_store2(float* sm, int x2off, int k, f2 tx, f2 ty, const f2 (*tap)[4]) {
@@ -339,111 +353,30 @@ DVS_HD void lerp_store2(float* sm, int x2off, int k, f2 tx, f2 ty, const f2 (*ta
 // warp both sources onto R2 for scale s (interleaved float2 planes); store the up-sampled disparity.
 // Two pixels per iteration: their eight disparity taps are fetched together, then the 48 image taps of both are in flight
 // before the first interpolation (the phase is bound by the latency of the gather, not by its bandwidth).
+template <int IO>
 DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   PairLayout P;
   const SmemLayout& L = P.L;
   const int HW = p.H * p.W;
   const int dh = p.dh[s], dw = p.dw[s];
-  const float* d = p.disp[s] + (size_t)t.b * dh * dw;
+  constexpr bool U8 = (IO & kIoImgU8) != 0, BF = (IO & kIoDispBf16) != 0;
+  const float* d = disp_image<BF>(p.disp[s], (size_t)t.b * dh * dw);
   const bool direct = dh == p.H && dw == p.W;
   const float scy = (float)dh / (float)p.H, scx = (float)dw / (float)p.W;
   const int* posp = reinterpret_cast<const int*>(sm + L.pos());
-  const float* im0 = p.src[0] + (size_t)t.b * 3 * HW;
-  const float* im1 = p.src[1] + (size_t)t.b * 3 * HW;
+  const ImgPtr<U8> im0 = ImgPtr<U8>{p.src[0]}.off((size_t)t.b * 3 * HW), im1 = ImgPtr<U8>{p.src[1]}.off((size_t)t.b * 3 * HW);
   const int x2off = P.x2(0);
 
-#if defined(DVS_WSPLIT)
-  // pass 1 (arithmetic): up-sampled disparity, projection of both sources; the bilinear weights and tap offsets are parked
-  // in the pixel's own X2 slots.  pass 2 (gather): the loop body is only "fetch weights, 24 taps, interpolate", so two
-  // pixels' taps fit in registers and the loads of the next pixel are issued before the current one is interpolated.
-  {
-    int pk = posp[tid];
-    DispTaps dt;
-    disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
-    DVS_NOUNROLL
-    for (int k = tid; k < PLANE; k += NT) {
-      const int rx = pk & 0xffff, ry = pk >> 16;
-      const float du = disp_taps_value(dt, direct);
-      if (k + NT < PLANE) {
-        pk = posp[k + NT];
-        disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
-      }
-      sm[L.du() + k] = du;
-      f2 A[12];
-      DVS_UNROLL
-      for (int e = 0; e < 12; ++e) A[e] = ld2(sm + P.a2() + 2 * e);
-      Proj2 pr;
-      project2(A, (float)rx, (float)ry, rcp_fast(fmaf(du, p.disp_range, p.min_disp)), p.eps, p.H, p.W, pr);
-      st2(sm + x2off + 2 * k, pr.tx);
-      st2(sm + x2off + 2 * PLANE + 2 * k, pr.ty);
-      reinterpret_cast<int*>(sm)[x2off + 4 * PLANE + 2 * k] = pr.o0;
-      reinterpret_cast<int*>(sm)[x2off + 4 * PLANE + 2 * k + 1] = pr.o1;
-    }
-  }
-  {
-    f2 txc = ld2(sm + x2off + 2 * tid), tyc = ld2(sm + x2off + 2 * PLANE + 2 * tid);
-    f2 tapc[3][4];
-    gather_taps2(im0, im1, reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * tid],
-                 reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * tid + 1], HW, p.W, tapc);
-    DVS_NOUNROLL
-    for (int k = tid; k < PLANE; k += 2 * NT) {
-      // pixel k is in flight in (txc, tyc, tapc); fetch k + NT, interpolate k, fetch k + 2 NT, interpolate k + NT
-      const int k1 = k + NT, k2 = k + 2 * NT;
-      f2 txn, tyn, tapn[3][4];
-      if (k1 < PLANE) {
-        txn = ld2(sm + x2off + 2 * k1); tyn = ld2(sm + x2off + 2 * PLANE + 2 * k1);
-        gather_taps2(im0, im1, reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * k1],
-                     reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * k1 + 1], HW, p.W, tapn);
-      }
-      lerp_store2(sm, x2off, k, txc, tyc, tapc);
-      if (k1 < PLANE) {
-        if (k2 < PLANE) {
-          txc = ld2(sm + x2off + 2 * k2); tyc = ld2(sm + x2off + 2 * PLANE + 2 * k2);
-          gather_taps2(im0, im1, reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * k2],
-                       reinterpret_cast<const int*>(sm)[x2off + 4 * PLANE + 2 * k2 + 1], HW, p.W, tapc);
-        }
-        lerp_store2(sm, x2off, k1, txn, tyn, tapn);
-      }
-    }
-  }
-#elif defined(DVS_W2PX)
-  DVS_NOUNROLL
-  for (int k = tid; k < PLANE; k += 2 * NT) {
-    const bool hasb = k + NT < PLANE;
-    const int kb = hasb ? k + NT : k;
-    const int pka = posp[k], pkb = posp[kb];
-    const int rxa = pka & 0xffff, rya = pka >> 16, rxb = pkb & 0xffff, ryb = pkb >> 16;
-    DispTaps dta, dtb;
-    disp_taps_load(d, dh, dw, scy, scx, direct, rya, rxa, dta);
-    disp_taps_load(d, dh, dw, scy, scx, direct, ryb, rxb, dtb);
-    f2 A[12];                                            // projection constants: re-read per iteration (registers are short here)
-    DVS_UNROLL
-    for (int e = 0; e < 12; ++e) A[e] = ld2(sm + P.a2() + 2 * e);
-    const float dua = disp_taps_value(dta, direct), dub = disp_taps_value(dtb, direct);
-    Proj2 pa, pb;
-    f2 tapa[3][4], tapb[3][4];
-    sm[L.du() + k] = dua;
-    project2(A, (float)rxa, (float)rya, rcp_fast(fmaf(dua, p.disp_range, p.min_disp)), p.eps, p.H, p.W, pa);
-    gather_taps2(im0, im1, pa.o0, pa.o1, HW, p.W, tapa);
-    if (hasb) {
-      sm[L.du() + kb] = dub;
-      project2(A, (float)rxb, (float)ryb, rcp_fast(fmaf(dub, p.disp_range, p.min_disp)), p.eps, p.H, p.W, pb);
-      gather_taps2(im0, im1, pb.o0, pb.o1, HW, p.W, tapb);
-    }
-    lerp_store2(sm, x2off, k, pa.tx, pa.ty, tapa);
-    if (hasb) lerp_store2(sm, x2off, kb, pb.tx, pb.ty, tapb);
-  }
-#else
   int pk = posp[tid];
   DispTaps dt;
-  disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
+  disp_taps_load_t<BF>(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
   DVS_NOUNROLL
   for (int k = tid; k < PLANE; k += NT) {
     const int rx = pk & 0xffff, ry = pk >> 16;
     const float du = disp_taps_value(dt, direct);
     if (k + NT < PLANE) {                                // disparity of the next pixel: in flight during this one
       pk = posp[k + NT];
-      disp_taps_load(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
+      disp_taps_load_t<BF>(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
     }
     sm[L.du() + k] = du;
     f2 A[12];
@@ -455,7 +388,6 @@ DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int 
     gather_taps2(im0, im1, pr.o0, pr.o1, HW, p.W, tap);   // all 24 tap loads of the pixel before the first use
     lerp_store2(sm, x2off, k, pr.tx, pr.ty, tap);
   }
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------ phase S
@@ -496,11 +428,7 @@ DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int
         // The in-kernel generator is bounded (|n| <= sqrt(48 ln 2) = 5.77, i.e. 5.77e-5 after scaling): where a
         // reprojection term beats both identity terms by more than that, no draw can change the outcome (minimum,
         // argmin and loss value are the reprojection's), so the draw is skipped.  Given noise tensors are always read.
-#if defined(DVS_NO_NOISE_SKIP)
-        const bool need = true;
-#else
         const bool need = p.noise[s] != nullptr || !(fminf(r[j].x, r[j].y) < fminf(id0, id1) - 6.0e-5f);
-#endif
         if (in && need) {
           const int gy = gyb + jj;
           if (p.noise[s]) {
@@ -564,9 +492,11 @@ DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int
 // ------------------------------------------------------------------------------------------------ phase G
 // own pixels: pooled adjoint of the coefficient fields for both sources in one sweep -> d loss / d warped colour ->
 // sampling coordinates -> depth / pose moments.  Accumulates st.gdu and st.M.
+template <int IO>
 DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, int s, PairState& st) {
   PairLayout P;
   const SmemLayout& L = P.L;
+  constexpr bool U8 = (IO & kIoImgU8) != 0;
   if (!(st.flags >> 4)) return;                       // no own pixel
   int r0, cx;
   quad_coords(tid, r0, cx);
@@ -593,10 +523,8 @@ DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int 
   if (!any) return;                                    // F is all zero around the own pixels: no photometric gradient
   const f2 wl2 = bc2(wl), wr2 = bc2(wr), one2 = bc2(1.f);
 
-  // d loss / d warped colour of the own pixels, (source 0, source 1)
-#if defined(DVS_GREGS)
-  f2 G[3][4];
-#endif
+  // d loss / d warped colour of the own pixels, (source 0, source 1): parked in the pixel's own X2 slot for the chain below
+  // (selecting among 12 register pairs by the loop index cost more issue slots than three 64-bit shared-memory loads)
   DVS_UNROLL
   for (int c = 0; c < 3; ++c) {
     f2 pooled[3][4];                                    // (source 0, source 1) per field and pixel
@@ -637,30 +565,18 @@ DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int 
 #if defined(DVS_FAULT_GRAD_SCALE)
       g = mul2(g, bc2(DVS_FAULT_GRAD_SCALE));
 #endif
-#if !defined(DVS_GREGS)
       st2(X + 2 * j * PW, g);      // over the warped colour itself: only this thread reads its own pixels' X2 entries here
-#else
-      G[c][j] = g;
-#endif
     }
   }
 
   // chain through the bilinear gather and the projection (taps re-read; they are L1/L2 resident)
-  const float* im0 = p.src[0] + (size_t)t.b * 3 * HW;
-  const float* im1 = p.src[1] + (size_t)t.b * 3 * HW;
+  const ImgPtr<U8> im0 = ImgPtr<U8>{p.src[0]}.off((size_t)t.b * 3 * HW), im1 = ImgPtr<U8>{p.src[1]}.off((size_t)t.b * 3 * HW);
   DVS_NOUNROLL
   for (int j = 0; j < 4; ++j) {
-#if !defined(DVS_GREGS)
     if (!((st.flags >> (4 + j)) & 1)) continue;
     const f2 g0 = ld2(sm + P.x2(0) + 2 * (base + j * PW));
     const f2 g1 = ld2(sm + P.x2(1) + 2 * (base + j * PW));
     const f2 g2 = ld2(sm + P.x2(2) + 2 * (base + j * PW));
-#else
-    const f2 g0 = j == 0 ? G[0][0] : (j == 1 ? G[0][1] : (j == 2 ? G[0][2] : G[0][3]));
-    const f2 g1 = j == 0 ? G[1][0] : (j == 1 ? G[1][1] : (j == 2 ? G[1][2] : G[1][3]));
-    const f2 g2 = j == 0 ? G[2][0] : (j == 1 ? G[2][1] : (j == 2 ? G[2][2] : G[2][3]));
-    if (!((st.flags >> (4 + j)) & 1)) continue;
-#endif
     if (g0.x == 0.f && g1.x == 0.f && g2.x == 0.f && g0.y == 0.f && g1.y == 0.f && g2.y == 0.f) continue;
     const float v = (float)(gyb + j);
     const float D = rcp_fast(fmaf(sm[L.du() + base + j * PW], p.disp_range, p.min_disp));

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("DVSLOSS_LIB") or os.path.join(_HERE, "libdvsloss.so")
 
 MAX_SCALES = 4
 MAX_SOURCES = 4
+DTYPE_F32, DTYPE_BF16, DTYPE_U8 = 0, 1, 2      # include/dvsloss.h: DVS_DTYPE_*
 
 
 class DvsShape(C.Structure):
@@ -52,6 +53,9 @@ _SIGNATURES = {
     "dvs_photometric_forward": [C.POINTER(DvsShape), C.POINTER(DvsParams), _FPP, _vp, _FPP, _vp, _vp, _FPP, _FPP,
                                 C.c_uint64, C.c_uint64, _vp, _vp, _U8PP, _FPP, _vp, _vp, _vp],
     "dvs_photometric_backward": [C.POINTER(DvsShape), _vp, _FPP, _vp, _FPP, _FPP, _vp],
+    "dvs_photometric_forward_ex": [C.POINTER(DvsShape), C.POINTER(DvsParams), _FPP, C.c_int, _vp, _FPP, C.c_int, _vp, _vp, _FPP,
+                                   _FPP, C.c_uint64, C.c_uint64, _vp, _vp, _U8PP, _FPP, _vp, _vp, _vp],
+    "dvs_photometric_backward_ex": [C.POINTER(DvsShape), _vp, _FPP, _vp, _FPP, C.c_int, _FPP, _vp],
     "dvs_photometric_backward_recompute": [C.POINTER(DvsShape), C.POINTER(DvsParams), _FPP, _vp, _FPP, _vp, _vp, _FPP,
                                            _FPP, C.c_uint64, C.c_uint64, _vp, _FPP, _FPP, _vp, _vp],
     "dvs_disp_to_depth_fwd": [_vp, _vp, _vp, C.c_int64, C.c_float, C.c_float, _vp],
@@ -116,8 +120,8 @@ def require_cuda(*tensors: torch.Tensor) -> None:
             continue
         if not t.is_cuda:
             raise DvsError("dvsloss operators run on CUDA tensors only (no CPU fallback by design)")
-        if t.dtype != torch.float32 and t.dtype != torch.uint8:
-            raise DvsError(f"expected float32, got {t.dtype}")
+        if t.dtype not in (torch.float32, torch.uint8, torch.bfloat16):
+            raise DvsError(f"expected float32 (or bfloat16 disparities / uint8 images), got {t.dtype}")
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

@@ -30,13 +30,33 @@ def _prep(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+def _prep_disps(disps, N: int):
+    """bf16 disparity maps (DepthNet under bf16 autocast, vo/train.py:177-181) are read by the two-source kernel as they
+    are -- no ``.float()`` pass per scale, and the gradients go back as bf16; anything else is widened to fp32."""
+    if N == 2 and all(d.dtype == torch.bfloat16 for d in disps):
+        return [d.contiguous() for d in disps], _lib.DTYPE_BF16
+    return [_prep(d) for d in disps], _lib.DTYPE_F32
+
+
+def _prep_images(target, sources, N: int):
+    """uint8 images (the loader's decoded frames before ToTensor, vo/dataset/common.py:39-46,77) are read by the
+    two-source kernel as bytes (x/255 in-register, exact); for other source counts they are expanded on the device first."""
+    imgs = [target] + list(sources)
+    if all(t.dtype == torch.uint8 for t in imgs):
+        if N == 2:
+            return imgs[0].contiguous(), [t.contiguous() for t in imgs[1:]], _lib.DTYPE_U8
+        from .ops import images_u8_to_f32
+        imgs = [images_u8_to_f32(t.contiguous()) for t in imgs]
+    return _prep(imgs[0]), [_prep(t) for t in imgs[1:]], _lib.DTYPE_F32
+
+
 class _ViewSynthesisLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg: dict, target, sources, K, inv_K, noise, S: int, N: int, *diff):
-        disps = [_prep(d) for d in diff[:S]]
+        disps, disp_dtype = _prep_disps(diff[:S], N)
         Ts = [_prep(t) for t in diff[S:S + N]]
-        target, K, inv_K = _prep(target), _prep(K), _prep(inv_K)
-        sources = [_prep(s) for s in sources]
+        K, inv_K = _prep(K), _prep(inv_K)
+        target, sources, image_dtype = _prep_images(target, sources, N)
         require_cuda(target, K, inv_K, *disps, *Ts, *sources)
         dev = target.device
         B, C3, H, W = target.shape
@@ -68,7 +88,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             sel = [torch.empty(B, H, W, dtype=torch.uint8, device=dev) for _ in range(S)]
         ugrad = uT = None
         if want_grad:
-            ugrad = [torch.empty_like(d) for d in disps]
+            ugrad = [torch.empty(d.shape, dtype=torch.float32, device=dev) for d in disps]
             uT = torch.empty(S * N * B * 16 + S * B, dtype=torch.float32, device=dev)
         noise_arr = None
         if noise is not None:
@@ -79,13 +99,14 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             require_cuda(*noise)
             noise_arr = fptr_array(noise)
         with torch.cuda.device(dev):
-            rc = L.dvs_photometric_forward(
-                C.byref(shape), C.byref(params), fptr_array(disps), ptr(target), fptr_array(sources), ptr(K),
-                ptr(inv_K), fptr_array(Ts), noise_arr, C.c_uint64(cfg["seed"]), C.c_uint64(cfg["offset"]),
+            rc = L.dvs_photometric_forward_ex(
+                C.byref(shape), C.byref(params), fptr_array(disps), disp_dtype, ptr(target), fptr_array(sources), image_dtype,
+                ptr(K), ptr(inv_K), fptr_array(Ts), noise_arr, C.c_uint64(cfg["seed"]), C.c_uint64(cfg["offset"]),
                 ptr(per_scale), ptr(total), u8ptr_array(sel) if sel is not None else None,
                 fptr_array(ugrad) if want_grad else None, ptr(uT), ws_ptr, stream_ptr(dev))
-        check(rc, "dvs_photometric_forward")
+        check(rc, "dvs_photometric_forward_ex")
         ctx.shape, ctx.S, ctx.N, ctx.B = shape, S, N, B
+        ctx.disp_dtype = disp_dtype
         ctx.ugrad, ctx.uT = ugrad, uT
         ctx.keep = (ws, noise, disps, Ts, sources, target, K, inv_K)   # keep inputs alive until the stream has used them
         outs = (total.view(()), per_scale)
@@ -107,12 +128,13 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         if g_total is not None:
             g = g + g_total.float() / S
         g = g.contiguous()
-        grad_disp = [torch.empty_like(u) for u in ctx.ugrad]
+        gdt = torch.bfloat16 if ctx.disp_dtype == _lib.DTYPE_BF16 else torch.float32
+        grad_disp = [torch.empty(u.shape, dtype=gdt, device=dev) for u in ctx.ugrad]
         grad_T = [torch.empty(B, 4, 4, dtype=torch.float32, device=dev) for _ in range(N)]
         with torch.cuda.device(dev):
-            rc = lib().dvs_photometric_backward(C.byref(ctx.shape), ptr(g), fptr_array(ctx.ugrad), ptr(ctx.uT),
-                                                fptr_array(grad_disp), fptr_array(grad_T), stream_ptr(dev))
-        check(rc, "dvs_photometric_backward")
+            rc = lib().dvs_photometric_backward_ex(C.byref(ctx.shape), ptr(g), fptr_array(ctx.ugrad), ptr(ctx.uT),
+                                                   fptr_array(grad_disp), ctx.disp_dtype, fptr_array(grad_T), stream_ptr(dev))
+        check(rc, "dvs_photometric_backward_ex")
         return (None,) * 8 + tuple(grad_disp) + tuple(grad_T)
 
 
@@ -124,7 +146,9 @@ def view_synthesis_loss(disps: Sequence[torch.Tensor], target: torch.Tensor, sou
                         ) -> Tuple[torch.Tensor, ...]:
     """Fused Monodepth2 view-synthesis loss over S=len(disps) scales and N=len(sources) source frames.
 
-    disps[s] [B,1,h_s,w_s] sigmoid disparities (outputs[("disp", s)]), target/sources [B,3,H,W] in [0,1],
+    disps[s] [B,1,h_s,w_s] sigmoid disparities (outputs[("disp", s)]; fp32, or bf16 as emitted under autocast -- read directly
+    by the two-source kernel, gradients returned as bf16), target/sources [B,3,H,W] in [0,1] (fp32, or uint8 frames: x/255
+    is formed inside the kernel),
     K/inv_K [B,4,4] scale-0 intrinsics, Ts[i] [B,4,4] cam_T_cam of source i.
 
     noise: "kernel" -> automask tie-break noise from an in-kernel counter-based generator (fast);

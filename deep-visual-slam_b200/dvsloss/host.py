@@ -19,12 +19,14 @@ from .ops import images_u8_to_f32
 
 class HostLossPipeline:
     def __init__(self, B: int, H: int, W: int, disp_sizes: Sequence[Sequence[int]], num_sources: int = 2, chunks: int = 4,
-                 device=None, uint8_images: bool = False, **loss_kwargs):
+                 device=None, uint8_images: bool = False, u8_in_kernel: bool = False, **loss_kwargs):
         if B % chunks:
             raise ValueError("the batch must split into equal chunks (batch means must stay batch means)")
         self.B, self.Bc, self.chunks, self.N, self.S = B, B // chunks, chunks, num_sources, len(disp_sizes)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.uint8_images = uint8_images        # images arrive as bytes (dataset precision) and are expanded on the device
+        # ... or, with two sources, not expanded at all: the tile kernel reads the bytes (x/255 in-register, same bits)
+        self.u8_in_kernel = bool(uint8_images and u8_in_kernel and num_sources == 2)
         self.kw = dict(loss_kwargs)
         self.kw.setdefault("noise", "kernel")
         Bc, d = self.Bc, self.dev
@@ -59,8 +61,9 @@ class HostLossPipeline:
                 if self.uint8_images:
                     for a, b in zip(S_["raw"], [h_in["target"]] + h_in["sources"]):
                         a.copy_(b[sl], non_blocking=True)
-                    for raw, img in zip(S_["raw"], [S_["target"]] + S_["sources"]):
-                        images_u8_to_f32(raw, img)                 # x / 255 on the copy stream, exact
+                    if not self.u8_in_kernel:
+                        for raw, img in zip(S_["raw"], [S_["target"]] + S_["sources"]):
+                            images_u8_to_f32(raw, img)             # x / 255 on the copy stream, exact
                 else:
                     S_["target"].copy_(h_in["target"][sl], non_blocking=True)
                     for a, b in zip(S_["sources"], h_in["sources"]):
@@ -74,8 +77,8 @@ class HostLossPipeline:
                 self.s_run.wait_event(self.ev_in[c])
                 for t in S_["disps"] + S_["Ts"]:
                     t.grad = None
-                loss, per_scale = view_synthesis_loss(S_["disps"], S_["target"], S_["sources"], S_["K"], S_["inv_K"], S_["Ts"],
-                                                      **self.kw)
+                tgt, srcs = (S_["raw"][0], S_["raw"][1:]) if self.u8_in_kernel else (S_["target"], S_["sources"])
+                loss, per_scale = view_synthesis_loss(S_["disps"], tgt, srcs, S_["K"], S_["inv_K"], S_["Ts"], **self.kw)
                 loss.backward(torch.full_like(loss, 1.0 / C))
                 part = torch.cat([loss.detach().view(1), per_scale.detach()])
                 parts.append(part)

@@ -100,6 +100,28 @@ int dvs_photometric_forward(const DvsShape* shape, const DvsParams* params,
                             float* const* ugrad_disp, float* ugrad_T,
                             void* workspace, void* stream);
 
+/* The same with reduced-precision INPUTS read directly by the kernel (two sources only, N == 2):
+ *   disp_dtype  DVS_DTYPE_F32 | DVS_DTYPE_BF16   disp[s] as DepthNet emits them under bf16 autocast (vo/train.py:177-181)
+ *   image_dtype DVS_DTYPE_F32 | DVS_DTYPE_U8     target / src[i] as the loader decodes them, before ToTensor
+ *                                                (vo/dataset/common.py:39-46,77); x/255 is formed in-register, correctly
+ *                                                rounded, so results are bit-identical to the fp32-expanded tensors
+ * All arithmetic, the unit gradients and every output stay fp32. */
+enum { DVS_DTYPE_F32 = 0, DVS_DTYPE_BF16 = 1, DVS_DTYPE_U8 = 2 };
+int dvs_photometric_forward_ex(const DvsShape* shape, const DvsParams* params,
+                               const void* const* disp, int disp_dtype,
+                               const void* target, const void* const* src, int image_dtype,
+                               const float* K, const float* inv_K, const float* const* T,
+                               const float* const* noise, uint64_t seed, uint64_t offset,
+                               float* loss_per_scale, float* loss_total,
+                               uint8_t* const* sel,
+                               float* const* ugrad_disp, float* ugrad_T,
+                               void* workspace, void* stream);
+/* dvs_photometric_backward writing grad_disp[s] in grad_dtype (DVS_DTYPE_F32 | DVS_DTYPE_BF16, round-to-nearest-even):
+ * what autograd hands back to a bf16 disparity tensor. */
+int dvs_photometric_backward_ex(const DvsShape* shape, const float* grad_per_scale,
+                                const float* const* ugrad_disp, const float* ugrad_T,
+                                void* const* grad_disp, int grad_dtype, float* const* grad_T, void* stream);
+
 /* Backward of the above given what forward stored: for upstream gradients
  * grad_per_scale[s] = d objective / d loss/s (device, [S]; add grad_total/S to each if the total is used)
  *   grad_disp[s] = grad_per_scale[s] * ugrad_disp[s]            (in place allowed: grad_disp[s]==ugrad_disp[s])

@@ -59,14 +59,14 @@ void run_block_pair(const FusedParams& p, int blk, std::vector<float>& smv) {
   Tile t = make_tile(p, blk);
   PairLayout P;
   std::vector<PairState> st(NT);
-  for (int tid = 0; tid < NT; ++tid) { phase_consts<2>(p, t, sm, tid, sm + P.a2()); pair_phase_load(p, t, sm, tid, st[tid]); }
+  for (int tid = 0; tid < NT; ++tid) { phase_consts<2>(p, t, sm, tid, sm + P.a2()); pair_phase_load<0>(p, t, sm, tid, st[tid]); }
   for (int tid = 0; tid < NT; ++tid) pair_phase_identity(p, t, sm, tid, st[tid]);
   for (int s = 0; s < p.S; ++s) {
-    for (int tid = 0; tid < NT; ++tid) { pair_reset_scale_state(st[tid]); pair_phase_warp(p, t, sm, tid, s); }
+    for (int tid = 0; tid < NT; ++tid) { pair_reset_scale_state(st[tid]); pair_phase_warp<0>(p, t, sm, tid, s); }
     for (int tid = 0; tid < NT; ++tid) pair_phase_stats<GRAD>(p, t, sm, tid, s, st[tid]);
     const bool direct = (p.dh[s] == p.H && p.dw[s] == p.W);
     if (GRAD) {
-      for (int tid = 0; tid < NT; ++tid) pair_phase_grad(p, t, sm, tid, s, st[tid]);
+      for (int tid = 0; tid < NT; ++tid) pair_phase_grad<0>(p, t, sm, tid, s, st[tid]);
       for (int tid = 0; tid < NT; ++tid) {
         if (direct) pair_store_gdu_direct(p, t, tid, s, st[tid]);
         else pair_stage_gdu(sm, tid, st[tid]);

@@ -80,3 +80,25 @@ def test_python_front_end_refuses_cpu_tensors():
     with pytest.raises(dvsloss.DvsError):
         dvsloss.view_synthesis_loss(p["disps"], p["target"], p["sources"], p["K"], p["inv_K"],
                                     [torch.eye(4)[None]] * 2, noise=None)
+
+
+def test_extended_entry_points_validate_dtypes(lib):
+    sh = _lib.make_shape(1, 48, 64, 2, [(48, 64)])
+    pr = _lib.DvsParams(0.1, 10.0, 0.85, 1e-3, 1e-7, 1)
+    args = (None, None, None, None, 0, 0, None, None, None, None, None, None, None)
+    assert lib.dvs_photometric_forward_ex(C.byref(sh), C.byref(pr), None, 7, None, None, 0, *args) == -1     # unknown dtype
+    assert lib.dvs_photometric_forward_ex(C.byref(sh), C.byref(pr), None, _lib.DTYPE_U8, None, None, 0, *args) == -1
+    assert lib.dvs_photometric_forward_ex(C.byref(sh), C.byref(pr), None, 0, None, None, _lib.DTYPE_BF16, *args) == -1
+    assert lib.dvs_photometric_backward_ex(C.byref(sh), None, None, None, None, _lib.DTYPE_U8, None, None) == -1
+
+
+def test_uint8_to_unit_conversion_is_exactly_x_over_255():
+    """The in-kernel conversion q = x * r; q += fma(-q, 255, x) * r  (r = fl(1/255)) equals the correctly rounded x / 255 of
+    ToTensor for every byte value (restated with numpy float32 / float64 fma)."""
+    import numpy as np
+    x = np.arange(256, dtype=np.float32)
+    r = np.float32(1.0) / np.float32(255.0)
+    q = (x * r).astype(np.float32)
+    e = (x.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)      # fma(-q, 255, x): exact in float64, one rounding
+    q2 = (e.astype(np.float64) * np.float64(r) + q.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(q2, x / np.float32(255.0))

@@ -391,3 +391,97 @@ def test_host_pipeline_uint8_images():
         assert torch.equal(a, b)
     assert torch.equal(outs[0]["gd"][0], outs[1]["gd"][0])
 
+
+
+def _problem_tensors(B, H, W, seed):
+    from dvsloss.synthetic import pose_matrix
+    dev = torch.device("cuda:0")
+    p = make_problem(B, H, W, 2, 4, seed=seed, consistent=True)
+    cut = lambda t: t.to(dev).contiguous()
+    Ts = [cut(pose_matrix(a.view(B, 3), t.view(B, 3), inv)) for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+    return p, cut, Ts
+
+
+def test_fused_reads_bf16_disparities_and_uint8_images_in_kernel():
+    """bf16 disparity maps (DepthNet under autocast) and uint8 frames (before ToTensor) go to the two-source
+    kernel as they are; conversion on load is exact, so every result equals the call on the fp32-expanded tensors bit for bit
+    (the bf16 gradients are the fp32 ones rounded to nearest even, i.e. what autograd's .to(bf16) backward would hand back)."""
+    from dvsloss import view_synthesis_loss
+    p, cut, Ts = _problem_tensors(2, 96, 128, 41)
+    q8 = lambda t: (t * 255).round().clamp(0, 255).to(torch.uint8)
+    tgt8, src8 = cut(q8(p["target"])), [cut(q8(s)) for s in p["sources"]]
+    dbf = [cut(d).to(torch.bfloat16) for d in p["disps"]]
+    K, iK, noise = cut(p["K"]), cut(p["inv_K"]), [cut(n) for n in p["noise"]]
+
+    def run(disps, tgt, srcs):
+        disps = [d.clone().requires_grad_(True) for d in disps]
+        T = [t.clone().requires_grad_(True) for t in Ts]
+        out = view_synthesis_loss(disps, tgt, srcs, K, iK, T, noise=noise, return_selection=True)
+        out[0].backward()
+        return out, [d.grad for d in disps], [t.grad for t in T]
+
+    ref, gd_ref, gT_ref = run([d.float() for d in dbf], tgt8.float().div(255), [s.float().div(255) for s in src8])
+    for disps, tgt, srcs, what in ((dbf, tgt8, src8, "bf16+u8"), ([d.float() for d in dbf], tgt8, src8, "u8"),
+                                   (dbf, tgt8.float().div(255), [s.float().div(255) for s in src8], "bf16")):
+        got, gd, gT = run(disps, tgt, srcs)
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), what
+        for a, b in zip(got[2:], ref[2:]):
+            assert torch.equal(a, b), what
+        for a, b in zip(gT, gT_ref):
+            assert torch.equal(a, b), what
+        for a, b, d in zip(gd, gd_ref, disps):
+            assert a.dtype == d.dtype
+            assert torch.equal(a, b.to(a.dtype)), what
+
+
+def test_reduced_precision_inputs_with_other_source_counts_fall_back_to_expansion():
+    """N != 2 has no in-kernel conversion: the front end widens the tensors first; the C ABI refuses."""
+    import ctypes as C
+    from dvsloss import _lib, view_synthesis_loss
+    from dvsloss.synthetic import pose_matrix
+    dev = torch.device("cuda:0")
+    B, H, W, N = 1, 64, 96, 3
+    p = make_problem(B, H, W, N, 4, seed=5, consistent=True)
+    cut = lambda t: t.to(dev).contiguous()
+    Ts = [cut(pose_matrix(a.view(B, 3), t.view(B, 3), inv)) for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+    q8 = lambda t: (t * 255).round().clamp(0, 255).to(torch.uint8)
+    tgt8, src8 = cut(q8(p["target"])), [cut(q8(s)) for s in p["sources"]]
+    disps = [cut(d) for d in p["disps"]]
+    a = view_synthesis_loss(disps, tgt8, src8, cut(p["K"]), cut(p["inv_K"]), Ts, noise=None)
+    b = view_synthesis_loss(disps, tgt8.float().div(255), [s.float().div(255) for s in src8], cut(p["K"]), cut(p["inv_K"]), Ts,
+                            noise=None)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    sh = _lib.make_shape(B, H, W, N, [tuple(d.shape[2:]) for d in disps])
+    pr = _lib.DvsParams(0.1, 10.0, 0.85, 1e-3, 1e-7, 1)
+    out = torch.empty(5, device=dev)
+    ws = torch.empty(1 << 22, dtype=torch.uint8, device=dev)
+    rc = _lib.lib().dvs_photometric_forward_ex(C.byref(sh), C.byref(pr), _lib.fptr_array(disps), 0, tgt8.data_ptr(),
+                                               _lib.fptr_array(src8), _lib.DTYPE_U8, p["K"].to(dev).data_ptr(),
+                                               p["inv_K"].to(dev).data_ptr(), _lib.fptr_array(Ts), None, 0, 0,
+                                               out.data_ptr(), out[4:].data_ptr(), None, None, None,
+                                               (ws.data_ptr() + 255) // 256 * 256, 0)
+    assert rc == -1
+
+
+def test_host_pipeline_uint8_in_kernel():
+    """Host-resident entry point with the bytes handed to the kernel (no expansion pass) == expanded on the device."""
+    from dvsloss import HostLossPipeline
+    from dvsloss.synthetic import pose_matrix
+    dev = torch.device("cuda:0")
+    B, H, W = 4, 64, 96
+    p = make_problem(B, H, W, 2, 4, seed=34, consistent=True)
+    Ts = [pose_matrix(a.view(B, 3), t.view(B, 3), inv) for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+    q8 = lambda t: (t * 255).round().clamp(0, 255).to(torch.uint8)
+    pin = lambda t: t.contiguous().pin_memory()
+    h_in = dict(target=pin(q8(p["target"])), sources=[pin(q8(s)) for s in p["sources"]], disps=[pin(d) for d in p["disps"]],
+                K=pin(p["K"]), inv_K=pin(p["inv_K"]), Ts=[pin(T) for T in Ts])
+    outs = []
+    for flag in (True, False):
+        h_out = dict(loss=torch.empty(5).pin_memory(), gd=[torch.empty_like(d).pin_memory() for d in h_in["disps"]],
+                     gT=[torch.empty_like(T).pin_memory() for T in h_in["Ts"]])
+        HostLossPipeline(B, H, W, [tuple(d.shape[2:]) for d in h_in["disps"]], 2, chunks=2, device=dev, noise=None,
+                         uint8_images=True, u8_in_kernel=flag).run(h_in, h_out)
+        outs.append(h_out)
+    assert torch.equal(outs[0]["loss"], outs[1]["loss"])
+    for a, b in zip(outs[0]["gT"] + outs[0]["gd"], outs[1]["gT"] + outs[1]["gd"]):
+        assert torch.equal(a, b)
