@@ -804,3 +804,46 @@ extern "C" int dvs_u8_to_f32(const uint8_t* src, float* dst, int64_t n, void* st
   return DVS_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ triplet batcher
+// GPU side of MonoDataset.__getitem__ + collation (vo/dataset/common.py:48-92) for frames that are resident on the device
+// as decoded, resized uint8 RGB (what _read_image returns): for every sample b and role r (source_left, target_image,
+// source_right) copy frame idx[b][r], turn HWC into CHW and either keep the bytes or apply ToTensor (x / 255, exact).
+// One thread per output pixel (all three channels), consecutive threads -> consecutive pixels of a row: the three planes
+// are written as coalesced rows, the interleaved source bytes are read as 3 consecutive bytes per thread.
+template <bool OUT_F32, bool HWC>
+__global__ void __launch_bounds__(256) gather_triplets_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ idx,
+                                                              void* o0, void* o1, void* o2, int B, int HW) {
+  const int b = blockIdx.y, r = blockIdx.z;
+  const uint8_t* src = frames + (size_t)idx[b * 3 + r] * 3 * HW;
+  void* out = r == 0 ? o0 : (r == 1 ? o1 : o2);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < HW; e += gridDim.x * blockDim.x) {
+    uint8_t v[3];
+    if (HWC) { v[0] = src[3 * e]; v[1] = src[3 * e + 1]; v[2] = src[3 * e + 2]; }
+    else { v[0] = src[e]; v[1] = src[HW + e]; v[2] = src[2 * HW + e]; }
+    const size_t o = (size_t)b * 3 * HW + e;
+    if (OUT_F32) {
+      float* f = static_cast<float*>(out);
+      f[o] = __fdiv_rn((float)v[0], 255.f); f[o + HW] = __fdiv_rn((float)v[1], 255.f); f[o + 2 * HW] = __fdiv_rn((float)v[2], 255.f);
+    } else {
+      uint8_t* u = static_cast<uint8_t*>(out);
+      u[o] = v[0]; u[o + HW] = v[1]; u[o + 2 * HW] = v[2];
+    }
+  }
+}
+extern "C" int dvs_gather_triplets_u8(const uint8_t* frames, int frames_hwc, const int32_t* idx, void* out_left,
+                                      void* out_target, void* out_right, int out_dtype, int B, int H, int W, void* stream) {
+  if (!frames || !idx || !out_left || !out_target || !out_right || B < 1 || H < 1 || W < 1) return DVS_EINVAL;
+  if (out_dtype != DVS_DTYPE_F32 && out_dtype != DVS_DTYPE_U8) return DVS_EINVAL;
+  const int HW = H * W;
+  int gx = (HW + 255) / 256;
+  if (gx > 148 * 4) gx = 148 * 4;
+  const dim3 grid(gx, B, 3);
+  const bool f32 = out_dtype == DVS_DTYPE_F32;
+  if (f32 && frames_hwc) gather_triplets_kernel<true, true><<<grid, 256, 0, ST(stream)>>>(frames, idx, out_left, out_target, out_right, B, HW);
+  else if (f32) gather_triplets_kernel<true, false><<<grid, 256, 0, ST(stream)>>>(frames, idx, out_left, out_target, out_right, B, HW);
+  else if (frames_hwc) gather_triplets_kernel<false, true><<<grid, 256, 0, ST(stream)>>>(frames, idx, out_left, out_target, out_right, B, HW);
+  else gather_triplets_kernel<false, false><<<grid, 256, 0, ST(stream)>>>(frames, idx, out_left, out_target, out_right, B, HW);
+  LAUNCH_CHECK();
+  return DVS_OK;
+}

@@ -212,6 +212,15 @@ int dvs_pose_matrix_bwd(const float* grad_M, const float* axisangle, const float
  * (IEEE division), so uint8 image batches can cross PCIe as bytes and be expanded on the device. */
 int dvs_u8_to_f32(const uint8_t* src, float* dst, int64_t n, void* stream);
 
+/* Device side of MonoDataset.__getitem__ + the DataLoader's collation (vo/dataset/common.py:48-92) for frames already
+ * resident on the device as decoded, resized uint8 RGB (what _read_image returns; decoding and resizing stay on the host):
+ *   frames  [T,H,W,3] (frames_hwc != 0, PIL / OpenCV order) or [T,3,H,W]
+ *   idx     [B,3] int32 device array: frame numbers of (source_left, target_image, source_right) of every sample
+ *   out_*   [B,3,H,W] each, out_dtype DVS_DTYPE_F32 (ToTensor applied: x / 255, exact) or DVS_DTYPE_U8 (bytes kept; feed
+ *           dvs_photometric_forward_ex with image_dtype = DVS_DTYPE_U8) */
+int dvs_gather_triplets_u8(const uint8_t* frames, int frames_hwc, const int32_t* idx, void* out_left, void* out_target,
+                           void* out_right, int out_dtype, int B, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
