@@ -44,9 +44,16 @@ def test_checkpoint_round_trip_with_live_reference_classes():
     d.load_state_dict(rd.state_dict())                      # strict: raises on any missing / unexpected key
     p.load_state_dict(rp.state_dict())
     x, pair = torch.rand(1, 3, 64, 96), torch.rand(1, 6, 64, 96)
+    from model.layers import Conv3x3
     with torch.no_grad():
         a, b = d(x), rd(x)
-        assert all(torch.equal(a[k], b[k]) for k in b)
+        assert all(torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-6) for k in b)       # border strips: another summation order
+        Conv3x3.fast_reflect = False
+        try:
+            a = d(x)
+        finally:
+            Conv3x3.fast_reflect = True
+        assert all(torch.equal(a[k], b[k]) for k in b)                                  # literal sequence: bit-identical
         assert all(torch.equal(u, v) for u, v in zip(p(pair), rp(pair)))
     rd.load_state_dict(d.state_dict())                      # and back: checkpoints written here load in the reference
     rp.load_state_dict(p.state_dict())
@@ -94,3 +101,25 @@ def test_shadowing_packages_keep_reference_submodules_importable():
     lines = r.stdout.strip().splitlines()[-5:]
     assert lines[0].startswith(PKG) and lines[1].startswith(PKG), lines
     assert lines[2].startswith(REF) and lines[3].startswith(REF) and lines[4].startswith(REF), lines
+
+
+def test_conv3x3_without_padded_copy_equals_reflection_pad_conv():
+    """model/layers.py: Conv3x3 computes conv(ReflectionPad2d(1)(x)) as a zero-padded convolution + four border strips; values
+    and every gradient must equal the literal sequence of the reference (model/layers.py:120-136)."""
+    from model.layers import Conv3x3
+    torch.manual_seed(0)
+    m = Conv3x3(5, 4).double()
+    x = torch.randn(2, 5, 9, 11, dtype=torch.float64, requires_grad=True)
+    g = torch.randn(2, 4, 9, 11, dtype=torch.float64)
+    outs = []
+    for fast in (True, False):
+        Conv3x3.fast_reflect = fast
+        try:
+            y = m(x)
+            outs.append((y, torch.autograd.grad(y, (x, m.conv.weight, m.conv.bias), g)))
+        finally:
+            Conv3x3.fast_reflect = True
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=0, atol=1e-12)
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.allclose(a, b, rtol=0, atol=1e-12)
+    assert tuple(Conv3x3(3, 2)(torch.rand(1, 3, 2, 2)).shape) == (1, 2, 2, 2)        # too small for the strips: literal path
