@@ -20,7 +20,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "dvsloss", "libdvsloss.so")
 OBJ_DIR = os.path.join(HERE, "_build")
-SOURCES = ["dvs_api.cu", "dvs_fused.cu", "dvs_pair.cu", "dvs_ops.cu"]
+SOURCES = ["dvs_api.cu", "dvs_fused.cu", "dvs_pair.cu", "dvs_ops.cu", "dvs_head.cu"]
 HEADERS = ["dvs_fused_core.cuh", "dvs_pair_core.cuh", "dvs_host.h", os.path.join(ROOT, "include", "dvsloss.h")]
 
 NVCC_FLAGS = [

@@ -349,3 +349,65 @@ def images_u8_to_f32(src: torch.Tensor, out: torch.Tensor = None) -> torch.Tenso
         check(lib().dvs_u8_to_f32(src.data_ptr(), out.data_ptr(), src.numel(), stream_ptr(src.device)), "dvs_u8_to_f32")
     return out
 
+
+
+# ---------------------------------------------------------------------------------------------------- DepthNet disparity head
+class _DispHead(torch.autograd.Function):
+    """ReflectionPad2d(1) + Conv2d(C, 1, 3) + Sigmoid in one kernel (model/depthnet.py:57-58,87-88; model/layers.py:120-136)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_dtype):
+        from ._lib import DTYPE_BF16, DTYPE_F32
+        if not x.is_cuda:
+            raise DvsError("disp_head runs on CUDA tensors only (no CPU fallback by design)")
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        B, Cc, H, W = x.shape
+        xc = x.contiguous(memory_format=torch.channels_last)            # no copy when the decoder already runs channels-last
+        w = weight.detach().float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        disp = torch.empty(B, 1, H, W, dtype=out_dtype, device=x.device)
+        code = lambda dt: DTYPE_BF16 if dt == torch.bfloat16 else DTYPE_F32
+        with torch.cuda.device(x.device):
+            check(lib().dvs_disp_head_fwd(xc.data_ptr(), code(xc.dtype), w.data_ptr(), ptr(b), disp.data_ptr(), code(out_dtype),
+                                          B, Cc, H, W, stream_ptr(x.device)), "dvs_disp_head_fwd")
+        ctx.save_for_backward(xc, w, disp)
+        ctx.has_bias = bias is not None
+        ctx.wdtype = weight.dtype
+        return disp
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        from ._lib import DTYPE_BF16, DTYPE_F32
+        xc, w, disp = ctx.saved_tensors
+        B, Cc, H, W = xc.shape
+        g = g.to(disp.dtype).contiguous()
+        gx = torch.empty_like(xc, memory_format=torch.channels_last)
+        gw = torch.empty_like(w)
+        gb = torch.empty(1, dtype=torch.float32, device=xc.device) if ctx.has_bias else None
+        n = C.c_size_t(0)
+        L = lib()
+        check(L.dvs_disp_head_bwd_workspace_bytes(B, Cc, H, W, C.byref(n)), "dvs_disp_head_bwd_workspace_bytes")
+        ws = torch.empty(n.value + 256, dtype=torch.uint8, device=xc.device)
+        code = lambda dt: DTYPE_BF16 if dt == torch.bfloat16 else DTYPE_F32
+        with torch.cuda.device(xc.device):
+            check(L.dvs_disp_head_bwd(g.data_ptr(), disp.data_ptr(), code(disp.dtype), xc.data_ptr(), code(xc.dtype), w.data_ptr(),
+                                      gx.data_ptr(), gw.data_ptr(), ptr(gb), B, Cc, H, W, (ws.data_ptr() + 255) // 256 * 256,
+                                      stream_ptr(xc.device)), "dvs_disp_head_bwd")
+        return gx, gw.to(ctx.wdtype), (gb.to(ctx.wdtype) if gb is not None else None), None
+
+
+def disp_head(x: torch.Tensor, weight: torch.Tensor, bias, out_dtype=None) -> torch.Tensor:
+    """sigmoid(conv3x3(reflection_pad(x))) with one output channel: x [B,C,H,W] (fp32 / bf16; channels-last memory is read in
+    place), weight [1,C,3,3], bias [1] or None -> disparity [B,1,H,W] in ``out_dtype`` (default: x's dtype, which is what the
+    stock modules produce under autocast)."""
+    if weight.dim() != 4 or weight.shape[0] != 1 or tuple(weight.shape[2:]) != (3, 3) or weight.shape[1] != x.shape[1]:
+        raise DvsError(f"disp_head needs a [1,C,3,3] weight for a [B,C,H,W] input, got {tuple(weight.shape)} / {tuple(x.shape)}")
+    if out_dtype is None:
+        out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
+    return _DispHead.apply(x, weight, bias, out_dtype)
+
+
+def disp_head_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dim() == 4 and x.shape[1] % 8 == 0 and 8 <= x.shape[1] <= 128 and x.shape[2] >= 3 and x.shape[3] >= 3

@@ -10,11 +10,15 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .layers import Conv3x3, ConvBlock, upsample
+from .layers import Conv3x3, ConvBlock, upsample            # (puts the package root on sys.path for dvsloss)
+from dvsloss.ops import disp_head, disp_head_supported  # noqa: E402
 from .resnet_encoder import ResnetEncoder
 
 
 class DepthNet(nn.Module):
+    # the ("dispconv", s) + sigmoid tails run as one fused kernel on CUDA (dvsloss.ops.disp_head); False = stock modules
+    fused_heads = True
+
     def __init__(self, num_layers: int = 18, pretrained: bool = True, num_input_images: int = 1, scales=range(4),
                  num_output_channels: int = 1, use_skips: bool = True):
         super().__init__()
@@ -48,6 +52,16 @@ class DepthNet(nn.Module):
                 x = torch.cat([x, feats[i - 1]], 1)
             x = self.convs[("upconv", i, 1)](x)
             if i in self.scales:
-                outputs[("disp", i)] = torch.sigmoid(self.convs[("dispconv", i)](x))
+                head = self.convs[("dispconv", i)]
+                if self.fused_heads and self.num_output_channels == 1 and head.use_refl and disp_head_supported(x):
+                    # pad + one-channel convolution + sigmoid in one kernel, written in the dtype the loss kernel reads
+                    w = head.conv.weight
+                    if torch.is_autocast_enabled() and x.dtype == torch.float32:
+                        x_in = x.to(torch.get_autocast_dtype("cuda"))     # what autocast would feed the convolution
+                    else:
+                        x_in = x
+                    outputs[("disp", i)] = disp_head(x_in, w, head.conv.bias)
+                else:
+                    outputs[("disp", i)] = torch.sigmoid(head(x))
         self.outputs = outputs
         return outputs

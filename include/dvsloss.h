@@ -212,6 +212,19 @@ int dvs_pose_matrix_bwd(const float* grad_M, const float* axisangle, const float
  * (IEEE division), so uint8 image batches can cross PCIe as bytes and be expanded on the device. */
 int dvs_u8_to_f32(const uint8_t* src, float* dst, int64_t n, void* stream);
 
+/* Disparity head of DepthNet, fused: ReflectionPad2d(1) + Conv2d(C, 1, 3) + Sigmoid (the ("dispconv", s) blocks,
+ * model/depthnet.py:57-58,87-88; Conv3x3 = model/layers.py:120-136) in one pass, writing disp_s in the dtype the loss
+ * kernel reads.  x: the decoder activation, CHANNELS-LAST [B,H,W,C] (C a multiple of 8, <= 128; 16-byte aligned), fp32 or
+ * bf16; weight: the Conv2d weight [1,C,3,3] fp32 as stored; bias [1] fp32 (may be NULL); disp [B,1,H,W] fp32 or bf16. */
+int dvs_disp_head_fwd(const void* x, int x_dtype, const float* weight, const float* bias, void* disp, int disp_dtype,
+                      int B, int C, int H, int W, void* stream);
+/* Backward: grad_disp and disp (the saved forward output) [B,1,H,W] in disp_dtype; grad_x channels-last in x_dtype;
+ * grad_weight [1,C,3,3] and grad_bias [1] (may be NULL) fp32, fixed-order reductions (bit-reproducible). */
+int dvs_disp_head_bwd_workspace_bytes(int B, int C, int H, int W, size_t* bytes);
+int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int disp_dtype, const void* x, int x_dtype,
+                      const float* weight, void* grad_x, float* grad_weight, float* grad_bias, int B, int C, int H, int W,
+                      void* workspace, void* stream);
+
 /* Device side of MonoDataset.__getitem__ + the DataLoader's collation (vo/dataset/common.py:48-92) for frames already
  * resident on the device as decoded, resized uint8 RGB (what _read_image returns; decoding and resizing stay on the host):
  *   frames  [T,H,W,3] (frames_hwc != 0, PIL / OpenCV order) or [T,3,H,W]
