@@ -847,3 +847,112 @@ extern "C" int dvs_gather_triplets_u8(const uint8_t* frames, int frames_hwc, con
   LAUNCH_CHECK();
   return DVS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ supervised depth: SILog
+// Scale-invariant log loss of depth/depth_learner.py:75-95:  d = log(max(pred, 1e-6)) - log(target) over valid pixels,
+// loss = sqrt(mean(d^2) - variance_focus * mean(d)^2).  Forward: per-block partial sums of (d, d^2, count) in double (the
+// two means nearly cancel under the square root), then one block sums them in a fixed order.  Backward is elementwise:
+// d loss / d pred_p = (d_p - vf * mean(d)) / (n * loss * max(pred_p, 1e-6)) where pred_p > 1e-6 and valid, else 0.
+__global__ void __launch_bounds__(256) silog_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                            const uint8_t* __restrict__ valid, int64_t n, double* __restrict__ part) {
+  double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    if (!valid[e]) continue;
+    const float d = logf(fmaxf(pred[e], 1e-6f)) - logf(target[e]);
+    s1 += (double)d; s2 += (double)d * (double)d; cnt += 1.0;
+  }
+  __shared__ double red[3][8];
+  for (int o = 16; o; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; red[2][threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
+    part[(size_t)blockIdx.x * 3 + threadIdx.x] = t;
+  }
+}
+// stats[0] = loss, [1] = mean(d), [2] = n, [3] = mean(d^2)   (fp32; kept for the backward)
+__global__ void silog_finish_kernel(const double* __restrict__ part, int nblk, float vf, float* __restrict__ stats) {
+  __shared__ double tot[3];
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int b = 0; b < nblk; ++b) t += part[(size_t)b * 3 + threadIdx.x];
+    tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double n = tot[2], m1 = tot[0] / n, m2 = tot[1] / n;
+    stats[0] = (float)sqrt(m2 - (double)vf * m1 * m1);
+    stats[1] = (float)m1; stats[2] = (float)n; stats[3] = (float)m2;
+  }
+}
+__global__ void __launch_bounds__(256) silog_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ stats,
+                                                        const float* __restrict__ pred, const float* __restrict__ target,
+                                                        const uint8_t* __restrict__ valid, float vf, int64_t n,
+                                                        float* __restrict__ gpred) {
+  const float k = gout[0] / (stats[2] * stats[0]), m1 = stats[1];
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    float g = 0.f;
+    const float p = pred[e];
+    if (valid[e] && p >= 1e-6f) g = k * (logf(p) - logf(target[e]) - vf * m1) / p;     // torch.clamp passes the gradient at the bound
+    gpred[e] = g;
+  }
+}
+static int silog_blocks(int64_t n) {
+  int64_t b = (n + 256 * 8 - 1) / (256 * 8);
+  return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
+}
+extern "C" int dvs_silog_workspace_bytes(int64_t n, size_t* bytes) {
+  if (!bytes || n < 1) return DVS_EINVAL;
+  *bytes = sizeof(double) * 3 * (size_t)silog_blocks(n) + 256;
+  return DVS_OK;
+}
+extern "C" int dvs_silog_fwd(const float* pred, const float* target, const uint8_t* valid, int64_t n, float variance_focus,
+                             float* stats, void* workspace, void* stream) {
+  if (!pred || !target || !valid || !stats || n < 1) return DVS_EINVAL;
+  if (!workspace || ((uintptr_t)workspace & 255)) return DVS_EWORKSPACE;
+  const int nb = silog_blocks(n);
+  double* part = static_cast<double*>(workspace);
+  silog_partial_kernel<<<nb, 256, 0, ST(stream)>>>(pred, target, valid, n, part);
+  LAUNCH_CHECK();
+  silog_finish_kernel<<<1, 32, 0, ST(stream)>>>(part, nb, variance_focus, stats);
+  LAUNCH_CHECK();
+  return DVS_OK;
+}
+extern "C" int dvs_silog_bwd(const float* grad_out, const float* stats, const float* pred, const float* target,
+                             const uint8_t* valid, int64_t n, float variance_focus, float* grad_pred, void* stream) {
+  if (!grad_out || !stats || !pred || !target || !valid || !grad_pred || n < 1) return DVS_EINVAL;
+  silog_bwd_kernel<<<silog_blocks(n), 256, 0, ST(stream)>>>(grad_out, stats, pred, target, valid, variance_focus, n, grad_pred);
+  LAUNCH_CHECK();
+  return DVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ depth map -> world points
+// EvalTrajectory.depth_to_pointcloud (vo/eval_traj.py:85-128) and the point cloud of vo/predict.py:81-95 on the device:
+// X_world = T [ depth * K^-1 (u, v, 1) ; 1 ] for every pixel, points [H*W,3]; valid[e] = depth > 0 (the host keeps those).
+__global__ void __launch_bounds__(256) pointcloud_kernel(const float* __restrict__ depth, const float* __restrict__ invK,
+                                                         const float* __restrict__ T, float* __restrict__ pts,
+                                                         uint8_t* __restrict__ valid, int H, int W) {
+  const int n = H * W;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const float u = (float)(e % W), v = (float)(e / W), z = depth[e];
+    const float rx = fmaf(invK[0], u, fmaf(invK[1], v, invK[2])), ry = fmaf(invK[4], u, fmaf(invK[5], v, invK[6])),
+                rz = fmaf(invK[8], u, fmaf(invK[9], v, invK[10]));
+    const float cx = rx * z, cy = ry * z, cz = rz * z;
+    pts[3 * (size_t)e + 0] = fmaf(T[0], cx, fmaf(T[1], cy, fmaf(T[2], cz, T[3])));
+    pts[3 * (size_t)e + 1] = fmaf(T[4], cx, fmaf(T[5], cy, fmaf(T[6], cz, T[7])));
+    pts[3 * (size_t)e + 2] = fmaf(T[8], cx, fmaf(T[9], cy, fmaf(T[10], cz, T[11])));
+    if (valid) valid[e] = z > 0.f;
+  }
+}
+extern "C" int dvs_depth_to_pointcloud(const float* depth, const float* inv_K, const float* T, float* points, uint8_t* valid,
+                                       int H, int W, void* stream) {
+  if (!depth || !inv_K || !T || !points || H < 1 || W < 1) return DVS_EINVAL;
+  int gx = (H * W + 255) / 256;
+  if (gx > 148 * 8) gx = 148 * 8;
+  pointcloud_kernel<<<gx, 256, 0, ST(stream)>>>(depth, inv_K, T, points, valid, H, W);
+  LAUNCH_CHECK();
+  return DVS_OK;
+}

@@ -82,6 +82,10 @@ _SIGNATURES = {
     "dvs_disp_head_fwd": [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     "dvs_disp_head_bwd_workspace_bytes": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)],
     "dvs_disp_head_bwd": [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp],
+    "dvs_silog_workspace_bytes": [C.c_int64, C.POINTER(C.c_size_t)],
+    "dvs_silog_fwd": [_vp, _vp, _vp, C.c_int64, C.c_float, _vp, _vp, _vp],
+    "dvs_silog_bwd": [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_float, _vp, _vp],
+    "dvs_depth_to_pointcloud": [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp],
     "dvs_gather_triplets_u8": [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
 }
 _RESTYPES = {"dvs_error_string": C.c_char_p}

@@ -411,3 +411,59 @@ def disp_head(x: torch.Tensor, weight: torch.Tensor, bias, out_dtype=None) -> to
 
 def disp_head_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dim() == 4 and x.shape[1] % 8 == 0 and 8 <= x.shape[1] <= 128 and x.shape[2] >= 3 and x.shape[3] >= 3
+
+
+# ---------------------------------------------------------------------------------------------------- supervised depth
+class _Silog(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, valid, variance_focus):
+        pred, target = _f32(pred), _f32(target)
+        require_cuda(pred, target)
+        if pred.shape != target.shape or valid.shape != pred.shape:
+            raise DvsError("silog_loss expects prediction, target and valid_mask of one shape")
+        v8 = valid.to(torch.uint8).contiguous()
+        n = pred.numel()
+        nb = C.c_size_t(0)
+        check(lib().dvs_silog_workspace_bytes(n, C.byref(nb)), "dvs_silog_workspace_bytes")
+        ws = _ws(nb.value, pred.device)
+        stats = torch.empty(4, dtype=torch.float32, device=pred.device)
+        with torch.cuda.device(pred.device):
+            check(lib().dvs_silog_fwd(ptr(pred), ptr(target), v8.data_ptr(), n, float(variance_focus), ptr(stats), ptr(ws),
+                                      stream_ptr(pred.device)), "dvs_silog_fwd")
+        ctx.save_for_backward(pred, target, v8, stats)
+        ctx.vf = float(variance_focus)
+        return stats[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target, v8, stats = ctx.saved_tensors
+        g = _f32(g).reshape(1)
+        gp = torch.empty_like(pred)
+        with torch.cuda.device(pred.device):
+            check(lib().dvs_silog_bwd(ptr(g), ptr(stats), ptr(pred), ptr(target), v8.data_ptr(), pred.numel(), ctx.vf, ptr(gp),
+                                      stream_ptr(pred.device)), "dvs_silog_bwd")
+        return gp, None, None, None
+
+
+def silog_loss(prediction: torch.Tensor, target: torch.Tensor, valid_mask: torch.Tensor, variance_focus: float = 0.85) -> torch.Tensor:
+    """depth/depth_learner.py:75-95: scale-invariant log loss over the valid pixels (one reduction kernel, double sums)."""
+    return _Silog.apply(prediction, target, valid_mask, variance_focus)
+
+
+def depth_to_pointcloud(depth: torch.Tensor, pose: torch.Tensor, intrinsic: torch.Tensor):
+    """vo/eval_traj.py:85-128 on the device: depth [H,W], camera-to-world pose [4,4], K [3,3] or [4,4] ->
+    world points [N,3] of the pixels with depth > 0 (row-major pixel order; the caller sub-samples as it likes)."""
+    depth = _f32(depth)
+    require_cuda(depth)
+    H, W = depth.shape
+    dev = depth.device
+    K = torch.eye(4, dtype=torch.float64, device=dev)
+    K[:intrinsic.shape[0], :intrinsic.shape[1]] = intrinsic.to(dev, torch.float64)
+    inv_K = torch.linalg.inv(K).float().contiguous()
+    T = pose.to(dev, torch.float32).contiguous()
+    pts = torch.empty(H * W, 3, dtype=torch.float32, device=dev)
+    valid = torch.empty(H * W, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().dvs_depth_to_pointcloud(ptr(depth), ptr(inv_K), ptr(T), ptr(pts), valid.data_ptr(), H, W, stream_ptr(dev)),
+              "dvs_depth_to_pointcloud")
+    return pts[valid.bool()]

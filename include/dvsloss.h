@@ -225,6 +225,22 @@ int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int disp_dtype, c
                       const float* weight, void* grad_x, float* grad_weight, float* grad_bias, int B, int C, int H, int W,
                       void* workspace, void* stream);
 
+/* Supervised-depth path (depth/depth_learner.py).  SILog loss (:75-95): over the n elements with valid[e] != 0,
+ * d = log(max(pred, 1e-6)) - log(target), loss = sqrt(mean(d^2) - variance_focus * mean(d)^2).  stats [4] receives
+ * {loss, mean(d), count, mean(d^2)} (kept for the backward); sums in double, fixed order.  The multi-scale loss around it
+ * (:97-117) re-uses dvs_upsample_bilinear_* and dvs_smooth_loss_*. */
+int dvs_silog_workspace_bytes(int64_t n, size_t* bytes);
+int dvs_silog_fwd(const float* pred, const float* target, const uint8_t* valid, int64_t n, float variance_focus,
+                  float* stats, void* workspace, void* stream);
+int dvs_silog_bwd(const float* grad_out, const float* stats, const float* pred, const float* target, const uint8_t* valid,
+                  int64_t n, float variance_focus, float* grad_pred, void* stream);
+
+/* EvalTrajectory.depth_to_pointcloud (vo/eval_traj.py:85-128) / the point cloud of vo/predict.py:81-95: depth [H,W],
+ * inv_K [4,4], T [4,4] (camera-to-world) -> points [H*W,3] = (T [depth * inv_K (u,v,1); 1])[:3]; valid [H*W] = depth > 0
+ * (may be NULL). */
+int dvs_depth_to_pointcloud(const float* depth, const float* inv_K, const float* T, float* points, uint8_t* valid,
+                            int H, int W, void* stream);
+
 /* Device side of MonoDataset.__getitem__ + the DataLoader's collation (vo/dataset/common.py:48-92) for frames already
  * resident on the device as decoded, resized uint8 RGB (what _read_image returns; decoding and resizing stay on the host):
  *   frames  [T,H,W,3] (frames_hwc != 0, PIL / OpenCV order) or [T,3,H,W]
