@@ -1,12 +1,13 @@
 // Fused view-synthesis loss for sm_100a: kernels + C ABI (include/dvsloss.h).
 //
 // Launch sequence of dvs_photometric_forward (all on the caller's stream, no host sync):
-//   1. mean_partial_kernel   partial sums of the up-sampled disparity per (scale, image)      [reads disp once]
-//   2. fused_tile_kernel     one CTA per 30x30 tile x image, all scales, loss sums (+ unit gradients)
-//   2b. gather_gdisp_kernel  unit gradients of the up-sampled scales: fixed-order sum of the tiles' coarse boxes
-//   3. finish_kernel         per (scale, image): fixed-order reduction of the per-CTA partials, pose
-//                            gradient dL/dT = K^T dL/dP, smoothness mean-coupling coefficient
-//   4. final_kernel          loss/s and loss
+//   1. mean_partial_kernel   partial sums of the up-sampled disparity per (scale, image)      [reads disp once];
+//                            when pose parameters are the inputs: the 4x4 matrices (transformation_from_parameters)
+//   2. fused_tile_kernel / fused_pair_kernel (dvs_pair.cu)   one CTA per 30x30 tile x image, all scales, loss sums (+ unit gradients)
+//   3. postpass_kernel       per (scale, image): fixed-order reduction of the per-CTA partials, pose gradient
+//                            dL/dT = K^T dL/dP (-> d/d(axisangle, translation)), smoothness mean-coupling coefficient;
+//                            unit gradients of the up-sampled scales (fixed-order sum of the tiles' coarse boxes);
+//                            the last block forms loss/s and loss
 // dvs_photometric_backward is one elementwise kernel: grad = g_s * (unit - coupling), pose combine.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,6 +21,7 @@
 
 #include "dvs_fused_core.cuh"
 #include "dvs_host.h"
+#include "dvs_pose.cuh"
 
 namespace dvs {
 
@@ -28,8 +30,25 @@ constexpr int kMaxDevices = 64;
 // ------------------------------------------------------------------------------------------------ 1. disparity mean
 // mean(up-sample(d)) is a fixed linear functional of d: sum_ij rw[i] cw[j] d[i,j] / (H W); for the
 // exact power-of-two pyramids of the reference the weights are the constant (H/h)(W/w).
-__global__ void __launch_bounds__(256) mean_partial_kernel(FusedParams p, float* mean_part) {
+// Pose parameters handed to the loss instead of matrices: the pre-pass builds
+// T_i = transformation_from_parameters(axisangle_i, translation_i, invert_i) (vo/learner_func.py:29-104) into the workspace,
+// the post-pass chains d loss / d T_i back to the six pose numbers -- no separate pose launches.
+struct PoseIO {
+  const float* aa[kMaxN];     // [B,3] each; aa[0] == null: matrices were given
+  const float* tr[kMaxN];
+  int invert[kMaxN];
+  float* Tws;                 // [N][B][16]
+  float* uP;                  // [S][N][B][6] unit gradients (axis-angle, translation)
+  int* done;                  // post-pass ticket counter (zeroed here)
+};
+
+__global__ void __launch_bounds__(256) mean_partial_kernel(FusedParams p, float* mean_part, PoseIO pose) {
   const int chunk = blockIdx.x, b = blockIdx.y, s = blockIdx.z;
+  if ((chunk | s) == 0 && pose.aa[0] && threadIdx.x < p.N) {
+    const int i = threadIdx.x;
+    pose_matrix(pose.aa[i] + 3 * b, pose.tr[i] + 3 * b, pose.invert[i], pose.Tws + ((size_t)i * p.B + b) * 16);
+  }
+  if ((chunk | b | s) == 0 && threadIdx.x == 0) *pose.done = 0;
   const int h = p.dh[s], w = p.dw[s], n = h * w;
   const float* d = p.disp[s] + (size_t)b * n;
   const bool exact = (p.H % h == 0) && (p.W % w == 0);
@@ -124,25 +143,17 @@ __global__ void __launch_bounds__(NT, (NS <= 2 ? 2 : 1)) fused_tile_kernel(const
   }
 }
 
-// ------------------------------------------------------------------------------------------------ 2b. coarse gradients
-// unit gradients of the up-sampled scales: one thread per disparity element gathers the tile boxes (gather_gdisp).
-__global__ void __launch_bounds__(256) gather_gdisp_kernel(const __grid_constant__ FusedParams p) {
-  const int s = blockIdx.y;
-  const int dh = p.dh[s], dw = p.dw[s];
-  if (dh == p.H && dw == p.W) return;
-  const int n = p.B * dh * dw;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const int b = e / (dh * dw), r = e - b * dh * dw;
-    const int I = r / dw, J = r - I * dw;
-    p.gdisp[s][e] = gather_gdisp(p, s, b, I, J);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ 3. finish
-// grid (B, S), 256 threads = 8 warps; warp y reduces values v = y, y+8, ... over the tiles of image b in a
-// fixed order (lane-strided, then xor-shuffle) -> deterministic.
+// ------------------------------------------------------------------------------------------------ 3. post-pass
+// One launch after the tile kernel:
+//   blocks [0, B S)        per (image, scale): fixed-order reduction over the image's tiles (warp y reduces values v = y,
+//                          y+8, ...: lane-strided, then xor-shuffle -> deterministic); pose moments -> dL/dP -> dL/dT =
+//                          K^T dL/dP (-> the six pose parameters when those were the inputs); smoothness mean-coupling
+//                          coefficient.  The block that finishes LAST (ticket counter) also forms loss/s and loss from
+//                          the per-image sums, again in a fixed order.
+//   blocks [B S, ...)      unit gradients of the up-sampled scales: one thread per disparity element gathers the tile
+//                          boxes (gather_gdisp).
 struct FinishParams {
-  int B, H, W, N, S, tiles_per_img, want_grad;
+  int B, H, W, N, S, tiles_per_img, want_grad, gather_blocks;
   float smooth_w;
   const float* part;        // [nblk][S][nv]
   const float* mean_part;   // [S][B][kMeanBlocks]
@@ -151,12 +162,31 @@ struct FinishParams {
   float* perimg;            // [S][B][3]
   float* uT;                // [S][N][B][16] or null
   float* coup;              // [S][B] or null
+  float* loss_per_scale;    // [S]
+  float* loss_total;        // [1]
 };
-__global__ void __launch_bounds__(256) finish_kernel(FinishParams f) {
-  const int b = blockIdx.x, s = blockIdx.y;
+__global__ void __launch_bounds__(256) postpass_kernel(const __grid_constant__ FusedParams p, FinishParams f, PoseIO pose) {
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x >= f.B * f.S) {
+    // ---- gather: grid-stride over the elements of every up-sampled scale
+    const int g = blockIdx.x - f.B * f.S;
+    for (int s = 0; s < p.S; ++s) {
+      const int dh = p.dh[s], dw = p.dw[s];
+      if (dh == p.H && dw == p.W) continue;
+      const int n = p.B * dh * dw;
+      for (int e = g * blockDim.x + tid; e < n; e += f.gather_blocks * blockDim.x) {
+        const int b = e / (dh * dw), r = e - b * dh * dw;
+        const int I = r / dw, J = r - I * dw;
+        p.gdisp[s][e] = gather_gdisp(p, s, b, I, J);
+      }
+    }
+    return;
+  }
+  const int b = blockIdx.x % f.B, s = blockIdx.x / f.B;
   const int nv = 3 + 12 * f.N;
-  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int lane = tid & 31, wy = tid >> 5;
   __shared__ float res[3 + 12 * kMaxN];
+  __shared__ int last;
   for (int v = wy; v < nv; v += 8) {
     float a = 0.f;
     for (int tl = lane; tl < f.tiles_per_img; tl += 32)
@@ -165,52 +195,58 @@ __global__ void __launch_bounds__(256) finish_kernel(FinishParams f) {
     if (lane == 0) res[v] = a;
   }
   __syncthreads();
-  const int tid = threadIdx.x;
   if (tid < 3) f.perimg[(s * f.B + b) * 3 + tid] = res[tid];
-  if (!f.want_grad) return;
-  if (tid < f.N) {
-    // pose moments -> dL/dP -> dL/dT = K^T dL/dP
-    float dT[16];
-    moments_to_dT(res + 3 + 12 * tid, f.K + b * 16, f.invK + b * 16, dT);
-    for (int e = 0; e < 16; ++e) f.uT[(((size_t)s * f.N + tid) * f.B + b) * 16 + e] = dT[e];
-  }
-  if (tid == 64) {
-    const float* mp = f.mean_part + (s * f.B + b) * kMeanBlocks;
-    float mu = 0.f;
-    for (int k = 0; k < kMeanBlocks; ++k) mu += mp[k];
-    mu = mu / ((float)f.H * (float)f.W);
-    float inv = 1.0f / (fmaxf(mu, 0.001f) + 1e-7f);
-    float live = mu >= 0.001f ? 1.f : 0.f;
-    float kap = f.smooth_w / (float)(1 << s);
-    float Nx = (float)f.B * (float)f.H * (float)(f.W - 1), Ny = (float)f.B * (float)(f.H - 1) * (float)f.W;
-    // sum_q gn_q * n_q == kappa * (Sx/Nx + Sy/Ny) (Euler: the term is 1-homogeneous in n)
-    f.coup[s * f.B + b] = kap * (res[1] / Nx + res[2] / Ny) * inv * live / ((float)f.H * (float)f.W);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ 4. final
-__global__ void final_kernel(const float* perimg, int B, int H, int W, int S, float smooth_w,
-                             float* loss_per_scale, float* loss_total) {
-  __shared__ float ls[kMaxS];
-  int s = threadIdx.x;
-  if (s < S) {
-    float ph = 0.f, sx = 0.f, sy = 0.f;
-    for (int b = 0; b < B; ++b) {
-      ph += perimg[(s * B + b) * 3 + 0];
-      sx += perimg[(s * B + b) * 3 + 1];
-      sy += perimg[(s * B + b) * 3 + 2];
+  if (f.want_grad) {
+    if (tid < f.N) {
+      // pose moments -> dL/dP -> dL/dT = K^T dL/dP
+      float dT[16];
+      moments_to_dT(res + 3 + 12 * tid, f.K + b * 16, f.invK + b * 16, dT);
+      if (f.uT)
+        for (int e = 0; e < 16; ++e) f.uT[(((size_t)s * f.N + tid) * f.B + b) * 16 + e] = dT[e];
+      if (pose.aa[0]) {
+        float* o = pose.uP + (((size_t)s * f.N + tid) * f.B + b) * 6;
+        pose_matrix_grad(dT, pose.aa[tid] + 3 * b, pose.tr[tid] + 3 * b, pose.invert[tid], o, o + 3);
+      }
     }
-    float kap = smooth_w / (float)(1 << s);
-    float Nx = (float)B * (float)H * (float)(W - 1), Ny = (float)B * (float)(H - 1) * (float)W;
-    float l = ph / ((float)B * (float)H * (float)W) + kap * (sx / Nx + sy / Ny);
-    ls[s] = l;
-    loss_per_scale[s] = l;
+    if (tid == 64) {
+      const float* mp = f.mean_part + (s * f.B + b) * kMeanBlocks;
+      float mu = 0.f;
+      for (int k = 0; k < kMeanBlocks; ++k) mu += mp[k];
+      mu = mu / ((float)f.H * (float)f.W);
+      float inv = 1.0f / (fmaxf(mu, 0.001f) + 1e-7f);
+      float live = mu >= 0.001f ? 1.f : 0.f;
+      float kap = f.smooth_w / (float)(1 << s);
+      float Nx = (float)f.B * (float)f.H * (float)(f.W - 1), Ny = (float)f.B * (float)(f.H - 1) * (float)f.W;
+      // sum_q gn_q * n_q == kappa * (Sx/Nx + Sy/Ny) (Euler: the term is 1-homogeneous in n)
+      f.coup[s * f.B + b] = kap * (res[1] / Nx + res[2] / Ny) * inv * live / ((float)f.H * (float)f.W);
+    }
+  }
+  // ---- the last (image, scale) block to get here forms the losses
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(pose.done, 1) == f.B * f.S - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  __shared__ float ls[kMaxS];
+  if (tid < f.S) {
+    float ph = 0.f, sx = 0.f, sy = 0.f;
+    for (int bb = 0; bb < f.B; ++bb) {
+      ph += __ldcg(f.perimg + (tid * f.B + bb) * 3 + 0);
+      sx += __ldcg(f.perimg + (tid * f.B + bb) * 3 + 1);
+      sy += __ldcg(f.perimg + (tid * f.B + bb) * 3 + 2);
+    }
+    float kap = f.smooth_w / (float)(1 << tid);
+    float Nx = (float)f.B * (float)f.H * (float)(f.W - 1), Ny = (float)f.B * (float)(f.H - 1) * (float)f.W;
+    float l = ph / ((float)f.B * (float)f.H * (float)f.W) + kap * (sx / Nx + sy / Ny);
+    ls[tid] = l;
+    f.loss_per_scale[tid] = l;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     float t = 0.f;
-    for (int k = 0; k < S; ++k) t += ls[k];
-    loss_total[0] = t / (float)S;
+    for (int k = 0; k < f.S; ++k) t += ls[k];
+    f.loss_total[0] = t / (float)f.S;
   }
 }
 
@@ -225,9 +261,23 @@ struct BackwardParams {
   const float* coup;              // [S][B]
   float* gT[kMaxN];
   int out_bf16;                   // grad_disp tensors are bf16 (disparities were bf16)
+  // pose-parameter mode: uT is [S][N][B][6] and the outputs are gaa[i], gtr[i] [B,3] instead of gT[i] [B,4,4]
+  int pose;
+  float* gaa[kMaxN];
+  float* gtr[kMaxN];
 };
 __global__ void __launch_bounds__(256) backward_scale_kernel(BackwardParams q) {
   const int s = blockIdx.y;
+  if (s == q.S && q.pose) {   // grad_(axisangle, translation)[i][b] = sum_s g_s uP[s][i][b]
+    const int n = q.N * q.B * 6;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+      const int i = e / (q.B * 6), r = e - i * q.B * 6, b = r / 6, k = r - b * 6;
+      float a = 0.f;
+      for (int kk = 0; kk < q.S; ++kk) a = fmaf(q.g[kk], q.uT[((size_t)kk * q.N + i) * q.B * 6 + r], a);
+      if (k < 3) q.gaa[i][b * 3 + k] = a; else q.gtr[i][b * 3 + k - 3] = a;
+    }
+    return;
+  }
   if (s == q.S) {   // pose: grad_T[i][b] = sum_s g_s uT[s][i][b]
     int n = q.N * q.B * 16;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
@@ -285,7 +335,7 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(BackwardParams q) {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t mean_part, part, perimg, uT, coup, lossbuf, cpart, total;
+  size_t mean_part, part, perimg, uT, coup, lossbuf, counter, Tws, cpart, total;
   int tiles_x, tiles_y, nblk;
   int cstride, coff[kMaxS], cbw[kMaxS];
 };
@@ -301,6 +351,8 @@ static WsLayout ws_layout(const DvsShape& sh) {
   w.uT = o;        o = align_up(o + sizeof(float) * sh.S * sh.N * sh.B * 16, 256);   // used by backward_recompute
   w.coup = o;      o = align_up(o + sizeof(float) * sh.S * sh.B, 256);
   w.lossbuf = o;   o = align_up(o + sizeof(float) * 8, 256);
+  w.counter = o;   o = align_up(o + sizeof(int), 256);
+  w.Tws = o;       o = align_up(o + sizeof(float) * sh.N * sh.B * 16, 256);
   w.cstride = 0;
   for (int s = 0; s < sh.S; ++s) {
     const bool direct = sh.dh[s] == sh.H && sh.dw[s] == sh.W;
@@ -379,14 +431,15 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
                        const float* const* src, const float* K, const float* inv_K, const float* const* T,
                        const float* const* noise, uint64_t seed, uint64_t offset, float* loss_per_scale,
                        float* loss_total, uint8_t* const* sel, float* const* ugrad_disp, float* uT, float* coup,
-                       void* workspace, cudaStream_t st, int io_flags = 0) {
+                       void* workspace, cudaStream_t st, int io_flags = 0, const PoseIO* pose_in = nullptr,
+                       const unsigned long long* offset_dev = nullptr) {
   int rc = check_shape(sh);
   if (rc) return rc;
   if (io_flags && sh->N != 2) return DVS_EINVAL;      // bf16 / uint8 inputs are read by the two-source kernel only
-  if (!pr || !disp || !target || !src || !K || !inv_K || !T || !loss_per_scale || !loss_total) return DVS_EINVAL;
+  if (!pr || !disp || !target || !src || !K || !inv_K || (!T && !pose_in) || !loss_per_scale || !loss_total) return DVS_EINVAL;
   if (!workspace || ((uintptr_t)workspace & 255)) return DVS_EWORKSPACE;
   const bool want_grad = ugrad_disp != nullptr;
-  if (want_grad && (!uT || !coup)) return DVS_EINVAL;
+  if (want_grad && (!coup || (!uT && !(pose_in && pose_in->uP)))) return DVS_EINVAL;
   WsLayout w = ws_layout(*sh);
   char* base = static_cast<char*>(workspace);
 
@@ -401,12 +454,23 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
     p.gdisp[s] = want_grad ? ugrad_disp[s] : nullptr;
     if (want_grad && !ugrad_disp[s]) return DVS_EINVAL;
   }
+  PoseIO pose{};
+  if (pose_in) pose = *pose_in;
+  pose.Tws = reinterpret_cast<float*>(base + w.Tws);
+  pose.done = reinterpret_cast<int*>(base + w.counter);
   for (int i = 0; i < sh->N; ++i) {
-    if (!src[i] || !T[i]) return DVS_EINVAL;
-    p.src[i] = src[i]; p.T[i] = T[i];
+    if (!src[i]) return DVS_EINVAL;
+    p.src[i] = src[i];
+    if (pose_in) {
+      if (!pose.aa[i] || !pose.tr[i]) return DVS_EINVAL;
+      p.T[i] = pose.Tws + (size_t)i * sh->B * 16;
+    } else {
+      if (!T[i]) return DVS_EINVAL;
+      p.T[i] = T[i];
+    }
   }
   p.target = target; p.K = K; p.invK = inv_K;
-  p.seed = seed; p.offset = offset;
+  p.seed = seed; p.offset = offset; p.offset_dev = offset_dev;
   p.min_disp = 1.0f / pr->max_depth;
   p.disp_range = 1.0f / pr->min_depth - 1.0f / pr->max_depth;
   p.ssim_w = pr->ssim_ratio; p.l1_w = 1.0f - pr->ssim_ratio;
@@ -432,7 +496,7 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
   p.cstride = w.cstride;
   for (int s = 0; s < sh->S; ++s) { p.coff[s] = w.coff[s]; p.cbw[s] = w.cbw[s]; }
 
-  mean_partial_kernel<<<dim3(kMeanBlocks, sh->B, sh->S), 256, 0, st>>>(p, reinterpret_cast<float*>(base + w.mean_part));
+  mean_partial_kernel<<<dim3(kMeanBlocks, sh->B, sh->S), 256, 0, st>>>(p, reinterpret_cast<float*>(base + w.mean_part), pose);
   DVS_CUDA_TRY(cudaGetLastError());
   ProfileEvents* pe = nullptr;
   if (g_profile.load()) {
@@ -456,33 +520,32 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
     g_prof_dev.store(dev);
   }
 
-  if (want_grad && w.cstride > 0) {
-    size_t nmax = 0;
-    for (int s = 0; s < sh->S; ++s)
-      if (w.cbw[s]) nmax = nmax > (size_t)sh->B * sh->dh[s] * sh->dw[s] ? nmax : (size_t)sh->B * sh->dh[s] * sh->dw[s];
-    int gx = (int)((nmax + 255) / 256);
-    if (gx > 148 * 16) gx = 148 * 16;
-    gather_gdisp_kernel<<<dim3(gx, sh->S), 256, 0, st>>>(p);
-    DVS_CUDA_TRY(cudaGetLastError());
-  }
-
   FinishParams f{};
   f.B = sh->B; f.H = sh->H; f.W = sh->W; f.N = sh->N; f.S = sh->S;
   f.tiles_per_img = w.tiles_x * w.tiles_y; f.want_grad = p.want_grad; f.smooth_w = p.smooth_w;
   f.part = p.part; f.mean_part = p.mean_part; f.K = K; f.invK = inv_K;
   f.perimg = reinterpret_cast<float*>(base + w.perimg);
   f.uT = uT; f.coup = coup;
-  finish_kernel<<<dim3(sh->B, sh->S), 256, 0, st>>>(f);
-  DVS_CUDA_TRY(cudaGetLastError());
-  final_kernel<<<1, 32, 0, st>>>(f.perimg, sh->B, sh->H, sh->W, sh->S, p.smooth_w, loss_per_scale, loss_total);
+  f.loss_per_scale = loss_per_scale; f.loss_total = loss_total;
+  f.gather_blocks = 0;
+  if (want_grad && w.cstride > 0) {
+    size_t ntot = 0;
+    for (int s = 0; s < sh->S; ++s)
+      if (w.cbw[s]) ntot += (size_t)sh->B * sh->dh[s] * sh->dw[s];
+    size_t gb = (ntot + 255) / 256;
+    f.gather_blocks = (int)(gb > 148 * 16 ? 148 * 16 : gb);
+  }
+  postpass_kernel<<<sh->B * sh->S + f.gather_blocks, 256, 0, st>>>(p, f, pose);
   DVS_CUDA_TRY(cudaGetLastError());
   return DVS_OK;
 }
 
 static int run_backward(const DvsShape* sh, const float* g, const float* const* u, const float* uT, const float* coup,
-                        float* const* grad_disp, float* const* grad_T, cudaStream_t st, int out_bf16 = 0) {
+                        float* const* grad_disp, float* const* grad_T, cudaStream_t st, int out_bf16 = 0,
+                        float* const* grad_aa = nullptr, float* const* grad_tr = nullptr) {
   BackwardParams q{};
   q.out_bf16 = out_bf16;
+  q.pose = grad_aa != nullptr;
   q.B = sh->B; q.H = sh->H; q.W = sh->W; q.N = sh->N; q.S = sh->S;
   q.g = g; q.uT = uT; q.coup = coup;
   for (int s = 0; s < sh->S; ++s) {
@@ -490,8 +553,13 @@ static int run_backward(const DvsShape* sh, const float* g, const float* const* 
     q.dh[s] = sh->dh[s]; q.dw[s] = sh->dw[s]; q.u[s] = u[s]; q.out[s] = grad_disp[s];
   }
   for (int i = 0; i < sh->N; ++i) {
-    if (!grad_T[i]) return DVS_EINVAL;
-    q.gT[i] = grad_T[i];
+    if (q.pose) {
+      if (!grad_aa[i] || !grad_tr || !grad_tr[i]) return DVS_EINVAL;
+      q.gaa[i] = grad_aa[i]; q.gtr[i] = grad_tr[i];
+    } else {
+      if (!grad_T || !grad_T[i]) return DVS_EINVAL;
+      q.gT[i] = grad_T[i];
+    }
   }
   size_t n0 = (size_t)sh->B * sh->dh[0] * sh->dw[0];
   int gx = (int)((n0 + 256 * 8 - 1) / (256 * 8));
@@ -583,6 +651,48 @@ extern "C" int dvs_photometric_backward_ex(const DvsShape* shape, const float* g
   return run_backward(shape, grad_per_scale, ugrad_disp, ugrad_T, ugrad_T + ut_floats(shape),
                       reinterpret_cast<float* const*>(grad_disp), grad_T, static_cast<cudaStream_t>(stream),
                       grad_dtype == DVS_DTYPE_BF16 ? 1 : 0);
+}
+
+// ugrad_pose buffer = [S,N,B,6] unit gradients w.r.t. (axis-angle, translation) followed by [S,B] coupling coefficients
+static size_t up_floats(const DvsShape* sh) { return (size_t)sh->S * sh->N * sh->B * 6; }
+
+extern "C" int dvs_photometric_forward_pose(const DvsShape* shape, const DvsParams* params, const void* const* disp,
+                                            int disp_dtype, const void* target, const void* const* src, int image_dtype,
+                                            const float* K, const float* inv_K, const float* const* axisangle,
+                                            const float* const* translation, const int32_t* invert,
+                                            const float* const* noise, uint64_t seed, uint64_t offset,
+                                            const uint64_t* offset_dev, float* loss_per_scale, float* loss_total,
+                                            uint8_t* const* sel, float* const* ugrad_disp, float* ugrad_pose,
+                                            void* workspace, void* stream) {
+  if ((ugrad_disp == nullptr) != (ugrad_pose == nullptr)) return DVS_EINVAL;
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  if (!axisangle || !translation || !invert) return DVS_EINVAL;
+  int io = 0;
+  rc = dtype_flags(disp_dtype, image_dtype, &io);
+  if (rc) return rc;
+  PoseIO pose{};
+  for (int i = 0; i < shape->N; ++i) { pose.aa[i] = axisangle[i]; pose.tr[i] = translation[i]; pose.invert[i] = invert[i] ? 1 : 0; }
+  pose.uP = ugrad_pose;
+  float* coup = ugrad_pose ? ugrad_pose + up_floats(shape) : nullptr;
+  // the 4x4 unit gradients are not kept in this mode (uT == nullptr); want_grad is signalled by ugrad_disp
+  return run_forward(shape, params, reinterpret_cast<const float* const*>(disp), static_cast<const float*>(target),
+                     reinterpret_cast<const float* const*>(src), K, inv_K, nullptr, noise, seed, offset, loss_per_scale,
+                     loss_total, sel, ugrad_disp, nullptr, coup, workspace, static_cast<cudaStream_t>(stream), io, &pose,
+                     reinterpret_cast<const unsigned long long*>(offset_dev));
+}
+
+extern "C" int dvs_photometric_backward_pose(const DvsShape* shape, const float* grad_per_scale,
+                                             const float* const* ugrad_disp, const float* ugrad_pose,
+                                             void* const* grad_disp, int grad_dtype, float* const* grad_axisangle,
+                                             float* const* grad_translation, void* stream) {
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  if (!grad_per_scale || !ugrad_disp || !ugrad_pose || !grad_disp || !grad_axisangle || !grad_translation) return DVS_EINVAL;
+  if (grad_dtype != DVS_DTYPE_F32 && grad_dtype != DVS_DTYPE_BF16) return DVS_EINVAL;
+  return run_backward(shape, grad_per_scale, ugrad_disp, ugrad_pose, ugrad_pose + up_floats(shape),
+                      reinterpret_cast<float* const*>(grad_disp), nullptr, static_cast<cudaStream_t>(stream),
+                      grad_dtype == DVS_DTYPE_BF16 ? 1 : 0, grad_axisangle, grad_translation);
 }
 
 extern "C" int dvs_photometric_backward(const DvsShape* shape, const float* grad_per_scale,

@@ -68,6 +68,7 @@ struct FusedParams {
   const float* T[kMaxN];
   const float* noise[kMaxS];       // null -> hash generator
   unsigned long long seed, offset;
+  const unsigned long long* offset_dev;   // optional device counter added to `offset` (advances under CUDA-graph replay)
   float min_disp, disp_range;      // scaled = min_disp + disp_range*disp
   float ssim_w, l1_w, smooth_w, eps;
   int auto_mask;
@@ -96,6 +97,8 @@ struct FusedParams {
 // Upper bound of the coarse rows (columns) touched by the 30 fine rows (columns) of one tile: the clamped source
 // coordinate spans 29 * in/out, plus the two taps.
 DVS_HD int coarse_box_extent(int in, int out) { int e = (29 * in) / out + 3; return e < in ? e : in; }
+
+DVS_HD unsigned long long noise_offset(const FusedParams& p) { return p.offset + (p.offset_dev ? *p.offset_dev : 0ull); }
 
 // per-block partial sums: [0] photometric, [1] smooth-x, [2] smooth-y, then per source 12 pose moments
 //   M[r*4 + 0..2] = sum g_c[r] * D * (u, v, 1),  M[r*4 + 3] = sum g_c[r]      (r = row of the 3x4 projection)
@@ -751,7 +754,7 @@ DVS_HD void phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid,
             n0 = p.noise[s][((size_t)(t.b * NS + i) * p.H + gy) * p.W + gx];
             if (i + 1 < NS) n1 = p.noise[s][((size_t)(t.b * NS + i + 1) * p.H + gy) * p.W + gx];
           } else {
-            hash_normal2(p.seed, p.offset, (unsigned)((t.b * p.H + gy) * p.W + gx), (unsigned)(s * kMaxN + i), n0, n1);
+            hash_normal2(p.seed, noise_offset(p), (unsigned)((t.b * p.H + gy) * p.W + gx), (unsigned)(s * kMaxN + i), n0, n1);
           }
         }
         float v0 = fmaf(n0, 0.00001f, st.ident[i][j]);

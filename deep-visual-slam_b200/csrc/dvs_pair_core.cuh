@@ -435,7 +435,7 @@ DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int
             n0 = p.noise[s][((size_t)(t.b * 2) * p.H + gy) * p.W + gx];
             n1 = p.noise[s][((size_t)(t.b * 2 + 1) * p.H + gy) * p.W + gx];
           } else {
-            hash_normal2(p.seed, p.offset, (unsigned)((t.b * p.H + gy) * p.W + gx), (unsigned)(s * kMaxN), n0, n1);
+            hash_normal2(p.seed, noise_offset(p), (unsigned)((t.b * p.H + gy) * p.W + gx), (unsigned)(s * kMaxN), n0, n1);
           }
         }
         const float v0 = fmaf(n0, 0.00001f, id0);

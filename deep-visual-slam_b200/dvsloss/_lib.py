@@ -55,6 +55,10 @@ _SIGNATURES = {
     "dvs_photometric_backward": [C.POINTER(DvsShape), _vp, _FPP, _vp, _FPP, _FPP, _vp],
     "dvs_photometric_forward_ex": [C.POINTER(DvsShape), C.POINTER(DvsParams), _FPP, C.c_int, _vp, _FPP, C.c_int, _vp, _vp, _FPP,
                                    _FPP, C.c_uint64, C.c_uint64, _vp, _vp, _U8PP, _FPP, _vp, _vp, _vp],
+    "dvs_photometric_forward_pose": [C.POINTER(DvsShape), C.POINTER(DvsParams), _FPP, C.c_int, _vp, _FPP, C.c_int, _vp, _vp,
+                                     _FPP, _FPP, C.POINTER(C.c_int32), _FPP, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _U8PP,
+                                     _FPP, _vp, _vp, _vp],
+    "dvs_photometric_backward_pose": [C.POINTER(DvsShape), _vp, _FPP, _vp, _FPP, C.c_int, _FPP, _FPP, _vp],
     "dvs_photometric_backward_ex": [C.POINTER(DvsShape), _vp, _FPP, _vp, _FPP, C.c_int, _FPP, _vp],
     "dvs_photometric_backward_recompute": [C.POINTER(DvsShape), C.POINTER(DvsParams), _FPP, _vp, _FPP, _vp, _vp, _FPP,
                                            _FPP, C.c_uint64, C.c_uint64, _vp, _FPP, _FPP, _vp, _vp],

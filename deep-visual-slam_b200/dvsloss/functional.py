@@ -54,7 +54,9 @@ class _ViewSynthesisLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg: dict, target, sources, K, inv_K, noise, S: int, N: int, *diff):
         disps, disp_dtype = _prep_disps(diff[:S], N)
-        Ts = [_prep(t) for t in diff[S:S + N]]
+        pose_mode = cfg["pose_mode"]                  # diff = disps + Ts   or   disps + axisangles + translations
+        Ts = [_prep(t) for t in diff[S:]]
+        ctx.pose_shapes = [tuple(t.shape) for t in diff[S:]]
         K, inv_K = _prep(K), _prep(inv_K)
         target, sources, image_dtype = _prep_images(target, sources, N)
         require_cuda(target, K, inv_K, *disps, *Ts, *sources)
@@ -68,9 +70,13 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         for s_ in sources:
             if s_.shape != target.shape:
                 raise _lib.DvsError("source images must have the target's shape")
-        for t in Ts + [K, inv_K]:
+        for t in ([] if pose_mode else Ts) + [K, inv_K]:
             if tuple(t.shape) != (B, 4, 4):
                 raise _lib.DvsError("K, inv_K and T must be [B,4,4]")
+        if pose_mode:
+            Ts = [t.reshape(B, 3) for t in Ts]
+            if len(Ts) != 2 * N:
+                raise _lib.DvsError("need one axis-angle and one translation per source frame")
         shape = make_shape(B, H, W, N, [d.shape[2:] for d in disps])
         params = DvsParams(cfg["min_depth"], cfg["max_depth"], cfg["ssim_ratio"], cfg["smoothness_ratio"], 1e-7,
                            int(bool(cfg["auto_mask"])))
@@ -80,7 +86,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=dev)
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
 
-        want_grad = any(ctx.needs_input_grad[8:8 + S + N])
+        want_grad = any(ctx.needs_input_grad[8:])
         per_scale = torch.empty(S, dtype=torch.float32, device=dev)
         total = torch.empty(1, dtype=torch.float32, device=dev)
         sel = None
@@ -89,7 +95,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         ugrad = uT = None
         if want_grad:
             ugrad = [torch.empty(d.shape, dtype=torch.float32, device=dev) for d in disps]
-            uT = torch.empty(S * N * B * 16 + S * B, dtype=torch.float32, device=dev)
+            uT = torch.empty(S * N * B * (6 if pose_mode else 16) + S * B, dtype=torch.float32, device=dev)
         noise_arr = None
         if noise is not None:
             noise = [_prep(n) for n in noise]
@@ -99,12 +105,26 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             require_cuda(*noise)
             noise_arr = fptr_array(noise)
         with torch.cuda.device(dev):
-            rc = L.dvs_photometric_forward_ex(
-                C.byref(shape), C.byref(params), fptr_array(disps), disp_dtype, ptr(target), fptr_array(sources), image_dtype,
-                ptr(K), ptr(inv_K), fptr_array(Ts), noise_arr, C.c_uint64(cfg["seed"]), C.c_uint64(cfg["offset"]),
-                ptr(per_scale), ptr(total), u8ptr_array(sel) if sel is not None else None,
-                fptr_array(ugrad) if want_grad else None, ptr(uT), ws_ptr, stream_ptr(dev))
-        check(rc, "dvs_photometric_forward_ex")
+            if pose_mode:
+                ctr = None
+                if noise is None and cfg["auto_mask"]:
+                    ctr = _device_counter(dev)
+                    ctr.add_(1)                      # on the stream: captured graphs advance it on every replay
+                inv = (C.c_int32 * N)(*[int(bool(v)) for v in cfg["invert"]])
+                rc = L.dvs_photometric_forward_pose(
+                    C.byref(shape), C.byref(params), fptr_array(disps), disp_dtype, ptr(target), fptr_array(sources),
+                    image_dtype, ptr(K), ptr(inv_K), fptr_array(Ts[:N]), fptr_array(Ts[N:]), inv, noise_arr,
+                    C.c_uint64(cfg["seed"]), C.c_uint64(0 if ctr is not None else cfg["offset"]), ptr(ctr), ptr(per_scale), ptr(total),
+                    u8ptr_array(sel) if sel is not None else None, fptr_array(ugrad) if want_grad else None, ptr(uT), ws_ptr,
+                    stream_ptr(dev))
+            else:
+                rc = L.dvs_photometric_forward_ex(
+                    C.byref(shape), C.byref(params), fptr_array(disps), disp_dtype, ptr(target), fptr_array(sources), image_dtype,
+                    ptr(K), ptr(inv_K), fptr_array(Ts), noise_arr, C.c_uint64(cfg["seed"]), C.c_uint64(cfg["offset"]),
+                    ptr(per_scale), ptr(total), u8ptr_array(sel) if sel is not None else None,
+                    fptr_array(ugrad) if want_grad else None, ptr(uT), ws_ptr, stream_ptr(dev))
+        check(rc, "dvs_photometric_forward")
+        ctx.pose_mode = pose_mode
         ctx.shape, ctx.S, ctx.N, ctx.B = shape, S, N, B
         ctx.disp_dtype = disp_dtype
         ctx.ugrad, ctx.uT = ugrad, uT
@@ -130,6 +150,14 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         g = g.contiguous()
         gdt = torch.bfloat16 if ctx.disp_dtype == _lib.DTYPE_BF16 else torch.float32
         grad_disp = [torch.empty(u.shape, dtype=gdt, device=dev) for u in ctx.ugrad]
+        if ctx.pose_mode:
+            gp = [torch.empty(B, 3, dtype=torch.float32, device=dev) for _ in range(2 * N)]
+            with torch.cuda.device(dev):
+                rc = lib().dvs_photometric_backward_pose(C.byref(ctx.shape), ptr(g), fptr_array(ctx.ugrad), ptr(ctx.uT),
+                                                         fptr_array(grad_disp), ctx.disp_dtype, fptr_array(gp[:N]),
+                                                         fptr_array(gp[N:]), stream_ptr(dev))
+            check(rc, "dvs_photometric_backward_pose")
+            return (None,) * 8 + tuple(grad_disp) + tuple(t.view(sh) for t, sh in zip(gp, ctx.pose_shapes))
         grad_T = [torch.empty(B, 4, 4, dtype=torch.float32, device=dev) for _ in range(N)]
         with torch.cuda.device(dev):
             rc = lib().dvs_photometric_backward_ex(C.byref(ctx.shape), ptr(g), fptr_array(ctx.ugrad), ptr(ctx.uT),
@@ -138,18 +166,57 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         return (None,) * 8 + tuple(grad_disp) + tuple(grad_T)
 
 
+_counters = {}
+
+
+def _device_counter(dev) -> torch.Tensor:
+    """Per-device int64 step counter of the in-kernel noise generator (checkpoint it with ``noise_state`` / ``set_noise_state``)."""
+    key = torch.device(dev).index or 0
+    if key not in _counters:
+        _counters[key] = torch.zeros(1, dtype=torch.int64, device=dev)
+    return _counters[key]
+
+
+def noise_state(device=None) -> int:
+    """Number of in-kernel noise draws made so far on ``device`` (pose-parameter calls); restore with ``set_noise_state``."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return int(_device_counter(dev).item())
+
+
+def set_noise_state(value: int, device=None) -> None:
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    _device_counter(dev).fill_(int(value))
+
+
+def _default_seed(dev) -> int:
+    """torch's seed mixed with the process rank and the device, so data-parallel ranks seeded alike draw different noise."""
+    rank = 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank = dist.get_rank()
+    except Exception:
+        rank = 0
+    return (torch.initial_seed() ^ ((rank + 1) * 0x9E3779B97F4A7C15) ^ ((torch.device(dev).index or 0) << 48)) & (2 ** 64 - 1)
+
+
 def view_synthesis_loss(disps: Sequence[torch.Tensor], target: torch.Tensor, sources: Sequence[torch.Tensor],
-                        K: torch.Tensor, inv_K: torch.Tensor, Ts: Sequence[torch.Tensor], *,
+                        K: torch.Tensor, inv_K: torch.Tensor, Ts: Optional[Sequence[torch.Tensor]] = None, *,
                         noise: NoiseArg = "kernel", min_depth: float = 0.1, max_depth: float = 10.0,
                         ssim_ratio: float = 0.85, smoothness_ratio: float = 1e-3, auto_mask: bool = True,
-                        return_selection: bool = False, seed: Optional[int] = None
-                        ) -> Tuple[torch.Tensor, ...]:
+                        return_selection: bool = False, seed: Optional[int] = None,
+                        axisangles: Optional[Sequence[torch.Tensor]] = None,
+                        translations: Optional[Sequence[torch.Tensor]] = None,
+                        inverts: Optional[Sequence[bool]] = None) -> Tuple[torch.Tensor, ...]:
     """Fused Monodepth2 view-synthesis loss over S=len(disps) scales and N=len(sources) source frames.
 
     disps[s] [B,1,h_s,w_s] sigmoid disparities (outputs[("disp", s)]; fp32, or bf16 as emitted under autocast -- read directly
     by the two-source kernel, gradients returned as bf16), target/sources [B,3,H,W] in [0,1] (fp32, or uint8 frames: x/255
     is formed inside the kernel),
-    K/inv_K [B,4,4] scale-0 intrinsics, Ts[i] [B,4,4] cam_T_cam of source i.
+    K/inv_K [B,4,4] scale-0 intrinsics, Ts[i] [B,4,4] cam_T_cam of source i -- or, instead of ``Ts``, the pose parameters
+    themselves: ``axisangles[i]``, ``translations[i]`` ([B,3], [B,1,3] or [B,1,1,3], what PoseNet returns) and ``inverts[i]``
+    (vo/learner_new.py:124-127: True for frames before the target).  Then transformation_from_parameters and its backward run
+    inside the loss's own launches and the gradients arrive at the pose parameters directly.
 
     noise: "kernel" -> automask tie-break noise from an in-kernel counter-based generator (fast);
            "torch"  -> ``torch.randn([B,N,H,W])`` per scale, i.e. exactly the draws (shape, order, device)
@@ -159,8 +226,15 @@ def view_synthesis_loss(disps: Sequence[torch.Tensor], target: torch.Tensor, sou
     channel over [identity_0..N-1, reproj_0..N-1] (``identity_selection/s`` of the reference is ``sel >= N``).
     """
     S, N = len(disps), len(sources)
-    if len(Ts) != N:
-        raise _lib.DvsError("need one pose per source frame")
+    pose_mode = Ts is None
+    if pose_mode:
+        if axisangles is None or translations is None or inverts is None or not (len(axisangles) == len(translations) == len(inverts) == N):
+            raise _lib.DvsError("give either Ts or axisangles + translations + inverts, one per source frame")
+        pose_args = list(axisangles) + list(translations)
+    else:
+        if len(Ts) != N:
+            raise _lib.DvsError("need one pose per source frame")
+        pose_args = list(Ts)
     B, _, H, W = target.shape
     noise_t = None
     if auto_mask:
@@ -178,6 +252,6 @@ def view_synthesis_loss(disps: Sequence[torch.Tensor], target: torch.Tensor, sou
     cfg = dict(min_depth=float(min_depth), max_depth=float(max_depth), ssim_ratio=float(ssim_ratio),
                smoothness_ratio=float(smoothness_ratio), auto_mask=bool(auto_mask),
                return_selection=bool(return_selection),
-               seed=int(torch.initial_seed() if seed is None else seed) & (2 ** 64 - 1),
-               offset=next(_offset_counter))
-    return _ViewSynthesisLoss.apply(cfg, target, list(sources), K, inv_K, noise_t, S, N, *disps, *Ts)
+               seed=int(_default_seed(target.device) if seed is None else seed) & (2 ** 64 - 1),
+               offset=next(_offset_counter), pose_mode=pose_mode, invert=list(inverts) if pose_mode else None)
+    return _ViewSynthesisLoss.apply(cfg, target, list(sources), K, inv_K, noise_t, S, N, *disps, *pose_args)

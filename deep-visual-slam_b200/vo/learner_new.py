@@ -40,25 +40,29 @@ from model.layers import BackprojectDepth, Project3D, SSIM  # noqa: E402
 
 class LazyOutputs(dict):
     """``outputs`` of ``process_batch``.  A plain dict for everything the step computed; the full-resolution side
-    products of vo/learner_new.py:142,146,158,165-172 are produced on first access (``d[key]``, ``d.get(key)``,
-    ``key in d``) by the bound filler and then stay in the dict like any other entry."""
+    products of vo/learner_new.py:142,146,158,165-172 (and the 4x4 pose matrices, :124-127) are produced on first access
+    (``d[key]``, ``d.get(key)``, ``key in d``) by the filler bound to the key's kind and then stay in the dict like any
+    other entry.  Each filler runs at most once."""
 
-    LAZY_KINDS = ("disp_up", "depth", "sample", "color", "color_identity")
+    LAZY_KINDS = ("disp_up", "depth", "sample", "color", "color_identity", "cam_T_cam")
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        self._filler = None
+        self._fillers = {}
 
-    def bind(self, filler) -> "LazyOutputs":
-        self._filler = filler
+    def bind(self, filler, kinds=None) -> "LazyOutputs":
+        for k in (self.LAZY_KINDS if kinds is None else kinds):
+            self._fillers[k] = filler
         return self
 
     def _is_lazy(self, key) -> bool:
-        return self._filler is not None and isinstance(key, tuple) and len(key) > 1 and key[0] in self.LAZY_KINDS
+        return isinstance(key, tuple) and len(key) > 1 and key[0] in self._fillers
 
     def __missing__(self, key):
         if self._is_lazy(key):
-            filler, self._filler = self._filler, None
+            filler = self._fillers[key[0]]
+            for k in [k for k, f in self._fillers.items() if f is filler]:
+                del self._fillers[k]
             filler(self)
             if dict.__contains__(self, key):
                 return dict.__getitem__(self, key)
@@ -125,16 +129,21 @@ class MonodepthTrainer:
             if isinstance(val, torch.Tensor):
                 sample[key] = val.to(self.device, non_blocking=True)
         outputs = LazyOutputs(self.depth_net(sample[("target_image", 0)]))
-        outputs.update(self._predict_poses(sample))
         if self.fused:
+            # pose parameters go to the loss as they are: transformation_from_parameters and its backward run inside the
+            # loss's launches; ("cam_T_cam", 0, f) joins the lazily materialised outputs
+            outputs.update(self._predict_poses(sample, matrices=False))
             losses = self._view_synthesis(sample, outputs)
-            outputs.bind(lambda out: self.materialize_outputs(sample, out))
+            outputs.bind(lambda out: self.materialize_outputs(sample, out),
+                         ("disp_up", "depth", "sample", "color", "color_identity"))
+            outputs.bind(self._materialize_poses, ("cam_T_cam",))
         else:
+            outputs.update(self._predict_poses(sample))
             self._generate_images_pred(sample, outputs)
             losses = self._compute_losses(sample, outputs)
         return outputs, losses
 
-    def _predict_poses(self, sample: Dict) -> Dict:
+    def _predict_poses(self, sample: Dict, matrices: bool = True) -> Dict:
         """PoseNet on (source, target) ordered in time; negative frame ids are inverted (Monodepth2 convention,
         reference: vo/learner_new.py:107-129)."""
         out = {}
@@ -145,16 +154,19 @@ class MonodepthTrainer:
             axisangle, translation = self.pose_net(pair)
             out[("axisangle", 0, f)] = axisangle
             out[("translation", 0, f)] = translation
-            out[("cam_T_cam", 0, f)] = _ops.transformation_from_parameters(axisangle[:, 0], translation[:, 0],
-                                                                           invert=(f < 0))
+            if matrices:
+                out[("cam_T_cam", 0, f)] = _ops.transformation_from_parameters(axisangle[:, 0], translation[:, 0],
+                                                                               invert=(f < 0))
         return out
 
     def _view_synthesis(self, sample: Dict, outputs: Dict) -> Dict:
         disps = [outputs[("disp", s)] for s in range(self.num_scales)]
-        Ts = [outputs[("cam_T_cam", 0, f)] for f in self.frame_ids]
         sources = [sample[self._source_key(f)] for f in self.frame_ids]
         res = view_synthesis_loss(disps, sample[("target_image", 0)], sources, sample[("K", 0)], sample[("inv_K", 0)],
-                                  Ts, noise=self.noise, min_depth=self.min_depth, max_depth=self.max_depth,
+                                  axisangles=[dict.__getitem__(outputs, ("axisangle", 0, f)) for f in self.frame_ids],
+                                  translations=[dict.__getitem__(outputs, ("translation", 0, f)) for f in self.frame_ids],
+                                  inverts=[f < 0 for f in self.frame_ids],
+                                  noise=self.noise, min_depth=self.min_depth, max_depth=self.max_depth,
                                   ssim_ratio=self.ssim_ratio, smoothness_ratio=self.smoothness_ratio,
                                   auto_mask=self.auto_mask, return_selection=bool(self.auto_mask))
         total, per_scale = res[0], res[1]
@@ -213,8 +225,18 @@ class MonodepthTrainer:
         return losses
 
     @torch.no_grad()
+    def _materialize_poses(self, outputs: Dict) -> None:
+        for f in self.frame_ids:
+            if not dict.__contains__(outputs, ("cam_T_cam", 0, f)):
+                aa, tr = dict.__getitem__(outputs, ("axisangle", 0, f)), dict.__getitem__(outputs, ("translation", 0, f))
+                dict.__setitem__(outputs, ("cam_T_cam", 0, f),
+                                 _ops.transformation_from_parameters(aa.detach().float()[:, 0], tr.detach().float()[:, 0],
+                                                                     invert=(f < 0)))
+
+    @torch.no_grad()
     def materialize_outputs(self, sample: Dict, outputs: Dict) -> Dict:
         """Fill the full-resolution side products the plotting code reads (("depth", s), ("color", f, s), ...)."""
+        self._materialize_poses(outputs)
         det = {k: (v.detach().float() if isinstance(v, torch.Tensor) else v) for k, v in dict.items(outputs)}
         self._generate_images_pred(sample, det)
         for k, v in det.items():

@@ -121,7 +121,10 @@ class Trainer:
         self.depth_net, self.pose_net = depth_net, pose_net
         params = [q for q in list(depth_net.parameters()) + list(pose_net.parameters()) if q.requires_grad]
         # fused=True: one multi-tensor kernel for the whole Adam update instead of ~10 launches per parameter group
-        self.optimizer = optim.Adam(params, lr=tr["init_lr"], fused=self.device.type == "cuda")
+        # capturable: the step counter lives on the device, so the update can sit inside a captured CUDA graph
+        self.optimizer = optim.Adam(params, lr=tr["init_lr"], fused=self.device.type == "cuda",
+                                    capturable=self.device.type == "cuda")
+        self._graph = None
         self.scheduler = PolynomialLR(self.optimizer, total_iters=tr["epoch"], power=0.9)
         self.frame_ids = list(frame_ids)
         self.joint = JointForward(module, self.frame_ids)
@@ -147,6 +150,45 @@ class Trainer:
         for k in losses:
             losses[k] = losses[k].detach().cpu() if self.sync_losses else losses[k].detach()
         return total, outputs, losses
+
+    # ------------------------------------------------------------------------------------------ whole-step CUDA graph
+    def capture_step(self, sample: Dict, warmup: int = 3) -> None:
+        """Capture zero_grad -> networks -> fused loss -> backward -> Adam as ONE CUDA graph.  The reference
+        launches ~1 150 loss kernels per step and copies five scalars to the host after every step (vo/train.py:196-197, :253),
+        which serialises host and device; here a step is a host-side copy of the batch into static buffers plus one
+        ``graph.replay()`` and the losses stay on the device.  The in-kernel automask noise keeps advancing under replay (its
+        step counter is a device scalar incremented inside the graph).  Single-process only (DDP's bucketing hooks are not
+        captured); shapes are frozen to those of ``sample``."""
+        if self.device.type != "cuda":
+            raise RuntimeError("capture_step needs a CUDA device")
+        if self.module is not self.nets:
+            raise RuntimeError("capture_step does not support DistributedDataParallel")
+        self._static = {k: (v.to(self.device).clone() if isinstance(v, torch.Tensor) else v) for k, v in sample.items()}
+        sync, self.sync_losses = self.sync_losses, False
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.train_mono_step(dict(self._static))
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.optimizer.zero_grad(set_to_none=True)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            total, outputs, losses = self.train_mono_step(dict(self._static))
+        self._graph_out = (total, {k: v for k, v in dict.items(outputs) if isinstance(v, torch.Tensor)}, losses)
+        self.sync_losses = sync
+
+    def train_graph_step(self, sample: Dict) -> Tuple[torch.Tensor, Dict, Dict]:
+        """One optimisation step by replaying the captured graph on ``sample`` (same shapes as at capture).  Returns the
+        static (device-resident) total loss, outputs and losses: read them before the next replay overwrites them."""
+        if self._graph is None:
+            raise RuntimeError("call capture_step(sample) first")
+        with torch.no_grad():
+            for k, v in sample.items():
+                if isinstance(v, torch.Tensor):
+                    self._static[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        return self._graph_out
 
     def _images(self, sample: Dict) -> Dict:
         if not self.channels_last:

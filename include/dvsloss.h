@@ -122,6 +122,29 @@ int dvs_photometric_backward_ex(const DvsShape* shape, const float* grad_per_sca
                                 const float* const* ugrad_disp, const float* ugrad_T,
                                 void* const* grad_disp, int grad_dtype, float* const* grad_T, void* stream);
 
+/* The same with the POSE PARAMETERS as inputs instead of matrices (no separate pose launches, nothing 4x4 crosses HBM):
+ * axisangle[i], translation[i] [B,3] and invert[i] (host ints) are what the reference feeds
+ * transformation_from_parameters (vo/learner_func.py:29-46; vo/learner_new.py:124-127: invert for the left frame); the
+ * pre-pass kernel builds T_i, the post-pass kernel chains d loss / d T_i back to the six numbers.
+ *   offset_dev   optional device counter added to `offset` for the in-kernel noise generator: a caller that increments
+ *                it on the stream gets fresh draws on every replay of a captured CUDA graph (NULL: `offset` alone).
+ *   ugrad_pose   [S,N,B,6] (d loss/s / d axisangle, d loss/s / d translation) followed by [S,B] floats of internal
+ *                coefficients; dvs_photometric_backward_pose combines it with the upstream gradients. */
+int dvs_photometric_forward_pose(const DvsShape* shape, const DvsParams* params,
+                                 const void* const* disp, int disp_dtype,
+                                 const void* target, const void* const* src, int image_dtype,
+                                 const float* K, const float* inv_K,
+                                 const float* const* axisangle, const float* const* translation, const int32_t* invert,
+                                 const float* const* noise, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                                 float* loss_per_scale, float* loss_total,
+                                 uint8_t* const* sel,
+                                 float* const* ugrad_disp, float* ugrad_pose,
+                                 void* workspace, void* stream);
+int dvs_photometric_backward_pose(const DvsShape* shape, const float* grad_per_scale,
+                                  const float* const* ugrad_disp, const float* ugrad_pose,
+                                  void* const* grad_disp, int grad_dtype,
+                                  float* const* grad_axisangle, float* const* grad_translation, void* stream);
+
 /* Backward of the above given what forward stored: for upstream gradients
  * grad_per_scale[s] = d objective / d loss/s (device, [S]; add grad_total/S to each if the total is used)
  *   grad_disp[s] = grad_per_scale[s] * ugrad_disp[s]            (in place allowed: grad_disp[s]==ugrad_disp[s])

@@ -73,7 +73,7 @@ def test_lazy_outputs_materialise_on_first_access_only():
             dict.__setitem__(out, ("depth", s), torch.full((1,), float(s)))
             dict.__setitem__(out, ("color", -1, s), torch.zeros(1))
 
-    out = LazyOutputs({("disp", 0): torch.ones(1)}).bind(fill)
+    out = LazyOutputs({("disp", 0): torch.ones(1)}).bind(fill, ("depth", "color"))
     out.update({("cam_T_cam", 0, 1): torch.eye(4)})
     assert ("disp", 0) in out and "loss" not in out and not calls          # ordinary keys never trigger the filler
     with pytest.raises(KeyError):
