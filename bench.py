@@ -18,6 +18,8 @@ for one batch.  Metric: warped pixels per second, B*S*N*H*W / t, whole job.  Pri
   cpu_baseline the oracle port (op-for-op restatement of the reference's PyTorch path) on the host cores, on a
                bounded sample (batch 2 of the same workload); rank 0, N=1 only
   eager_cuda_baseline   the same op sequence run eagerly on the GPU (the reference's own CUDA path), N=1 only
+  noise_torch  the same step with torch.randn noise tensors (the reference's RNG contract) instead of the in-kernel generator
+  train_step_r50x4   BASELINE configs[3]: ResNet-50, 1280x960, sources +-1 and +-2, batch 8/GPU (5 steps)
   train_step   BASELINE configs[2]: full VO training step (stock ResNet-18 DepthNet + PoseNet in bf16 autocast, fused
                fp32 loss, Adam, batch 32/GPU, DDP/NCCL when N>1) in triplets per second, whole job
   --impl reference   times that CPU path alone (all host threads), same metric/config
@@ -118,6 +120,25 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU (pinned staging buffers are then allocated
+    and filled on that NUMA node).  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"cpus {cpus[0]}-{cpus[-1]} ({len(cpus)}) local to GPU {index}"
+    except Exception as e:
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
+
+
 def make_inputs(B, seed, device):
     from dvsloss.synthetic import make_problem, pose_matrix
     p = make_problem(B, H, W, NSRC, NSCALE, seed=seed, consistent=True)
@@ -126,29 +147,97 @@ def make_inputs(B, seed, device):
     return host
 
 
-# ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_step(host, B_s):
-    """One fwd+bwd of the oracle port on the CPU for the first B_s items (checker code, timed as baseline)."""
-    from oracle import reference_port as port
-    sl = lambda t: t[:B_s].clone()
-    disps = [sl(d).requires_grad_(True) for d in host["disps"]]
-    Ts = [sl(T).requires_grad_(True) for T in host["Ts"]]
-    noise = [torch.randn(B_s, NSRC, H, W) for _ in range(NSCALE)]        # the reference draws it per scale
-    out = port.view_synthesis_loss(disps, sl(host["target"]), [sl(s) for s in host["sources"]], sl(host["K"]),
-                                   sl(host["inv_K"]), Ts, noise)
-    out["loss"].backward()
-    return float(out["loss"].detach())
+# ------------------------------------------------------------------------------------------------ reference arms
+class ReferenceLoss:
+    """The reference's own loss path on ``device``: the UNMODIFIED ``MonodepthTrainer._generate_images_pred`` +
+    ``_compute_losses`` + ``backward`` (vo/learner_new.py:132-258) from the staged copy ``baseline/_ref`` (kind "reference");
+    where that copy is absent, the op-for-op restatement ``oracle/reference_port.py`` (kind "port").  Inputs are resident
+    on ``device`` before the first step; a step draws the automask noise like the reference (torch.randn per scale)."""
+
+    def __init__(self, host, B_s, device):
+        from baseline import reference_loader as rl
+        self.dev = torch.device(device)
+        cut = lambda t: t[:B_s].to(self.dev).contiguous()
+        self.B = B_s
+        self.target, self.sources = cut(host["target"]), [cut(s) for s in host["sources"]]
+        self.K, self.inv_K = cut(host["K"]), cut(host["inv_K"])
+        self.disps = [cut(d).requires_grad_(True) for d in host["disps"]]
+        self.Ts = [cut(T).requires_grad_(True) for T in host["Ts"]]
+        self.kind = "reference" if rl.available() else "port"
+        if self.kind == "reference":
+            cfg = {"Train": dict(num_source=2, batch_size=B_s, img_h=H, img_w=W, smoothness_ratio=0.001, auto_mask=True,
+                                 ssim_ratio=0.85, min_depth=0.1, max_depth=10.0, use_compile=False)}
+            self.trainer = rl.load_learner().MonodepthTrainer(None, None, cfg, self.dev)
+            self.sample = {("K", 0): self.K, ("inv_K", 0): self.inv_K, ("target_image", 0): self.target,
+                           ("source_left", 0): self.sources[0], ("source_right", 0): self.sources[1]}
+
+    def step(self):
+        for t in self.disps + self.Ts:
+            t.grad = None
+        if self.kind == "reference":
+            outputs = {("disp", s): self.disps[s] for s in range(NSCALE)}
+            outputs[("cam_T_cam", 0, -1)], outputs[("cam_T_cam", 0, 1)] = self.Ts
+            self.trainer._generate_images_pred(self.sample, outputs)
+            loss = self.trainer._compute_losses(self.sample, outputs)["loss"]
+        else:
+            from oracle import reference_port as port
+            noise = [torch.randn(self.B, NSRC, H, W, device=self.dev) for _ in range(NSCALE)]
+            loss = port.view_synthesis_loss(self.disps, self.target, self.sources, self.K, self.inv_K, self.Ts, noise)["loss"]
+        loss.backward()
+        return loss
+
+    def what(self):
+        src = ("the unmodified MonodepthTrainer._generate_images_pred + _compute_losses + backward staged in baseline/_ref"
+               if self.kind == "reference" else "oracle/reference_port.py (op-for-op restatement of the reference's path)")
+        return f"{src}, fp32, batch {self.B}, inputs resident on {self.dev.type}"
 
 
 def time_cpu(host, B_s, steps, warmup):
     torch.set_num_threads(os.cpu_count() or 1)
+    ref = ReferenceLoss(host, B_s, "cpu")
     for _ in range(warmup):
-        cpu_port_step(host, B_s)
+        ref.step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_port_step(host, B_s)
+        ref.step()
     dt = (time.perf_counter() - t0) / steps
-    return B_s * NSCALE * NSRC * H * W / dt / 1e9, dt
+    return B_s * NSCALE * NSRC * H * W / dt / 1e9, dt, ref
+
+
+def time_cpu_train_step(B_s=2, steps=2, warmup=1):
+    """BASELINE configs[0]: one vo/train.py optimisation step on the CPU, fp32, batch 2, ResNet-18 DepthNet + PoseNet:
+    zero_grad -> process_batch -> backward -> Adam (vo/train.py:173-199) around the reference's MonodepthTrainer and
+    networks when staged (else this repository's stock-PyTorch networks with the restated loss)."""
+    from baseline import reference_loader as rl
+    from dvsloss.synthetic import make_problem
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    sample = make_problem(B_s, H, W, NSRC, NSCALE, seed=7, consistent=True)["sample"]
+    if rl.available():
+        DepthNet, PoseNet = rl.load_nets()
+        dn, pn = DepthNet(num_layers=18, pretrained=False), PoseNet(num_layers=18, pretrained=False, num_input_images=2)
+        cfg = {"Train": dict(num_source=2, batch_size=B_s, img_h=H, img_w=W, smoothness_ratio=0.001, auto_mask=True,
+                             ssim_ratio=0.85, min_depth=0.1, max_depth=10.0, use_compile=False)}
+        learner = rl.load_learner().MonodepthTrainer(dn, pn, cfg, torch.device("cpu"))
+        kind = "reference"
+    else:
+        return None
+    opt = torch.optim.Adam(list(dn.parameters()) + list(pn.parameters()), lr=1e-4)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        _, losses = learner.process_batch(dict(sample))
+        losses["loss"].backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"s_per_step": dt, "triplets_per_s": B_s / dt, "kind": kind, "batch": B_s,
+            "what": "BASELINE configs[0]: full VO training step (ResNet-18 DepthNet + 2x PoseNet + loss + Adam) on the host cores, fp32"}
 
 
 def run_reference(args):
@@ -157,48 +246,37 @@ def run_reference(args):
         return
     B_s = args.cpu_batch
     host = make_inputs(B_s, 0, "cpu")
-    val, dt = time_cpu(host, B_s, args.steps, args.warmup)
+    val, dt, ref = time_cpu(host, B_s, args.steps, args.warmup)
     cores = torch.get_num_threads()
-    sample = f"batch {B_s} of the {W}x{H}, {NSRC} sources, {NSCALE} scales workload per step, fp32, torch CPU ops"
+    sample = f"batch {B_s} of the {W}x{H}, {NSRC} sources, {NSCALE} scales workload per step: {ref.what()}"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_text(args.batch), "sample": f"bounded CPU sample: batch {B_s} per step"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ eager CUDA leg
-def time_eager_cuda(host, dev, steps=3, warmup=2):
-    """The reference's eager PyTorch op sequence (oracle port, op-for-op) on the SAME GPU: the denominator of
-    north_star's ">= 20x the reference's own eager CUDA-PyTorch loss throughput".  Checker code, timed as a
-    baseline only."""
-    from oracle import reference_port as port
+def time_eager_cuda(host, dev, steps=20, warmup=3):
+    """The reference's own eager CUDA-PyTorch loss (see ReferenceLoss) on the SAME GPU: the denominator of north_star's
+    ">= 20x the reference's own eager CUDA-PyTorch loss throughput".  Inputs resident, >= 3 warm-ups, >= 20 timed steps."""
     B = host["target"].shape[0]
-    tgt, srcs = host["target"].to(dev), [s.to(dev) for s in host["sources"]]
-    K, iK = host["K"].to(dev), host["inv_K"].to(dev)
-
-    def step():
-        disps = [d.to(dev).requires_grad_(True) for d in host["disps"]]
-        Ts = [T.to(dev).requires_grad_(True) for T in host["Ts"]]
-        noise = [torch.randn(B, NSRC, H, W, device=dev) for _ in range(NSCALE)]
-        out = port.view_synthesis_loss(disps, tgt, srcs, K, iK, Ts, noise)
-        out["loss"].backward()
-
+    ref = ReferenceLoss(host, B, dev)
     for _ in range(warmup):
-        step()
+        ref.step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        step()
+        ref.step()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"ms_per_step": ms, "value": B * NSCALE * NSRC * H * W / (ms * 1e-3) / 1e9, "unit": UNIT,
-            "what": f"oracle/reference_port.py (the reference's ATen op sequence) fwd+bwd on this GPU, fp32, batch {B}"}
+    return {"ms_per_step": ms, "value": B * NSCALE * NSRC * H * W / (ms * 1e-3) / 1e9, "unit": UNIT, "kind": ref.kind,
+            "steps": steps, "warmup": warmup, "what": ref.what()}
 
 
 # ------------------------------------------------------------------------------------------------ training-step leg
@@ -244,7 +322,8 @@ def run_train(args, world, rank, local, dev):
             "batch_per_gpu": Bt, "steps": args.train_steps, "warmup": 3, "final_loss": loss,
             "config": f"ResNet-{layers} DepthNet+PoseNet (stock PyTorch, bf16 autocast, channels_last), fused fp32 view-synthesis "
                       f"loss with {len(fids)} source frames, Adam, {Wt}x{Ht}, batch {Bt}/GPU, DDP over NCCL "
-                      f"(BASELINE configs[{3 if big else 2}]); synthetic frames resident in HBM"}
+                      f"(BASELINE configs[{3 if big else 2}]); synthetic frames resident in HBM; the only collective is DDP's "
+                      f"all-reduce of the network gradients ({'248' if big else '111'} MB fp32), overlapped with the convolution backward"}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -260,6 +339,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
@@ -310,6 +390,26 @@ def run_b200(args):
     pix_step = B * NSCALE * NSRC * H * W
     value = world * pix_step * args.steps / t_dev / 1e9
 
+    # ---- the reference's RNG contract: torch.randn([B,N,H,W]) per scale handed to the kernel (4 randn launches + 157 MB read)
+    def step_torch_noise():
+        for t in d_in["disps"] + d_in["Ts"]:
+            t.grad = None
+        loss, _ = view_synthesis_loss(d_in["disps"], d_in["target"], d_in["sources"], d_in["K"], d_in["inv_K"], d_in["Ts"],
+                                      noise="torch")
+        loss.backward()
+
+    for _ in range(3):
+        step_torch_noise()
+    torch.cuda.synchronize()
+    evn = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for e0, e1 in evn:
+        flush.zero_()
+        e0.record()
+        step_torch_noise()
+        e1.record()
+    torch.cuda.synchronize()
+    ms_torch_noise = sum(e0.elapsed_time(e1) for e0, e1 in evn) / len(evn)
+
     # ---- dominant kernel alone (events recorded by the library around its launch)
     L = lib()
     L.dvs_set_profiling(1)
@@ -351,6 +451,12 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * pix_step * args.steps / float(te.item()) / 1e9
+    h2d_rank_gbs = h2d * args.steps / t_e2e / 1e9                     # this rank's sustained H2D rate inside the pipeline
+    rates = [None] * world
+    if world > 1:
+        dist.all_gather_object(rates, round(h2d_rank_gbs, 2))
+    else:
+        rates = [round(h2d_rank_gbs, 2)]
 
     # ---- same, with the images crossing PCIe in dataset precision (uint8, expanded to x/255 on the device: SURVEY 8f rank 2)
     q8 = lambda t: (t * 255).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
@@ -373,6 +479,21 @@ def run_b200(args):
               "d2h_bytes_per_step": d2h, "note": "images quantised to 8 bits and sent as uint8 (the dataset's precision), expanded "
               "to float32 x/255 on the device; disparities, poses and gradients stay fp32; NOT the headline e2e"}
     del pipe8
+    pipe8k = HostLossPipeline(B, H, W, [tuple(d.shape[2:]) for d in h_in["disps"]], NSRC, chunks=args.e2e_chunks, device=dev,
+                              noise="kernel", uint8_images=True, u8_in_kernel=True)
+    for _ in range(3):
+        pipe8k.run(h_u8, h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pipe8k.run(h_u8, h_out)
+    barrier()
+    t8k = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t8k, op=dist.ReduceOp.MAX)
+    e2e_u8["in_kernel"] = {"value": world * pix_step * args.steps / float(t8k.item()) / 1e9, "unit": UNIT,
+                           "note": "same bytes, no expansion pass: the two-source kernel reads uint8 and forms x/255 in-register"}
+    del pipe8k
 
     eager = None
     if rank == 0 and world == 1 and not args.no_eager:
@@ -381,7 +502,7 @@ def run_b200(args):
         except Exception as e:                       # pragma: no cover - reported, never fatal for the headline number
             eager = {"error": repr(e)[:200]}
         torch.cuda.empty_cache()
-    train = None
+    train = train_big = None
     if not args.no_train:
         del pipe, h_out, flush
         torch.cuda.empty_cache()
@@ -389,6 +510,15 @@ def run_b200(args):
             train = run_train(args, world, rank, local, dev)
         except Exception as e:                       # pragma: no cover
             train = {"error": repr(e)[:300]}
+        train_big = None
+        if args.train_variant == "r18" and not args.no_train_big:
+            import copy as _copy
+            a2 = _copy.copy(args)
+            a2.train_variant, a2.train_batch, a2.train_steps = "r50x4", 0, 5
+            try:
+                train_big = run_train(a2, world, rank, local, dev)
+            except Exception as e:                   # pragma: no cover
+                train_big = {"error": repr(e)[:300]}
 
     if rank == 0:
         peak, how = measured_peak_gbs()
@@ -397,7 +527,7 @@ def run_b200(args):
         if t_kernel:
             ach = ba / t_kernel / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "kernel": "fused_tile_kernel<2,true>", "kernel_ms": t_kernel * 1e3, "bytes_alg": ba, "peak_source": how,
+                    "kernel": "fused_pair_kernel<true,0> (two-source tile kernel)", "kernel_ms": t_kernel * 1e3, "bytes_alg": ba, "peak_source": how,
                     "frac_step": ba / (t_dev / args.steps) / 1e9 / peak,
                     "frac_strict_floor": bytes_floor(B, H, W, NSRC, NSCALE) / t_kernel / 1e9 / peak}
             tr = os.path.join(ROOT, "profiles", "traffic.json")       # dram bytes per launch from the committed ncu capture
@@ -409,18 +539,27 @@ def run_b200(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             B_s = args.cpu_batch
-            val, dt = time_cpu(host, B_s, 2, 1)
-            cpu = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "s_per_step": dt,
-                   "sample": f"batch {B_s} of the same workload, 1 warm-up + 2 timed fwd+bwd of oracle/reference_port.py "
-                             f"(op-for-op the reference's eager PyTorch path) on CPU"}
+            val, dt, cref = time_cpu(host, B_s, 2, 1)
+            cpu = {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": cref.kind, "s_per_step": dt,
+                   "sample": f"batch {B_s} of the same workload, 1 warm-up + 2 timed fwd+bwd: {cref.what()}"}
+            try:
+                cpu["train_step_config0"] = time_cpu_train_step()
+            except Exception as e:               # pragma: no cover - reported, never fatal
+                cpu["train_step_config0"] = {"error": repr(e)[:200]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_text(B), "noise": "automask noise from the in-kernel generator",
                            "l2": "256 MB buffer written between timed steps (outside the event pairs)", "sharding": f"batch, {world} independent rank(s), no data-path collective"},
-                "clocks": clocks, "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": 5 * args.steps, "roofline": roof, "cpu_baseline": cpu, "eager_cuda_baseline": eager,
-                "train_step": train, "e2e_uint8_images": e2e_u8}
+                "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "h2d_gbs_per_rank": rates, "host_affinity": affinity,
+                        "note": "PCIe / host-DRAM bound: every rank streams 203 MB per step from pinned host memory"},
+                # kernels of this library inside one timed step: pre-pass, tile kernel, post-pass (forward) + gradient scaling
+                "gpu_launches": 4 * args.steps, "roofline": roof, "cpu_baseline": cpu, "eager_cuda_baseline": eager,
+                "train_step": train, "train_step_r50x4": train_big, "e2e_uint8_images": e2e_u8,
+                "noise_torch": {"ms_per_step": ms_torch_noise, "value": pix_step / (ms_torch_noise * 1e-3) / 1e9, "unit": UNIT,
+                                "note": "same step with the reference's RNG contract (torch.randn per scale handed to the kernel) instead of the in-kernel generator; this rank"}}
         if eager and "value" in eager:
             line["eager_cuda_baseline"]["speedup_device_timed"] = value / eager["value"]
         print(json.dumps(line), flush=True)
@@ -444,6 +583,7 @@ def main():
     ap.add_argument("--train-variant", default="r18", choices=["r18", "r50x4"],
                     help="r18 = BASELINE configs[2]; r50x4 = configs[3] (ResNet-50, 1280x960, sources +-1 and +-2)")
     ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--no-train-big", action="store_true", help="skip the BASELINE configs[3] training-step leg (r50x4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -55,41 +55,32 @@ __global__ void __launch_bounds__(256) mean_partial_kernel(FusedParams p, float*
   const int per = (n + kMeanBlocks - 1) / kMeanBlocks;
   const int lo = chunk * per, hi = min(lo + per, n);
   float acc = 0.f;
-  if (p.io_flags & 1) {
-    // bf16 disparities (two-source kernel only): widened on load; same summation weights
-    const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(p.disp[s]) + (size_t)b * n;
-    const float cw = exact ? (float)((p.H / h) * (p.W / w)) : 0.f;
-    for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
-      const float v = __bfloat162float(db[e]);
-      if (exact) acc += v;
-      else acc = fmaf(up_weight(e / w, h, p.H) * up_weight(e % w, w, p.W), v, acc);
-    }
-    if (exact) acc *= cw;
-  } else if (exact) {
-    // constant weight: plain sum, 128-bit loads where the chunk is aligned (independent accumulators keep several
-    // loads in flight per thread), scalar head/tail
+  const bool bf16 = (p.io_flags & 1) != 0;
+  const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(p.disp[s]) + (size_t)b * n;
+  auto at = [&](int e) -> float { return bf16 ? __bfloat162float(db[e]) : d[e]; };
+  if (exact) {
+    // constant weight: plain sum over groups of four consecutive elements with four independent accumulators (several
+    // loads in flight per thread), scalar head/tail.  The summation order is a function of the element indices only, so
+    // fp32 and bf16 maps of the same values give the same bits; fp32 maps use 128-bit loads when the image is aligned.
     const float cw = (float)((p.H / h) * (p.W / w));
-    int a0 = lo, a1 = hi;
-    if ((((uintptr_t)d) & 15) == 0) {
-      a0 = min((lo + 3) & ~3, hi);
-      a1 = max(a0, hi & ~3);
-      const float4* d4 = reinterpret_cast<const float4*>(d);
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      for (int e = a0 / 4 + threadIdx.x; e < a1 / 4; e += blockDim.x) {
-        float4 v = d4[e];
-        s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
-      }
-      acc = (s0 + s1) + (s2 + s3);
-      for (int e = lo + threadIdx.x; e < a0; e += blockDim.x) acc += d[e];
-      for (int e = a1 + threadIdx.x; e < hi; e += blockDim.x) acc += d[e];
-    } else {
-      for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) acc += d[e];
+    const int a0 = min((lo + 3) & ~3, hi), a1 = max(a0, hi & ~3);
+    const bool vec = !bf16 && (((uintptr_t)d) & 15) == 0;
+    const float4* d4 = reinterpret_cast<const float4*>(d);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int e = a0 / 4 + threadIdx.x; e < a1 / 4; e += blockDim.x) {
+      float4 v;
+      if (vec) v = d4[e];
+      else v = make_float4(at(4 * e), at(4 * e + 1), at(4 * e + 2), at(4 * e + 3));
+      s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
     }
+    acc = (s0 + s1) + (s2 + s3);
+    for (int e = lo + threadIdx.x; e < a0; e += blockDim.x) acc += at(e);
+    for (int e = a1 + threadIdx.x; e < hi; e += blockDim.x) acc += at(e);
     acc *= cw;
   } else {
     for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
       int i = e / w, j = e - i * w;
-      acc = fmaf(up_weight(i, h, p.H) * up_weight(j, w, p.W), d[e], acc);
+      acc = fmaf(up_weight(i, h, p.H) * up_weight(j, w, p.W), at(e), acc);
     }
   }
   __shared__ float red[8];
