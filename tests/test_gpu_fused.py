@@ -410,6 +410,9 @@ def test_fused_reads_bf16_disparities_and_uint8_images_in_kernel():
     p, cut, Ts = _problem_tensors(2, 96, 128, 41)
     q8 = lambda t: (t * 255).round().clamp(0, 255).to(torch.uint8)
     tgt8, src8 = cut(q8(p["target"])), [cut(q8(s)) for s in p["sources"]]
+    # ToTensor runs on the host in the reference (vo/dataset/common.py:77): a true IEEE division.  (torch's CUDA kernel for
+    # ``x.div(255)`` multiplies by the rounded reciprocal instead, which is off by one ulp for 126 of the 256 byte values.)
+    unit = lambda t8: cut(t8.cpu().float().div(255))
     dbf = [cut(d).to(torch.bfloat16) for d in p["disps"]]
     K, iK, noise = cut(p["K"]), cut(p["inv_K"]), [cut(n) for n in p["noise"]]
 
@@ -420,9 +423,9 @@ def test_fused_reads_bf16_disparities_and_uint8_images_in_kernel():
         out[0].backward()
         return out, [d.grad for d in disps], [t.grad for t in T]
 
-    ref, gd_ref, gT_ref = run([d.float() for d in dbf], tgt8.float().div(255), [s.float().div(255) for s in src8])
+    ref, gd_ref, gT_ref = run([d.float() for d in dbf], unit(tgt8), [unit(s) for s in src8])
     for disps, tgt, srcs, what in ((dbf, tgt8, src8, "bf16+u8"), ([d.float() for d in dbf], tgt8, src8, "u8"),
-                                   (dbf, tgt8.float().div(255), [s.float().div(255) for s in src8], "bf16")):
+                                   (dbf, unit(tgt8), [unit(s) for s in src8], "bf16")):
         got, gd, gT = run(disps, tgt, srcs)
         assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), what
         for a, b in zip(got[2:], ref[2:]):
@@ -448,8 +451,8 @@ def test_reduced_precision_inputs_with_other_source_counts_fall_back_to_expansio
     tgt8, src8 = cut(q8(p["target"])), [cut(q8(s)) for s in p["sources"]]
     disps = [cut(d) for d in p["disps"]]
     a = view_synthesis_loss(disps, tgt8, src8, cut(p["K"]), cut(p["inv_K"]), Ts, noise=None)
-    b = view_synthesis_loss(disps, tgt8.float().div(255), [s.float().div(255) for s in src8], cut(p["K"]), cut(p["inv_K"]), Ts,
-                            noise=None)
+    unit = lambda t8: cut(t8.cpu().float().div(255))        # host ToTensor: true division (see the test above)
+    b = view_synthesis_loss(disps, unit(tgt8), [unit(s) for s in src8], cut(p["K"]), cut(p["inv_K"]), Ts, noise=None)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     sh = _lib.make_shape(B, H, W, N, [tuple(d.shape[2:]) for d in disps])
     pr = _lib.DvsParams(0.1, 10.0, 0.85, 1e-3, 1e-7, 1)
