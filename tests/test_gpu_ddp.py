@@ -22,6 +22,13 @@ def _grads(tr):
     return torch.cat([p.grad.detach().flatten().float().cpu() for p in tr.nets.parameters() if p.requires_grad and p.grad is not None])
 
 
+def _exact_convs():
+    """TF32 convolutions (cuDNN's default) carry ~1e-3 of rounding that depends on the batch size: switch them off so that the
+    comparison tests the sharding, not the tensor-core rounding mode."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
 def _one_backward(tr, sample):
     """forward + backward of the training step without the optimizer update (so the gradients can be compared)."""
     tr.optimizer.zero_grad(set_to_none=True)
@@ -36,6 +43,7 @@ def _worker(rank, world, port, out_path, B, H, W):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
+    _exact_convs()
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     torch.manual_seed(0)
     tr = Trainer(_cfg(B // world, H, W), device=dev, distributed=True, noise=None, sync_losses=False, channels_last=False)
@@ -65,11 +73,14 @@ def test_two_rank_nccl_training_matches_single_rank_global_batch(tmp_path):
         assert p.exitcode == 0, "a rank failed"
     got = torch.load(out_path)
     dev = torch.device("cuda", 0)
+    tf32 = torch.backends.cudnn.allow_tf32
+    _exact_convs()
     torch.manual_seed(0)
     tr = Trainer(_cfg(B, H, W), device=dev, distributed=False, noise=None, sync_losses=False, channels_last=False)
     tr.nets.eval()
     loss = _one_backward(tr, synthetic_sample(B, H, W, seed=9, device=dev))
     ref = _grads(tr)
+    torch.backends.cudnn.allow_tf32 = tf32
     # the loss of a rank is the mean over its shard; DDP averages the gradients: together the global-batch mean
     assert got["grads"].shape == ref.shape
     scale = float(ref.abs().max())
