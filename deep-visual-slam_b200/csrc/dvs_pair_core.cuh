@@ -351,8 +351,8 @@ DVS_HD void lerp_store2(float* sm, int x2off, int k, f2 tx, f2 ty, const f2 (*ta
 
 // ------------------------------------------------------------------------------------------------ phase W
 // warp both sources onto R2 for scale s (interleaved float2 planes); store the up-sampled disparity.
-// Two pixels per iteration: their eight disparity taps are fetched together, then the 48 image taps of both are in flight
-// before the first interpolation (the phase is bound by the latency of the gather, not by its bandwidth).
+// One pixel per iteration: all 24 image taps are issued before the first interpolation, and the disparity taps of the NEXT
+// pixel are fetched one iteration ahead.
 template <int IO>
 DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   PairLayout P;
@@ -370,6 +370,9 @@ DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int 
   int pk = posp[tid];
   DispTaps dt;
   disp_taps_load_t<BF>(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
+  f2 A[12];                                              // projection constants: in registers for the whole phase
+  DVS_UNROLL
+  for (int e = 0; e < 12; ++e) A[e] = ld2(sm + P.a2() + 2 * e);
   DVS_NOUNROLL
   for (int k = tid; k < PLANE; k += NT) {
     const int rx = pk & 0xffff, ry = pk >> 16;
@@ -379,9 +382,6 @@ DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int 
       disp_taps_load_t<BF>(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
     }
     sm[L.du() + k] = du;
-    f2 A[12];
-    DVS_UNROLL
-    for (int e = 0; e < 12; ++e) A[e] = ld2(sm + P.a2() + 2 * e);
     Proj2 pr;
     project2(A, (float)rx, (float)ry, rcp_fast(fmaf(du, p.disp_range, p.min_disp)), p.eps, p.H, p.W, pr);
     f2 tap[3][4];
