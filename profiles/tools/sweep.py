@@ -27,8 +27,11 @@ def main():
     dev = torch.device("cuda:0")
     peak, how = measured_peak_gbs()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    only = [tuple(int(v) for v in q.split("x")) for q in os.environ.get("SWEEP_ONLY", "").split(",") if q]   # e.g. 1280x960x2
     for (W, H) in [(320, 240), (640, 480), (960, 720), (1280, 960), (1920, 1440)]:
         for N in (1, 2, 4):
+            if only and (W, H, N) not in only:
+                continue
             B = max(1, math.ceil(4915200 / (H * W)))
             p = make_problem(B, H, W, N, 4, seed=1, consistent=True)
             Ts = [pose_matrix(a.view(B, 3), t.view(B, 3), inv).to(dev).requires_grad_(True)
