@@ -452,11 +452,23 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * pix_step * args.steps / float(te.item()) / 1e9
     h2d_rank_gbs = h2d * args.steps / t_e2e / 1e9                     # this rank's sustained H2D rate inside the pipeline
+    # the ceiling: plain pinned -> device copies of the same buffers, all ranks at once, nothing else running
+    raw_dst = [torch.empty_like(t, device=dev) for t in [h_in["target"]] + h_in["sources"]]
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        for a, b_ in zip(raw_dst, [h_in["target"]] + h_in["sources"]):
+            a.copy_(b_, non_blocking=True)
+    torch.cuda.synchronize()
+    raw_gbs = 5 * sum(t.numel() * 4 for t in raw_dst) / (time.perf_counter() - t0) / 1e9
+    del raw_dst
+    raw_rates = [None] * world
     rates = [None] * world
     if world > 1:
         dist.all_gather_object(rates, round(h2d_rank_gbs, 2))
+        dist.all_gather_object(raw_rates, round(raw_gbs, 2))
     else:
-        rates = [round(h2d_rank_gbs, 2)]
+        rates, raw_rates = [round(h2d_rank_gbs, 2)], [round(raw_gbs, 2)]
 
     # ---- same, with the images crossing PCIe in dataset precision (uint8, expanded to x/255 on the device: SURVEY 8f rank 2)
     q8 = lambda t: (t * 255).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
@@ -553,8 +565,10 @@ def run_b200(args):
                            "l2": "256 MB buffer written between timed steps (outside the event pairs)", "sharding": f"batch, {world} independent rank(s), no data-path collective"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "h2d_gbs_per_rank": rates, "host_affinity": affinity,
-                        "note": "PCIe / host-DRAM bound: every rank streams 203 MB per step from pinned host memory"},
+                        "h2d_gbs_per_rank": rates, "h2d_raw_copy_gbs_per_rank": raw_rates, "host_affinity": affinity,
+                        "note": "PCIe / host-DRAM bound: every rank streams 203 MB per step from pinned host memory; "
+                                "h2d_raw_copy_gbs_per_rank = plain pinned->device copies of the same buffers by all ranks at once "
+                                "(the ceiling the pipeline's h2d_gbs_per_rank is to be read against; D2H of 26 MB/step runs concurrently)"},
                 # kernels of this library inside one timed step: pre-pass, tile kernel, post-pass (forward) + gradient scaling
                 "gpu_launches": 4 * args.steps, "roofline": roof, "cpu_baseline": cpu, "eager_cuda_baseline": eager,
                 "train_step": train, "train_step_r50x4": train_big, "e2e_uint8_images": e2e_u8,
