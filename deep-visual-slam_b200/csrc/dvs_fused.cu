@@ -410,6 +410,10 @@ static cudaError_t dispatch_tile(const FusedParams& p, int nblk, cudaStream_t st
 // Optional timing of the dominant kernel with events on the caller's stream (bench.py roofline leg).
 // The events belong to the device that was current when they were created: one pair per device, and the read-back
 // reports the pair of the device the last profiled launch ran on.
+// Optional per-device step counter of the in-kernel noise generator (dvs_set_noise_counter): added to `offset` by every
+// forward call that is not given its own offset_dev, so captured CUDA graphs draw fresh noise on every replay.
+static std::atomic<const unsigned long long*> g_noise_ctr[kMaxDevices];
+
 static std::atomic<bool> g_profile{false};
 struct ProfileEvents {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -462,6 +466,11 @@ static int run_forward(const DvsShape* sh, const DvsParams* pr, const float* con
   }
   p.target = target; p.K = K; p.invK = inv_K;
   p.seed = seed; p.offset = offset; p.offset_dev = offset_dev;
+  if (!p.offset_dev) {
+    int dev = 0;
+    DVS_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < kMaxDevices) p.offset_dev = g_noise_ctr[dev].load(std::memory_order_acquire);
+  }
   p.min_disp = 1.0f / pr->max_depth;
   p.disp_range = 1.0f / pr->min_depth - 1.0f / pr->max_depth;
   p.ssim_w = pr->ssim_ratio; p.l1_w = 1.0f - pr->ssim_ratio;
@@ -565,6 +574,12 @@ static int run_backward(const DvsShape* sh, const float* g, const float* const* 
 
 // ================================================================================================ C ABI
 using namespace dvs;
+
+extern "C" int dvs_set_noise_counter(int device, const uint64_t* counter) {
+  if (device < 0 || device >= kMaxDevices) return DVS_EINVAL;
+  g_noise_ctr[device].store(reinterpret_cast<const unsigned long long*>(counter), std::memory_order_release);
+  return DVS_OK;
+}
 
 extern "C" int dvs_set_profiling(int enabled) {
   g_profile.store(enabled != 0);

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "dvs_error_string": [C.c_int],
     "dvs_last_cuda_error": [],
     "dvs_set_profiling": [C.c_int],
+    "dvs_set_noise_counter": [C.c_int, _vp],
     "dvs_last_tile_kernel_ms": [C.POINTER(C.c_float)],
     "dvs_loss_workspace_bytes": [C.POINTER(DvsShape), C.POINTER(C.c_size_t)],
     "dvs_photometric_forward": [C.POINTER(DvsShape), C.POINTER(DvsParams), _FPP, _vp, _FPP, _vp, _vp, _FPP, _FPP,

@@ -9,7 +9,6 @@ of every ``loss/s`` (one pass over the images); backward only scales them by the
 from __future__ import annotations
 
 import ctypes as C
-import itertools
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -17,7 +16,6 @@ import torch
 from . import _lib
 from ._lib import DvsParams, check, fptr_array, lib, make_shape, ptr, require_cuda, stream_ptr, u8ptr_array
 
-_offset_counter = itertools.count()
 
 NoiseArg = Union[str, None, Sequence[torch.Tensor]]
 
@@ -105,22 +103,22 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             require_cuda(*noise)
             noise_arr = fptr_array(noise)
         with torch.cuda.device(dev):
+            ctr = None
+            if noise is None and cfg["auto_mask"]:
+                ctr = _device_counter(dev)           # registered with the library: every in-kernel draw adds it to `offset`
+                ctr.add_(1)                          # on the stream: captured graphs advance it on every replay
             if pose_mode:
-                ctr = None
-                if noise is None and cfg["auto_mask"]:
-                    ctr = _device_counter(dev)
-                    ctr.add_(1)                      # on the stream: captured graphs advance it on every replay
                 inv = (C.c_int32 * N)(*[int(bool(v)) for v in cfg["invert"]])
                 rc = L.dvs_photometric_forward_pose(
                     C.byref(shape), C.byref(params), fptr_array(disps), disp_dtype, ptr(target), fptr_array(sources),
                     image_dtype, ptr(K), ptr(inv_K), fptr_array(Ts[:N]), fptr_array(Ts[N:]), inv, noise_arr,
-                    C.c_uint64(cfg["seed"]), C.c_uint64(0 if ctr is not None else cfg["offset"]), ptr(ctr), ptr(per_scale), ptr(total),
+                    C.c_uint64(cfg["seed"]), C.c_uint64(0), ptr(ctr), ptr(per_scale), ptr(total),
                     u8ptr_array(sel) if sel is not None else None, fptr_array(ugrad) if want_grad else None, ptr(uT), ws_ptr,
                     stream_ptr(dev))
             else:
                 rc = L.dvs_photometric_forward_ex(
                     C.byref(shape), C.byref(params), fptr_array(disps), disp_dtype, ptr(target), fptr_array(sources), image_dtype,
-                    ptr(K), ptr(inv_K), fptr_array(Ts), noise_arr, C.c_uint64(cfg["seed"]), C.c_uint64(cfg["offset"]),
+                    ptr(K), ptr(inv_K), fptr_array(Ts), noise_arr, C.c_uint64(cfg["seed"]), C.c_uint64(0),
                     ptr(per_scale), ptr(total), u8ptr_array(sel) if sel is not None else None,
                     fptr_array(ugrad) if want_grad else None, ptr(uT), ws_ptr, stream_ptr(dev))
         check(rc, "dvs_photometric_forward")
@@ -174,11 +172,12 @@ def _device_counter(dev) -> torch.Tensor:
     key = torch.device(dev).index or 0
     if key not in _counters:
         _counters[key] = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(lib().dvs_set_noise_counter(key, _counters[key].data_ptr()), "dvs_set_noise_counter")
     return _counters[key]
 
 
 def noise_state(device=None) -> int:
-    """Number of in-kernel noise draws made so far on ``device`` (pose-parameter calls); restore with ``set_noise_state``."""
+    """Number of in-kernel noise draws made so far on ``device``; restore with ``set_noise_state`` (checkpoint / resume)."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     return int(_device_counter(dev).item())
 
@@ -253,5 +252,5 @@ def view_synthesis_loss(disps: Sequence[torch.Tensor], target: torch.Tensor, sou
                smoothness_ratio=float(smoothness_ratio), auto_mask=bool(auto_mask),
                return_selection=bool(return_selection),
                seed=int(_default_seed(target.device) if seed is None else seed) & (2 ** 64 - 1),
-               offset=next(_offset_counter), pose_mode=pose_mode, invert=list(inverts) if pose_mode else None)
+               pose_mode=pose_mode, invert=list(inverts) if pose_mode else None)
     return _ViewSynthesisLoss.apply(cfg, target, list(sources), K, inv_K, noise_t, S, N, *disps, *pose_args)

@@ -1,9 +1,11 @@
 """Host-resident entry point of the fused loss: inputs and results live in pinned host memory.
 
-``HostLossPipeline`` splits the batch into equal chunks and overlaps, on three CUDA streams, the host->device copy of
-chunk k+1, the fused loss forward+backward of chunk k and the device->host copy of the gradients of chunk k-1.
+``HostLossPipeline`` splits the batch into equal chunks and overlaps, on three CUDA streams, the host->device copies
+(all chunks are enqueued up-front into their own staging buffers -- a full batch is 0.2 GB of 180 -- so the copy engine
+never waits for the host), the fused loss forward+backward of chunk k as soon as its inputs have landed, and the
+device->host copy of the gradients of chunk k-1.
 Chunking is exact: every reduction of the loss is a batch mean (vo/learner_new.py:244, vo/learner_func.py:174), so
-the batch loss is the mean of the chunk losses and the gradients of a chunk are 1/chunks of its stand-alone
+the batch loss is the B_c/B-weighted sum of the chunk losses and the gradients of a chunk are B_c/B of its stand-alone
 gradients (tests/test_gpu_fused.py checks this decomposition).  PCIe is the bound of this path (203 MB in per step
 at the benchmark size against 1.8 ms of kernels), which is what the overlap is for.
 """
@@ -18,27 +20,44 @@ from .ops import images_u8_to_f32
 
 
 class HostLossPipeline:
-    def __init__(self, B: int, H: int, W: int, disp_sizes: Sequence[Sequence[int]], num_sources: int = 2, chunks: int = 4,
-                 device=None, uint8_images: bool = False, u8_in_kernel: bool = False, **loss_kwargs):
-        if B % chunks:
-            raise ValueError("the batch must split into equal chunks (batch means must stay batch means)")
-        self.B, self.Bc, self.chunks, self.N, self.S = B, B // chunks, chunks, num_sources, len(disp_sizes)
+    def __init__(self, B: int, H: int, W: int, disp_sizes: Sequence[Sequence[int]], num_sources: int = 2, chunks=4,
+                 device=None, uint8_images: bool = False, u8_in_kernel: bool = False, graph: bool = True, **loss_kwargs):
+        """``chunks``: a count (equal chunks) or a sequence of chunk sizes summing to B.  Chunk losses and gradients are combined
+        with the weights B_c / B, so unequal chunks are exact too; tapering the sizes (e.g. 5,4,3,2,2) shortens the part of the
+        step that cannot overlap the copy-in: the kernels and the copy-out of the LAST chunk.
+        ``graph``: record the whole step -- every copy, kernel and cross-stream dependency -- as one CUDA graph the first time a
+        given set of pinned buffers is seen and replay it afterwards: the step is then bound by the copy engines alone, not by
+        ~150 host-side launches (the in-kernel noise counter is a device scalar, so replays keep drawing fresh noise)."""
+        if isinstance(chunks, int):
+            if B % chunks:
+                raise ValueError("the batch must split into equal chunks (or give the chunk sizes)")
+            sizes = [B // chunks] * chunks
+        else:
+            sizes = [int(v) for v in chunks]
+            if sum(sizes) != B or min(sizes) < 1:
+                raise ValueError("chunk sizes must be positive and sum to the batch size")
+        self.sizes = sizes
+        self.starts = [sum(sizes[:i]) for i in range(len(sizes))]
+        chunks = len(sizes)
+        self.B, self.chunks, self.N, self.S = B, chunks, num_sources, len(disp_sizes)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.uint8_images = uint8_images        # images arrive as bytes (dataset precision) and are expanded on the device
         # ... or, with two sources, not expanded at all: the tile kernel reads the bytes (x/255 in-register, same bits)
         self.u8_in_kernel = bool(uint8_images and u8_in_kernel and num_sources == 2)
         self.kw = dict(loss_kwargs)
         self.kw.setdefault("noise", "kernel")
-        Bc, d = self.Bc, self.dev
+        d = self.dev
         mk = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=d)
         self.sets: List[Dict] = []
-        for _ in range(2):                                         # double-buffered device staging
+        for Bc in sizes:                                           # one staging set per chunk: H2D never waits for a free set
             self.sets.append(dict(
                 target=mk(Bc, 3, H, W), sources=[mk(Bc, 3, H, W) for _ in range(num_sources)],
                 disps=[mk(Bc, 1, h, w).requires_grad_(True) for h, w in disp_sizes], K=mk(Bc, 4, 4), inv_K=mk(Bc, 4, 4),
                 Ts=[mk(Bc, 4, 4).requires_grad_(True) for _ in range(num_sources)], losses=mk(1 + self.S),
                 raw=[torch.empty(Bc, 3, H, W, dtype=torch.uint8, device=d) for _ in range(1 + num_sources)] if uint8_images else None))
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(d) for _ in range(3))
+        self.graph_enabled = bool(graph)
+        self._graphs: Dict = {}
         self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
         self.ev_run = [torch.cuda.Event() for _ in range(chunks)]
         self.ev_out = [torch.cuda.Event() for _ in range(chunks)]
@@ -47,17 +66,41 @@ class HostLossPipeline:
         """h_in: pinned ``target``, ``K``, ``inv_K`` and lists ``sources``, ``disps``, ``Ts`` for the full batch;
         h_out: pinned ``loss`` [1+S] (total, then per scale), ``gd`` (list like disps), ``gT`` (list like Ts).
         Returns after everything has landed in h_out."""
-        Bc, C = self.Bc, self.chunks
+        if not self.graph_enabled:
+            self._enqueue(h_in, h_out)
+            self.s_out.synchronize()
+            return
+        flat = [h_in["target"], h_in["K"], h_in["inv_K"]] + h_in["sources"] + h_in["disps"] + h_in["Ts"] + \
+               [h_out["loss"]] + h_out["gd"] + h_out["gT"]
+        key = tuple(t.data_ptr() for t in flat)
+        g = self._graphs.get(key)
+        if g is None:
+            # two eager steps first (allocator warm-up, lazy module loading), then capture on a side stream
+            for _ in range(2):
+                self._enqueue(h_in, h_out)
+                self.s_out.synchronize()
+            cap = torch.cuda.Stream(self.dev)
+            cap.wait_stream(torch.cuda.current_stream(self.dev))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(cap):
+                with torch.cuda.graph(g, stream=cap):
+                    self._enqueue(h_in, h_out)
+            torch.cuda.current_stream(self.dev).wait_stream(cap)
+            self._graphs[key] = g
+            self._keep = getattr(self, "_keep", []) + [flat]          # the graph holds raw pointers into these buffers
+        g.replay()
+        torch.cuda.current_stream(self.dev).synchronize()
+
+    def _enqueue(self, h_in: Dict, h_out: Dict) -> None:
+        C = self.chunks
         cur = torch.cuda.current_stream(self.dev)
         for st in (self.s_in, self.s_run, self.s_out):
             st.wait_stream(cur)
         parts = []
-        for c in range(C):
-            S_ = self.sets[c & 1]
-            sl = slice(c * Bc, (c + 1) * Bc)
-            with torch.cuda.stream(self.s_in), torch.no_grad():
-                if c >= 2:
-                    self.s_in.wait_event(self.ev_out[c - 2])          # the set is free once its gradients left the device
+        with torch.cuda.stream(self.s_in), torch.no_grad():
+            for c in range(C):
+                S_ = self.sets[c]
+                sl = slice(self.starts[c], self.starts[c] + self.sizes[c])
                 if self.uint8_images:
                     for a, b in zip(S_["raw"], [h_in["target"]] + h_in["sources"]):
                         a.copy_(b[sl], non_blocking=True)
@@ -73,14 +116,18 @@ class HostLossPipeline:
                 for a, b in zip(S_["disps"] + S_["Ts"], h_in["disps"] + h_in["Ts"]):
                     a.copy_(b[sl], non_blocking=True)
                 self.ev_in[c].record(self.s_in)
+        for c in range(C):
+            S_ = self.sets[c]
+            sl = slice(self.starts[c], self.starts[c] + self.sizes[c])
+            wgt = self.sizes[c] / self.B
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(self.ev_in[c])
                 for t in S_["disps"] + S_["Ts"]:
                     t.grad = None
                 tgt, srcs = (S_["raw"][0], S_["raw"][1:]) if self.u8_in_kernel else (S_["target"], S_["sources"])
                 loss, per_scale = view_synthesis_loss(S_["disps"], tgt, srcs, S_["K"], S_["inv_K"], S_["Ts"], **self.kw)
-                loss.backward(torch.full_like(loss, 1.0 / C))
-                part = torch.cat([loss.detach().view(1), per_scale.detach()])
+                loss.backward(torch.full_like(loss, wgt))
+                part = torch.cat([loss.detach().view(1), per_scale.detach()]) * wgt
                 parts.append(part)
                 self.ev_run[c].record(self.s_run)
             with torch.cuda.stream(self.s_out), torch.no_grad():
@@ -90,6 +137,5 @@ class HostLossPipeline:
                 self.ev_out[c].record(self.s_out)
         with torch.cuda.stream(self.s_out), torch.no_grad():
             self.s_out.wait_stream(self.s_run)
-            h_out["loss"].copy_(torch.stack(parts).mean(0), non_blocking=True)
-        self.s_out.synchronize()
+            h_out["loss"].copy_(torch.stack(parts).sum(0), non_blocking=True)
         cur.wait_stream(self.s_out)

@@ -69,6 +69,12 @@ int dvs_last_cuda_error(void);
 int dvs_set_profiling(int enabled);
 int dvs_last_tile_kernel_ms(float* ms);
 
+/* In-kernel automask noise under CUDA-graph replay: register a device-resident uint64 step counter for `device` (NULL to
+ * clear).  Every dvs_photometric_forward* call on that device that draws its noise in the kernel (noise == NULL) and is not
+ * given its own offset_dev adds *counter to `offset`; a caller that increments the counter on the stream before each call
+ * gets fresh draws on every replay of a captured graph.  The pointer is not owned; it must outlive the calls. */
+int dvs_set_noise_counter(int device, const uint64_t* counter);
+
 /* Bytes of scratch the fused loss needs for this shape (>=256-byte aligned pointer expected). */
 int dvs_loss_workspace_bytes(const DvsShape* shape, size_t* bytes);
 

@@ -488,3 +488,63 @@ def test_host_pipeline_uint8_in_kernel():
     assert torch.equal(outs[0]["loss"], outs[1]["loss"])
     for a, b in zip(outs[0]["gT"] + outs[0]["gd"], outs[1]["gT"] + outs[1]["gd"]):
         assert torch.equal(a, b)
+
+
+def test_host_pipeline_unequal_chunks_are_exact():
+    """Chunk sizes that taper (5,2,1 of a batch of 8) combine with the weights B_c / B into the single-call result."""
+    from dvsloss import HostLossPipeline
+    from dvsloss.synthetic import pose_matrix
+    dev = torch.device("cuda:0")
+    B, H, W = 8, 64, 96
+    p = make_problem(B, H, W, 2, 4, seed=35, consistent=True)
+    Ts = [pose_matrix(a.view(B, 3), t.view(B, 3), inv) for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+    pin = lambda t: t.contiguous().pin_memory()
+    h_in = dict(target=pin(p["target"]), sources=[pin(s) for s in p["sources"]], disps=[pin(d) for d in p["disps"]],
+                K=pin(p["K"]), inv_K=pin(p["inv_K"]), Ts=[pin(T) for T in Ts])
+    outs = []
+    for chunks in (1, [5, 2, 1]):
+        h_out = dict(loss=torch.empty(5).pin_memory(), gd=[torch.empty_like(d).pin_memory() for d in h_in["disps"]],
+                     gT=[torch.empty_like(T).pin_memory() for T in h_in["Ts"]])
+        HostLossPipeline(B, H, W, [tuple(d.shape[2:]) for d in h_in["disps"]], 2, chunks=chunks, device=dev, noise=None).run(h_in, h_out)
+        outs.append(h_out)
+    np.testing.assert_allclose(outs[1]["loss"].numpy(), outs[0]["loss"].numpy(), rtol=2e-6)
+    for a, b in zip(outs[1]["gd"] + outs[1]["gT"], outs[0]["gd"] + outs[0]["gT"]):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())      # the weights 5/8, 2/8, 1/8 round once more
+
+
+def test_host_pipeline_graph_replay_matches_eager_enqueue():
+    """The recorded CUDA graph of a host-resident step gives the eager result, keeps doing so on replay with new contents in
+    the same pinned buffers, and the in-kernel noise counter advances once per chunk per replay."""
+    import dvsloss
+    from dvsloss import HostLossPipeline
+    from dvsloss.synthetic import pose_matrix
+    dev = torch.device("cuda:0")
+    B, H, W = 4, 64, 96
+    p = make_problem(B, H, W, 2, 4, seed=36, consistent=True)
+    Ts = [pose_matrix(a.view(B, 3), t.view(B, 3), inv) for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+    pin = lambda t: t.contiguous().pin_memory()
+    h_in = dict(target=pin(p["target"]), sources=[pin(s) for s in p["sources"]], disps=[pin(d) for d in p["disps"]],
+                K=pin(p["K"]), inv_K=pin(p["inv_K"]), Ts=[pin(T) for T in Ts])
+    mk_out = lambda: dict(loss=torch.empty(5).pin_memory(), gd=[torch.empty_like(d).pin_memory() for d in h_in["disps"]],
+                          gT=[torch.empty_like(T).pin_memory() for T in h_in["Ts"]])
+    sizes = [tuple(d.shape[2:]) for d in h_in["disps"]]
+    eager, graphed = mk_out(), mk_out()
+    HostLossPipeline(B, H, W, sizes, 2, chunks=2, device=dev, noise=None, graph=False).run(h_in, eager)
+    pipe = HostLossPipeline(B, H, W, sizes, 2, chunks=2, device=dev, noise=None, graph=True)
+    for _ in range(3):                                            # capture, then two replays
+        pipe.run(h_in, graphed)
+    assert torch.equal(eager["loss"], graphed["loss"])
+    for a, b in zip(eager["gd"] + eager["gT"], graphed["gd"] + graphed["gT"]):
+        assert torch.equal(a, b)
+    with torch.no_grad():
+        for d in h_in["disps"]:
+            d.mul_(0.9).add_(0.02)                               # new contents, same buffers
+    HostLossPipeline(B, H, W, sizes, 2, chunks=2, device=dev, noise=None, graph=False).run(h_in, eager)
+    pipe.run(h_in, graphed)
+    assert torch.equal(eager["loss"], graphed["loss"]) and torch.equal(eager["gd"][1], graphed["gd"][1])
+    noisy = HostLossPipeline(B, H, W, sizes, 2, chunks=2, device=dev, noise="kernel", graph=True)
+    noisy.run(h_in, graphed)                                      # capture (2 eager steps + capture do not replay)
+    n0 = dvsloss.noise_state()
+    noisy.run(h_in, graphed)
+    noisy.run(h_in, graphed)
+    assert dvsloss.noise_state() == n0 + 2 * 2
