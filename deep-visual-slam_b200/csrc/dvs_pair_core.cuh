@@ -580,7 +580,7 @@ DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int 
     if (g0.x == 0.f && g1.x == 0.f && g2.x == 0.f && g0.y == 0.f && g1.y == 0.f && g2.y == 0.f) continue;
     const float v = (float)(gyb + j);
     const float D = rcp_fast(fmaf(sm[L.du() + base + j * PW], p.disp_range, p.min_disp));
-    f2 A[12];
+    f2 A[12];                                            // re-read per pixel: held across the loop they cost more in registers
     DVS_UNROLL
     for (int e = 0; e < 12; ++e) A[e] = ld2(sm + P.a2() + 2 * e);
     Proj2 pr;
