@@ -348,8 +348,8 @@ static WsLayout ws_layout(const DvsShape& sh) {
   for (int s = 0; s < sh.S; ++s) {
     const bool direct = sh.dh[s] == sh.H && sh.dw[s] == sh.W;
     w.coff[s] = w.cstride;
-    w.cbw[s] = direct ? 0 : coarse_box_extent(sh.dw[s], sh.W);
-    w.cstride += direct ? 0 : coarse_box_extent(sh.dh[s], sh.H) * w.cbw[s];
+    w.cbw[s] = direct ? 0 : coarse_box_extent(sh.dw[s], sh.W, PITCH_X);
+    w.cstride += direct ? 0 : coarse_box_extent(sh.dh[s], sh.H, PITCH_Y) * w.cbw[s];
   }
   w.cpart = o;     o = align_up(o + sizeof(float) * (size_t)w.nblk * w.cstride, 256);
   w.total = o;

@@ -43,18 +43,24 @@ namespace dvs {
 constexpr int kMaxS = 4;
 constexpr int kMaxN = 4;
 constexpr int TW = 32;                 // R1 width  (one lane per column)
-constexpr int TH = 32;                 // R1 height (8 warps x 4 rows)
+#if !defined(DVS_TILE_ROWS)
+#define DVS_TILE_ROWS 32
+#endif
+constexpr int TH = DVS_TILE_ROWS;      // R1 height (a multiple of 4: TH / 4 warps x 4 rows)
 constexpr int PITCH_X = TW - 2;        // R0 width  = tile pitch in x
 constexpr int PITCH_Y = TH - 2;        // R0 height = tile pitch in y
 constexpr int RW2 = TW + 2;            // R2 width
 constexpr int RH2 = TH + 2;            // R2 height
 constexpr int PW = RW2;                // plane row stride (floats)
 constexpr int PLANE = RH2 * PW;        // 1156 floats; plane index of R2 pixel (ly,lx) is (ly+1)*PW + lx+1
-constexpr int NT = 256;                // threads per CTA
+constexpr int kWarps = TH / 4;
+constexpr int NT = 32 * kWarps;        // threads per CTA
 constexpr int kMeanBlocks = 16;        // partial sums per (scale, batch item) in the disparity-mean pre-pass
 constexpr float kC1 = 0.0001f, kC2 = 0.0009f;
 constexpr float kK1 = 81.0f * 0.0001f, kK2 = 81.0f * 0.0009f;   // SSIM constants on 9-sums
 constexpr int kSelNone = 255;
+constexpr int kTbufCols = 36;          // >= max coarse columns touched by 30 fine columns (+ slack)
+constexpr int kTbufFloats = TH * kTbufCols;   // one row per fine row of R0 (rows = TH - 2)
 
 // ------------------------------------------------------------------------------------------------
 struct FusedParams {
@@ -94,9 +100,9 @@ struct FusedParams {
   float kF, l1k, kxs[kMaxS], kys[kMaxS];
 };
 
-// Upper bound of the coarse rows (columns) touched by the 30 fine rows (columns) of one tile: the clamped source
-// coordinate spans 29 * in/out, plus the two taps.
-DVS_HD int coarse_box_extent(int in, int out) { int e = (29 * in) / out + 3; return e < in ? e : in; }
+// Upper bound of the coarse rows (columns) touched by the `fine` fine rows (columns) of one tile: the clamped source
+// coordinate spans (fine - 1) * in/out, plus the two taps.
+DVS_HD int coarse_box_extent(int in, int out, int fine) { int e = ((fine - 1) * in) / out + 3; return e < in ? e : in; }
 
 DVS_HD unsigned long long noise_offset(const FusedParams& p) { return p.offset + (p.offset_dev ? *p.offset_dev : 0ull); }
 
@@ -251,8 +257,8 @@ struct SmemLayout {
   DVS_HD int total() const { return consts() + 8 + 12 * kMaxN + 8 * kMaxS; }
   // scratch for block reductions / up-sample adjoint: aliases X (and the head of F) once those are dead
   DVS_HD int scratch() const { return x(0, 0); }
-  DVS_HD int tbuf() const { return f(9) - 1152; }                     // last 1152 floats of F
-  DVS_HD int rbuf() const { return f(9) - 1152 - 512; }               // 512 floats before it
+  DVS_HD int tbuf() const { return f(9) - kTbufFloats; }              // the tail of F
+  DVS_HD int rbuf() const { return f(9) - kTbufFloats - 512; }        // 512 floats before it
 };
 // consts block: [0..3] inv_mu[s]; [8+12i ..] A_i (3x3 row-major) then p_i (3); then per scale 8 ints for the up-sample
 // adjoint: coarse box i0, i1, j0, j1 of the tile and the integer ratios H/dh, W/dw (0 when not integer)
@@ -309,9 +315,15 @@ DVS_HD CoarseBox coarse_box(const FusedParams& p, const Tile& t, int s) {
 // constants of the tile: A_i = (K T_i)[:3,:3] inv_K[:3,:3], p_i = (K T_i)[:3,3], 1/(clamp(mean disp)+1e-7) per scale.
 // `a2` (two-source kernel): additionally the same numbers interleaved per source, a2[2 e + i] = (A_i | p_i)[e].
 template <int NS>
+DVS_HD void phase_consts_at(const FusedParams& p, const Tile& t, float* c, int tid, float* a2);
+template <int NS>
 DVS_HD void phase_consts(const FusedParams& p, const Tile& t, float* sm, int tid, float* a2 = nullptr) {
   SmemLayout L{NS};
-  float* c = sm + L.consts();
+  phase_consts_at<NS>(p, t, sm + L.consts(), tid, a2);
+}
+// `c`: the constants block of the tile (any layout)
+template <int NS>
+DVS_HD void phase_consts_at(const FusedParams& p, const Tile& t, float* c, int tid, float* a2) {
   if (tid < 12 * NS) {
     int i = tid / 12, e = tid - i * 12;
     const float* Kb = p.K + t.b * 16;
@@ -1002,10 +1014,8 @@ DVS_HD void fine_range(int J, int f, float inv, int& lo, int& hi) {
     hi = (int)(((float)J + 1.5f) * inv) + 2;
   }
 }
-constexpr int kTbufCols = 36;   // >= max coarse columns touched by 30 fine columns (+ slack), rows = 30
-template <int NS>
-DVS_HD void adjoint_rows(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
-  SmemLayout L{NS};
+template <class LT>
+DVS_HD void adjoint_rows_at(const LT& L, const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   const int* a = reinterpret_cast<const int*>(sm + L.consts() + kC_adj + 8 * s);
   const int j0 = a[2], ncj = a[3] - a[2] + 1, fxi = a[5];
   const int fy0 = t.gy0 + 1, fx0 = t.gx0 + 1, fx1 = imin(t.gx0 + TW - 2, p.W - 1);
@@ -1026,8 +1036,11 @@ DVS_HD void adjoint_rows(const FusedParams& p, const Tile& t, float* sm, int tid
   }
 }
 template <int NS>
-DVS_HD void adjoint_cols(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
-  SmemLayout L{NS};
+DVS_HD void adjoint_rows(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
+  adjoint_rows_at(SmemLayout{NS}, p, t, sm, tid, s);
+}
+template <class LT>
+DVS_HD void adjoint_cols_at(const LT& L, const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   const int* a = reinterpret_cast<const int*>(sm + L.consts() + kC_adj + 8 * s);
   const int nci = a[1] - a[0] + 1, ncj = a[3] - a[2] + 1, fyi = a[4], I0 = a[0];
   const int fy0 = t.gy0 + 1, fy1 = imin(t.gy0 + TH - 2, p.H - 1);
@@ -1044,6 +1057,10 @@ DVS_HD void adjoint_cols(const FusedParams& p, const Tile& t, float* sm, int tid
       acc = fmaf(tap_weight(y, scale, p.dh[s], I), sm[L.tbuf() + (y - fy0) * kTbufCols + Jl], acc);
     p.cpart[(size_t)t.blk * p.cstride + p.coff[s] + Il * p.cbw[s] + Jl] = acc;     // own box slot: no atomics
   }
+}
+template <int NS>
+DVS_HD void adjoint_cols(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
+  adjoint_cols_at(SmemLayout{NS}, p, t, sm, tid, s);
 }
 
 // d loss/s / d disp[s][b, I, J] of an up-sampled scale: the sum, in a fixed order (tile row, then tile column), of
@@ -1076,8 +1093,8 @@ DVS_HD float gather_gdisp(const FusedParams& p, int s, int b, int I, int J) {
 }
 
 // ------------------------------------------------------------------------------------------------ block reduction
-// (a) every thread writes its nv partial values; (b) 8 threads per value sum 32 entries each;
-// (c) one thread per value sums the 8 and writes the block partial.  Deterministic.
+// (a) every thread writes its nv partial values; (b) kWarps threads per value sum 32 entries each;
+// (c) one thread per value sums the kWarps and writes the block partial.  Deterministic.
 template <int NS>
 DVS_HD void reduce_write(const FusedParams& p, float* sm, int tid, const ThreadState<NS>& st) {
   SmemLayout L{NS};
@@ -1088,11 +1105,10 @@ DVS_HD void reduce_write(const FusedParams& p, float* sm, int tid, const ThreadS
   for (int i = 0; i < NS; ++i)
     for (int k = 0; k < 12; ++k) sc[3 + 12 * i + k] = st.dM[i][k];
 }
-template <int NS>
-DVS_HD void reduce_stage1(const FusedParams& p, float* sm, int tid) {
-  SmemLayout L{NS};
+template <int NS, class LT>
+DVS_HD void reduce_stage1_at(const LT& L, float* sm, int tid) {
   constexpr int nv = 3 + 12 * NS;
-  for (int w = tid; w < nv * 8; w += NT) {
+  for (int w = tid; w < nv * kWarps; w += NT) {
     int g = w / nv, v = w - g * nv;            // consecutive lanes -> consecutive words
     float a = 0.f;
     for (int k = 0; k < 32; ++k) a += sm[L.scratch() + (g * 32 + k) * nv + v];
@@ -1100,14 +1116,21 @@ DVS_HD void reduce_stage1(const FusedParams& p, float* sm, int tid) {
   }
 }
 template <int NS>
-DVS_HD void reduce_stage2(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
-  SmemLayout L{NS};
+DVS_HD void reduce_stage1(const FusedParams& p, float* sm, int tid) {
+  reduce_stage1_at<NS>(SmemLayout{NS}, sm, tid);
+}
+template <int NS, class LT>
+DVS_HD void reduce_stage2_at(const LT& L, const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   constexpr int nv = 3 + 12 * NS;
   if (tid < nv) {
     float a = 0.f;
-    for (int g = 0; g < 8; ++g) a += sm[L.rbuf() + g * nv + tid];
+    for (int g = 0; g < kWarps; ++g) a += sm[L.rbuf() + g * nv + tid];
     p.part[((size_t)t.blk * p.S + s) * nv + tid] = a;
   }
+}
+template <int NS>
+DVS_HD void reduce_stage2(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
+  reduce_stage2_at<NS>(SmemLayout{NS}, p, t, sm, tid, s);
 }
 
 template <int NS>

@@ -13,15 +13,20 @@ namespace dvs {
 // 4 % SLOWER at config 2 (1.650 vs 1.589 ms, profiles/r02_experiments.md): CTAs launched together stay phase-locked, so
 // the two CTAs of an SM sit in the latency-bound gather phase at the same time, whereas CTAs of a plain grid retire and
 // start at different times and overlap gather with arithmetic.
+// Resident CTAs per SM the kernel is compiled for: 3 with 28-row tiles (224 threads, <= 97 registers, 74.5 KB of shared
+// memory each), 2 with 32-row tiles.
+#if !defined(DVS_PAIR_MINBLOCKS)
+#define DVS_PAIR_MINBLOCKS (DVS_TILE_ROWS <= 28 ? 3 : 2)
+#endif
 template <bool GRAD, int IO>
-__global__ void __launch_bounds__(NT, 2) fused_pair_kernel(const __grid_constant__ FusedParams p) {
+__global__ void __launch_bounds__(NT, DVS_PAIR_MINBLOCKS) fused_pair_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
   PairLayout P;
   PairState st;
   const Tile t = make_tile(p, blockIdx.x);
 
-  phase_consts<2>(p, t, sm, tid, sm + P.a2());
+  phase_consts_at<2>(p, t, sm + P.consts(), tid, sm + P.a2());
   pair_phase_load<IO>(p, t, sm, tid, st);
   __syncthreads();
   pair_phase_identity(p, t, sm, tid, st);
@@ -42,11 +47,11 @@ __global__ void __launch_bounds__(NT, 2) fused_pair_kernel(const __grid_constant
     }
     pair_reduce_write(sm, tid, st);
     __syncthreads();
-    if (GRAD && !direct) adjoint_rows<2>(p, t, sm, tid, s);
-    reduce_stage1<2>(p, sm, tid);
+    if (GRAD && !direct) adjoint_rows_at(P, p, t, sm, tid, s);
+    reduce_stage1_at<2>(P, sm, tid);
     __syncthreads();
-    if (GRAD && !direct) adjoint_cols<2>(p, t, sm, tid, s);
-    reduce_stage2<2>(p, t, sm, tid, s);
+    if (GRAD && !direct) adjoint_cols_at(P, p, t, sm, tid, s);
+    reduce_stage2_at<2>(P, p, t, sm, tid, s);
     // as in fused_tile_kernel: the next warp phase writes only X / DU, which nobody reads any more
   }
 }

@@ -22,15 +22,31 @@
 
 namespace dvs {
 
-constexpr int kPairIdent = 8 * NT;   // identity terms parked in shared memory: [2 j + i][tid]
-
+// Shared memory of the two-source kernel (floats), 94 KB with 32-row tiles: two CTAs per SM fit the 196 KB carve-out, which
+// leaves 60 KB of L1 for the gathers (the generic layout's 103 KB forces the 228 KB carve-out and 28 KB of L1).  No position
+// table (the warp phase recomputes the reflected image coordinates), the identity terms live in registers, and the nine
+// coefficient planes cover R1 only (row pitch TW).
+//   Y[3] | X2[3] (float2) | F[9] (R1) | DU | WX | WY | SEL (bytes) | consts | A2
+constexpr int FP = TH * TW;            // floats of one coefficient plane; R1 pixel (ly, lx) is at ly * TW + lx
 struct PairLayout {
-  SmemLayout L{2};
-  DVS_HD int x2(int c) const { return L.x(0, 0) + 2 * c * PLANE; }                 // float2 plane of channel c
-  DVS_HD int ident() const { return (L.total() + 1) & ~1; }
-  DVS_HD int a2() const { return ident() + kPairIdent; }                           // 12 float2: (A_0[e], A_1[e]); 8-byte aligned
+  DVS_HD int y(int c) const { return c * PLANE; }
+  DVS_HD int x2(int c) const { return (3 + 2 * c) * PLANE; }                       // float2 plane of channel c
+  DVS_HD int f(int k) const { return 9 * PLANE + k * FP; }
+  DVS_HD int du() const { return f(9); }
+  DVS_HD int wx() const { return du() + PLANE; }                                   // edge weights of the smoothness term
+  DVS_HD int wy() const { return du() + 2 * PLANE; }
+  DVS_HD int sel() const { return du() + 3 * PLANE; }                              // PLANE bytes, indexed like an R2 plane
+  DVS_HD int consts() const { return sel() + (PLANE + 3) / 4; }
+  DVS_HD int a2() const { return (consts() + 8 + 12 * kMaxN + 8 * kMaxS + 1) & ~1; }   // 12 float2: (A_0[e], A_1[e]); 8-byte aligned
   DVS_HD int total() const { return a2() + 24; }
+  // scratch for the block reductions / the up-sample adjoint: aliases X2 (and the head of F), and the tail of F, once
+  // those are dead
+  DVS_HD int scratch() const { return x2(0); }
+  DVS_HD int tbuf() const { return f(9) - kTbufFloats; }
+  DVS_HD int rbuf() const { return f(9) - kTbufFloats - 512; }
 };
+static_assert(NT * (3 + 12 * 2) + kTbufFloats + 512 <= 6 * PLANE + 9 * FP,
+              "reduction scratch (from the start of X2) and tbuf / rbuf (at the end of F) must not overlap");
 
 DVS_HD f2 ld2(const float* p) {
 #if defined(__CUDA_ARCH__)
@@ -103,6 +119,7 @@ DVS_HD void disp_taps_load_t(const float* d, int dh, int dw, float sy, float sx,
 }
 
 struct PairState {
+  f2 ident[4];             // identity reprojection terms of the own pixels (scale independent), (source 0, source 1)
   int flags;               // bit j: pixel j inside the image; bit 4+j: pixel j belongs to R0 (own)
   float acc[3];            // photometric sum, smooth-x sum, smooth-y sum of the current scale
   f2 M[12];                // pose-gradient moments of the current scale, (source 0, source 1)
@@ -115,17 +132,15 @@ struct PairState {
 template <int IO>
 DVS_HD void pair_phase_load(const FusedParams& p, const Tile& t, float* sm, int tid, PairState& st) {
   PairLayout P;
-  const SmemLayout& L = P.L;
+  const PairLayout& L = P;
   const int HW = p.H * p.W;
   constexpr bool U8 = (IO & kIoImgU8) != 0;
   const ImgPtr<U8> tgt = ImgPtr<U8>{p.target}.off((size_t)t.b * 3 * HW);
   const ImgPtr<U8> sr0 = ImgPtr<U8>{p.src[0]}.off((size_t)t.b * 3 * HW), sr1 = ImgPtr<U8>{p.src[1]}.off((size_t)t.b * 3 * HW);
-  int* posp = reinterpret_cast<int*>(sm + L.pos());
   DVS_NOUNROLL
   for (int k = tid; k < PLANE; k += NT) {
     int ly = k / PW - 1, lx = k % PW - 1;
     int gy = reflect_clamp(t.gy0 + ly, p.H), gx = reflect_clamp(t.gx0 + lx, p.W);
-    posp[k] = (gy << 16) | gx;
     int o = gy * p.W + gx;
     sm[L.y(0) + k] = tgt.at(o);
     sm[L.y(1) + k] = tgt.at(o + HW);
@@ -136,13 +151,8 @@ DVS_HD void pair_phase_load(const FusedParams& p, const Tile& t, float* sm, int 
       st2(sm + P.x2(2) + 2 * k, f2{sr0.at(o + 2 * HW), sr1.at(o + 2 * HW)});
     }
   }
-#if defined(__CUDA_ARCH__)
-  float4* f4 = reinterpret_cast<float4*>(sm + L.f(0));
-  for (int k = tid; k < 9 * PLANE / 4; k += NT) f4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-#else
-  for (int k = tid; k < 9 * PLANE; k += NT) sm[L.f(0) + k] = 0.f;
-#endif
-  for (int k = tid; k < PLANE / 4; k += NT) reinterpret_cast<unsigned int*>(sm + L.sel())[k] = 0xffffffffu;   // kSelNone
+  // the coefficient planes are rewritten on all of R1 by every statistics phase: nothing to clear
+  for (int k = tid; k < (PLANE + 3) / 4; k += NT) reinterpret_cast<unsigned int*>(sm + L.sel())[k] = 0xffffffffu;   // kSelNone
   int r0, cx;
   quad_coords(tid, r0, cx);
   int fl = 0;
@@ -187,14 +197,15 @@ DVS_HD void ssim_coefs2(const SsimPair& t, f2 sx, float sy, float scale, f2& al,
 }
 
 // Reprojection terms r = ssim_w3 * sum_c SSIM + l1_w3 * sum_c |y - x| of both sources for the two pixels at R1 rows
-// (ra, ra + 1), column cx (base = pidx(ra, cx)); X2 holds what is compared with the target (warped colours, or the raw
-// sources for the identity terms).  COEFS: the SSIM coefficient fields of source 0 go to F, those of source 1 to `hold`.
-// EDGES: accumulate the |dy| sums of the smoothness edge weights.
+// (ra, ra + 1), column cx (base = pidx(ra, cx), fbase = ra * TW + cx); X2 holds what is compared with the target (warped
+// colours, or the raw sources for the identity terms).  COEFS: the SSIM coefficient fields of source 0 go to F, those of
+// source 1 to `hold`.  EDGES: the four |dy| sums per pixel behind the smoothness edge weights, e[j] = {right, left, down,
+// up} neighbour (sum over the channels of |y - y_neighbour|, accumulated in channel order like the reference's mean).
 template <bool COEFS, bool EDGES>
-DVS_HD void pair_half(float* sm, int base, float ssim_w3, float l1_w3, float kF, f2* r, float (*hold)[3][2], float* ax,
-                      float* ay) {
+DVS_HD void pair_half(float* sm, int base, int fbase, float ssim_w3, float l1_w3, float kF, f2* r, float (*hold)[3][2],
+                      float (*e)[4]) {
   PairLayout P;
-  const SmemLayout& L = P.L;
+  const PairLayout& L = P;
   f2 rs[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}}, rl[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}};
   DVS_UNROLL
   for (int c = 0; c < 3; ++c) {
@@ -227,11 +238,14 @@ DVS_HD void pair_half(float* sm, int base, float ssim_w3, float l1_w3, float kF,
       yc[m] = b;
       if (m == 1) xc[0] = xb;
       if (m == 2) xc[1] = xb;
-      if (EDGES && (m == 1 || m == 2)) ax[m - 1] += fabsf(b - d);
+      if (EDGES && (m == 1 || m == 2)) {
+        e[m - 1][0] += fabsf(b - d);                      // centre - right
+        e[m - 1][1] += fabsf(a - b);                      // left - centre (the left neighbour's "centre - right")
+      }
     }
     if (EDGES) {
-      ay[0] += fabsf(yc[1] - yc[2]);
-      ay[1] += fabsf(yc[2] - yc[3]);
+      e[0][2] += fabsf(yc[1] - yc[2]); e[0][3] += fabsf(yc[0] - yc[1]);     // centre - down, up - centre
+      e[1][2] += fabsf(yc[2] - yc[3]); e[1][3] += fabsf(yc[1] - yc[2]);
     }
     // vertical 3-sums, shared middle partial (same order as vsum4)
     const float uy = hy[1] + hy[2], uyy = hyy[1] + hyy[2];
@@ -252,8 +266,8 @@ DVS_HD void pair_half(float* sm, int base, float ssim_w3, float l1_w3, float kF,
       if (COEFS) {
         f2 al, be, ga;
         ssim_coefs2(t, sx, sy, kF, al, be, ga);
-        float* F = sm + L.f(c * 3) + base + j * PW;
-        F[0] = al.x; F[PLANE] = be.x; F[2 * PLANE] = ga.x;
+        float* F = sm + L.f(c * 3) + fbase + j * TW;
+        F[0] = al.x; F[FP] = be.x; F[2 * FP] = ga.x;
         hold[c][0][j] = al.y; hold[c][1][j] = be.y; hold[c][2][j] = ga.y;
       }
     }
@@ -263,40 +277,39 @@ DVS_HD void pair_half(float* sm, int base, float ssim_w3, float l1_w3, float kF,
 }
 
 // ------------------------------------------------------------------------------------------------ identity
-// identity terms (parked in shared memory) + smoothness edge weights of the own pixels (scale independent).
+// identity reprojection terms of the own pixels (scale independent; kept in registers).
 DVS_HD void pair_phase_identity(const FusedParams& p, const Tile& t, float* sm, int tid, PairState& st) {
-  PairLayout P;
-  const SmemLayout& L = P.L;
   int r0, cx;
   quad_coords(tid, r0, cx);
   const int base0 = pidx(r0, cx);
   const float sw3 = p.ssim_w * (1.f / 3.f), lw3 = p.l1_w * (1.f / 3.f);
+  DVS_UNROLL
+  for (int j = 0; j < 4; ++j) st.ident[j] = f2{0.f, 0.f};
+  PairLayout L;
   const int gx = t.gx0 + cx;
-  float* idp = sm + P.ident() + tid;
   DVS_NOUNROLL
   for (int h = 0; h < 2; ++h) {
-    const int base = base0 + 2 * h * PW;
-    float ax[2] = {0.f, 0.f}, ay[2] = {0.f, 0.f};
     f2 r[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}};
+    float e[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const int base = base0 + 2 * h * PW;
     if (p.auto_mask) {
-      pair_half<false, true>(sm, base, sw3, lw3, 0.f, r, nullptr, ax, ay);
+      pair_half<false, true>(sm, base, 0, sw3, lw3, 0.f, r, nullptr, e);
     } else {
       for (int c = 0; c < 3; ++c)
         for (int j = 0; j < 2; ++j) {
-          int o = base + j * PW;
-          float y0 = sm[L.y(c) + o];
-          ax[j] += fabsf(y0 - sm[L.y(c) + o + 1]);
-          ay[j] += fabsf(y0 - sm[L.y(c) + o + PW]);
+          const int o = base + j * PW;
+          const float y0 = sm[L.y(c) + o];
+          e[j][0] += fabsf(y0 - sm[L.y(c) + o + 1]);
+          e[j][2] += fabsf(y0 - sm[L.y(c) + o + PW]);
         }
     }
+    if (h == 0) { st.ident[0] = r[0]; st.ident[1] = r[1]; }
+    else { st.ident[2] = r[0]; st.ident[3] = r[1]; }
     for (int j = 0; j < 2; ++j) {
-      const int jj = 2 * h + j;
-      idp[(2 * jj) * NT] = r[j].x;
-      idp[(2 * jj + 1) * NT] = r[j].y;
-      const int gy = t.gy0 + r0 + jj, o = base + j * PW;
+      const int jj = 2 * h + j, gy = t.gy0 + r0 + jj, o = base + j * PW;
       const bool in = (st.flags >> jj) & 1;
-      sm[L.wx() + o] = (in && gx < p.W - 1) ? exp_fast(-ax[j] * (1.f / 3.f)) : 0.f;
-      sm[L.wy() + o] = (in && gy < p.H - 1) ? exp_fast(-ay[j] * (1.f / 3.f)) : 0.f;
+      sm[L.wx() + o] = (in && gx < p.W - 1) ? exp_fast(-e[j][0] * (1.f / 3.f)) : 0.f;
+      sm[L.wy() + o] = (in && gy < p.H - 1) ? exp_fast(-e[j][2] * (1.f / 3.f)) : 0.f;
     }
   }
 }
@@ -356,34 +369,39 @@ DVS_HD void lerp_store2(float* sm, int x2off, int k, f2 tx, f2 ty, const f2 (*ta
 template <int IO>
 DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int tid, int s) {
   PairLayout P;
-  const SmemLayout& L = P.L;
+  const PairLayout& L = P;
   const int HW = p.H * p.W;
   const int dh = p.dh[s], dw = p.dw[s];
   constexpr bool U8 = (IO & kIoImgU8) != 0, BF = (IO & kIoDispBf16) != 0;
   const float* d = disp_image<BF>(p.disp[s], (size_t)t.b * dh * dw);
   const bool direct = dh == p.H && dw == p.W;
   const float scy = (float)dh / (float)p.H, scx = (float)dw / (float)p.W;
-  const int* posp = reinterpret_cast<const int*>(sm + L.pos());
   const ImgPtr<U8> im0 = ImgPtr<U8>{p.src[0]}.off((size_t)t.b * 3 * HW), im1 = ImgPtr<U8>{p.src[1]}.off((size_t)t.b * 3 * HW);
   const int x2off = P.x2(0);
 
-  int pk = posp[tid];
+  // R2 coordinates of pixel k = tid + NT it, advanced incrementally (NT = dq PW + dr); the reflected image coordinates
+  // are recomputed from them (no position table in shared memory)
+  constexpr int dq = NT / PW, dr = NT % PW;
+  int ly = tid / PW, lx = tid - ly * PW;
+  int ry = reflect_clamp(t.gy0 + ly - 1, p.H), rx = reflect_clamp(t.gx0 + lx - 1, p.W);
   DispTaps dt;
-  disp_taps_load_t<BF>(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
+  disp_taps_load_t<BF>(d, dh, dw, scy, scx, direct, ry, rx, dt);
   f2 A[12];                                              // projection constants: in registers for the whole phase
   DVS_UNROLL
   for (int e = 0; e < 12; ++e) A[e] = ld2(sm + P.a2() + 2 * e);
   DVS_NOUNROLL
   for (int k = tid; k < PLANE; k += NT) {
-    const int rx = pk & 0xffff, ry = pk >> 16;
+    const float u = (float)rx, v = (float)ry;
     const float du = disp_taps_value(dt, direct);
     if (k + NT < PLANE) {                                // disparity of the next pixel: in flight during this one
-      pk = posp[k + NT];
-      disp_taps_load_t<BF>(d, dh, dw, scy, scx, direct, pk >> 16, pk & 0xffff, dt);
+      ly += dq; lx += dr;
+      if (lx >= PW) { lx -= PW; ly += 1; }
+      ry = reflect_clamp(t.gy0 + ly - 1, p.H); rx = reflect_clamp(t.gx0 + lx - 1, p.W);
+      disp_taps_load_t<BF>(d, dh, dw, scy, scx, direct, ry, rx, dt);
     }
     sm[L.du() + k] = du;
     Proj2 pr;
-    project2(A, (float)rx, (float)ry, rcp_fast(fmaf(du, p.disp_range, p.min_disp)), p.eps, p.H, p.W, pr);
+    project2(A, u, v, rcp_fast(fmaf(du, p.disp_range, p.min_disp)), p.eps, p.H, p.W, pr);
     f2 tap[3][4];
     gather_taps2(im0, im1, pr.o0, pr.o1, HW, p.W, tap);   // all 24 tap loads of the pixel before the first use
     lerp_store2(sm, x2off, k, pr.tx, pr.ty, tap);
@@ -394,41 +412,44 @@ DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int 
 template <bool GRAD>
 DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int tid, int s, PairState& st) {
   PairLayout P;
-  const SmemLayout& L = P.L;
+  const PairLayout& L = P;
   const float* cst = sm + L.consts();
   int r0, cx;
   quad_coords(tid, r0, cx);
   const int base0 = pidx(r0, cx);
   const int gx = t.gx0 + cx, gyb = t.gy0 + r0;
   const float sw3 = p.ssim_w * (1.f / 3.f), lw3 = p.l1_w * (1.f / 3.f);
-  const int HW = p.H * p.W;
   const int fl = st.flags;
   const float kF = p.kF;
-  const float* idp = sm + P.ident() + tid;
   unsigned char* selp = reinterpret_cast<unsigned char*>(sm + L.sel());
   const int off = p.auto_mask ? 2 : 0;
+  const float inv_mu = cst[kC_invmu + s];
+  const float kx = p.kxs[s], ky = p.kys[s];
+  const float* DU = sm + L.du();
   int tags = 0;
-  float photo = 0.f;
+  float photo = 0.f, smx = 0.f, smy = 0.f;
+  float g01[2] = {0.f, 0.f}, g23[2] = {0.f, 0.f};        // smoothness part of d loss / d disp_up of the four pixels
 
   DVS_NOUNROLL
   for (int h = 0; h < 2; ++h) {
     const int base = base0 + 2 * h * PW;
     f2 r[2];
     float hold[3][3][2];
-    pair_half<GRAD, false>(sm, base, sw3, lw3, kF, r, hold, nullptr, nullptr);
+    pair_half<GRAD, false>(sm, base, (r0 + 2 * h) * TW + cx, sw3, lw3, kF, r, hold, nullptr);
     DVS_UNROLL
     for (int j = 0; j < 2; ++j) {
       const int jj = 2 * h + j;
       const bool in = (fl >> jj) & 1;
+      const bool own = (fl >> (4 + jj)) & 1;
       float best = 3.0e38f;
       int tag = kSelNone, chan = 0;
       if (p.auto_mask) {
         float n0 = 0.f, n1 = 0.f;
-        const float id0 = idp[(2 * jj) * NT], id1 = idp[(2 * jj + 1) * NT];
+        const f2 idv = h ? st.ident[2 + j] : st.ident[j];
         // The in-kernel generator is bounded (|n| <= sqrt(48 ln 2) = 5.77, i.e. 5.77e-5 after scaling): where a
         // reprojection term beats both identity terms by more than that, no draw can change the outcome (minimum,
         // argmin and loss value are the reprojection's), so the draw is skipped.  Given noise tensors are always read.
-        const bool need = p.noise[s] != nullptr || !(fminf(r[j].x, r[j].y) < fminf(id0, id1) - 6.0e-5f);
+        const bool need = p.noise[s] != nullptr || !(fminf(r[j].x, r[j].y) < fminf(idv.x, idv.y) - 6.0e-5f);
         if (in && need) {
           const int gy = gyb + jj;
           if (p.noise[s]) {
@@ -438,8 +459,8 @@ DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int
             hash_normal2(p.seed, noise_offset(p), (unsigned)((t.b * p.H + gy) * p.W + gx), (unsigned)(s * kMaxN), n0, n1);
           }
         }
-        const float v0 = fmaf(n0, 0.00001f, id0);
-        const float v1 = fmaf(n1, 0.00001f, id1);
+        const float v0 = fmaf(n0, 0.00001f, idv.x);
+        const float v1 = fmaf(n1, 0.00001f, idv.y);
         if (v0 < best) { best = v0; chan = 0; }
         if (v1 < best) { best = v1; chan = 1; }
       }
@@ -448,45 +469,43 @@ DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int
       if (!in) tag = kSelNone;
       tags |= tag << (8 * jj);
       selp[base + j * PW] = (unsigned char)tag;
-      if ((fl >> (4 + jj)) & 1) {
+      if (own) {
         photo += best;
         if (p.sel[s]) p.sel[s][((size_t)t.b * p.H + gyb + jj) * p.W + gx] = (unsigned char)chan;
       }
       if (GRAD && tag != 0) {
         // F holds source 0's fields: replace them by source 1's where it won, by exact zeros where neither did
-        float* F = sm + L.f(0) + base + j * PW;
+        float* F = sm + L.f(0) + (r0 + jj) * TW + cx;
         DVS_UNROLL
         for (int c = 0; c < 3; ++c)
           DVS_UNROLL
-          for (int f = 0; f < 3; ++f) F[(c * 3 + f) * PLANE] = tag == 1 ? hold[c][f][j] : 0.f;
+          for (int f = 0; f < 3; ++f) F[(c * 3 + f) * FP] = tag == 1 ? hold[c][f][j] : 0.f;
       }
+      // smoothness on the normalised up-sampled disparity (own pixels); edge weights exp(-mean_c |dy|) from the sums
+      // pair_half collected (zero across the image border, learner_func.py:161-174)
+      float gsm = 0.f;
+      if (own) {
+        const int o = base + j * PW;
+        const float wxr = sm[L.wx() + o], wxl = sm[L.wx() + o - 1], wyd = sm[L.wy() + o], wyu = sm[L.wy() + o - PW];
+        // difference first, then normalise (see phase_stats)
+        const float d0 = DU[o];
+        const float dxr = (d0 - DU[o + 1]) * inv_mu, dxl = (DU[o - 1] - d0) * inv_mu;
+        const float dyd = (d0 - DU[o + PW]) * inv_mu, dyu = (DU[o - PW] - d0) * inv_mu;
+        smx += fabsf(dxr) * wxr;
+        smy += fabsf(dyd) * wyd;
+        if (GRAD) {
+          const float gn = kx * (sgn(dxr) * wxr - sgn(dxl) * wxl) + ky * (sgn(dyd) * wyd - sgn(dyu) * wyu);
+          gsm = gn * inv_mu;
+        }
+      }
+      if (h == 0) g01[j] = gsm; else g23[j] = gsm;
     }
   }
   st.tags = tags;
   st.acc[0] += photo;
-
-  // smoothness on the normalised up-sampled disparity (own pixels)
-  const float inv_mu = cst[kC_invmu + s];
-  const float kx = p.kxs[s], ky = p.kys[s];
-  const float* DU = sm + L.du();
-  const float* WX = sm + L.wx();
-  const float* WY = sm + L.wy();
-  for (int j = 0; j < 4; ++j) {
-    st.gdu[j] = 0.f;
-    if (!((fl >> (4 + j)) & 1)) continue;
-    int o = base0 + j * PW;
-    // difference first, then normalise (see phase_stats)
-    float d0 = DU[o];
-    float dxr = (d0 - DU[o + 1]) * inv_mu, dxl = (DU[o - 1] - d0) * inv_mu;
-    float dyd = (d0 - DU[o + PW]) * inv_mu, dyu = (DU[o - PW] - d0) * inv_mu;
-    float wxr = WX[o], wxl = WX[o - 1], wyd = WY[o], wyu = WY[o - PW];
-    st.acc[1] += fabsf(dxr) * wxr;
-    st.acc[2] += fabsf(dyd) * wyd;
-    if (GRAD) {
-      float gn = kx * (sgn(dxr) * wxr - sgn(dxl) * wxl) + ky * (sgn(dyd) * wyd - sgn(dyu) * wyu);
-      st.gdu[j] = gn * inv_mu;
-    }
-  }
+  st.acc[1] += smx;
+  st.acc[2] += smy;
+  st.gdu[0] = g01[0]; st.gdu[1] = g01[1]; st.gdu[2] = g23[0]; st.gdu[3] = g23[1];
 }
 
 // ------------------------------------------------------------------------------------------------ phase G
@@ -495,7 +514,7 @@ DVS_HD void pair_phase_stats(const FusedParams& p, const Tile& t, float* sm, int
 template <int IO>
 DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int tid, int s, PairState& st) {
   PairLayout P;
-  const SmemLayout& L = P.L;
+  const PairLayout& L = P;
   constexpr bool U8 = (IO & kIoImgU8) != 0;
   if (!(st.flags >> 4)) return;                       // no own pixel
   int r0, cx;
@@ -530,11 +549,11 @@ DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int 
     f2 pooled[3][4];                                    // (source 0, source 1) per field and pixel
     DVS_UNROLL
     for (int f = 0; f < 3; ++f) {
-      const float* F = sm + L.f(c * 3 + f) + base;
+      const float* F = sm + L.f(c * 3 + f) + r0 * TW + cx;     // coefficient planes cover R1 only, row pitch TW
       f2 hT[3], h0[3];
       for (int m2 = 0; m2 < 3; ++m2) {
-        const float* ra = F + (2 * m2 - 1) * PW;
-        const float* rb = ra + PW;
+        const float* ra = F + (2 * m2 - 1) * TW;
+        const float* rb = ra + TW;
         const f2 lft{ra[-1], rb[-1]}, mid{ra[0], rb[0]}, rgt{ra[1], rb[1]};
         // same operation order in both sums: where every selected neighbour chose source 0 they are bit-equal
         hT[m2] = fma2(rgt, wr2, fma2(mid, one2, mul2(lft, wl2)));
@@ -628,13 +647,13 @@ DVS_HD void pair_store_gdu_direct(const FusedParams& p, const Tile& t, int tid, 
     if ((st.flags >> (4 + j)) & 1) p.gdisp[s][((size_t)t.b * p.H + t.gy0 + r0 + j) * p.W + t.gx0 + cx] = st.gdu[j];
 }
 DVS_HD void pair_stage_gdu(float* sm, int tid, const PairState& st) {
-  SmemLayout L{2};
+  PairLayout L;
   int r0, cx;
   quad_coords(tid, r0, cx);
   for (int j = 0; j < 4; ++j) sm[L.du() + pidx(r0 + j, cx)] = ((st.flags >> (4 + j)) & 1) ? st.gdu[j] : 0.f;
 }
 DVS_HD void pair_reduce_write(float* sm, int tid, const PairState& st) {
-  SmemLayout L{2};
+  PairLayout L;
   constexpr int nv = 3 + 12 * 2;
   float* sc = sm + L.scratch() + tid * nv;
   sc[0] = st.acc[0]; sc[1] = st.acc[1]; sc[2] = st.acc[2];

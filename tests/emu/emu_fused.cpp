@@ -59,7 +59,7 @@ void run_block_pair(const FusedParams& p, int blk, std::vector<float>& smv) {
   Tile t = make_tile(p, blk);
   PairLayout P;
   std::vector<PairState> st(NT);
-  for (int tid = 0; tid < NT; ++tid) { phase_consts<2>(p, t, sm, tid, sm + P.a2()); pair_phase_load<0>(p, t, sm, tid, st[tid]); }
+  for (int tid = 0; tid < NT; ++tid) { phase_consts_at<2>(p, t, sm + P.consts(), tid, sm + P.a2()); pair_phase_load<0>(p, t, sm, tid, st[tid]); }
   for (int tid = 0; tid < NT; ++tid) pair_phase_identity(p, t, sm, tid, st[tid]);
   for (int s = 0; s < p.S; ++s) {
     for (int tid = 0; tid < NT; ++tid) { pair_reset_scale_state(st[tid]); pair_phase_warp<0>(p, t, sm, tid, s); }
@@ -74,12 +74,12 @@ void run_block_pair(const FusedParams& p, int blk, std::vector<float>& smv) {
     }
     for (int tid = 0; tid < NT; ++tid) pair_reduce_write(sm, tid, st[tid]);
     for (int tid = 0; tid < NT; ++tid) {
-      if (GRAD && !direct) adjoint_rows<2>(p, t, sm, tid, s);
-      reduce_stage1<2>(p, sm, tid);
+      if (GRAD && !direct) adjoint_rows_at(P, p, t, sm, tid, s);
+      reduce_stage1_at<2>(P, sm, tid);
     }
     for (int tid = 0; tid < NT; ++tid) {
-      if (GRAD && !direct) adjoint_cols<2>(p, t, sm, tid, s);
-      reduce_stage2<2>(p, t, sm, tid, s);
+      if (GRAD && !direct) adjoint_cols_at(P, p, t, sm, tid, s);
+      reduce_stage2_at<2>(P, p, t, sm, tid, s);
     }
   }
 }
@@ -151,8 +151,8 @@ extern "C" int emu_photometric_forward(const DvsShape* sh, const DvsParams* pr, 
   for (int s = 0; s < sh->S; ++s) {
     const bool direct = p.dh[s] == p.H && p.dw[s] == p.W;
     p.coff[s] = cstride;
-    p.cbw[s] = direct ? 0 : coarse_box_extent(p.dw[s], p.W);
-    cstride += direct ? 0 : coarse_box_extent(p.dh[s], p.H) * p.cbw[s];
+    p.cbw[s] = direct ? 0 : coarse_box_extent(p.dw[s], p.W, PITCH_X);
+    cstride += direct ? 0 : coarse_box_extent(p.dh[s], p.H, PITCH_Y) * p.cbw[s];
   }
   p.cstride = cstride;
   {

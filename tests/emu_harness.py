@@ -31,7 +31,8 @@ class DvsParams(C.Structure):
 def build(defines=()) -> str:
     """``defines``: extra -D macros (fault-injection builds); each set of macros gets its own library file."""
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    out = OUT if not defines else OUT.replace(".so", "_" + "_".join(d.split("=")[0].lower() for d in defines) + ".so")
+    defines = tuple(defines) + tuple(d for d in os.environ.get("DVS_EMU_DEFINES", "").split(",") if d)   # e.g. DVS_TILE_ROWS=28
+    out = OUT if not defines else OUT.replace(".so", "_" + "_".join(d.replace("=", "").replace(".", "").lower() for d in defines) + ".so")
     newest = max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(CORE.replace("dvs_fused_core", "dvs_pair_core")))
     if not os.path.exists(out) or os.path.getmtime(out) < newest:
         subprocess.check_call(["g++", "-O2", "-march=native", "-std=c++17", "-shared", "-fPIC", *[f"-D{d}" for d in defines],
