@@ -94,6 +94,16 @@ struct ImgPtr {
     return ImgPtr{static_cast<const float*>(p) + e};
   }
 };
+// A pointer the compiler must treat as an opaque base (global address space): taps are then addressed as base + 32-bit
+// offset (one widening multiply-add each) instead of being re-derived from the kernel parameters as 64-bit add chains.
+template <class T>
+DVS_HD const T* opaque_global(const T* q) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+l"(q));
+  __builtin_assume(__isGlobal(q));
+#endif
+  return q;
+}
 template <bool BF16>
 DVS_HD float ld_disp(const float* d, int i) {
   if (BF16) return bf16_bits_to_float(reinterpret_cast<const unsigned short*>(d)[i]);
@@ -118,6 +128,20 @@ DVS_HD void disp_taps_load_t(const float* d, int dh, int dw, float sy, float sx,
   q.c = ld_disp<BF16>(d, y1 * dw + x0); q.e = ld_disp<BF16>(d, y1 * dw + x1);
 }
 
+// Each source image is addressed from one base pointer
+// the compiler must treat as opaque (otherwise it re-derives every tap address as a 64-bit add chain from the kernel
+// parameters, ~50 instructions per pixel) with 32-bit element offsets: one add + one widening multiply-add per (plane, row).
+template <bool U8>
+struct SrcPlanes {
+  ImgPtr<U8> b0, b1;
+  DVS_HD SrcPlanes(const FusedParams& p, int b, int HW) {
+    b0 = ImgPtr<U8>{p.src[0]}.off((size_t)b * 3 * HW);
+    b1 = ImgPtr<U8>{p.src[1]}.off((size_t)b * 3 * HW);
+    b0.p = opaque_global(b0.p);
+    b1.p = opaque_global(b1.p);
+  }
+};
+
 struct PairState {
   f2 ident[4];             // identity reprojection terms of the own pixels (scale independent), (source 0, source 1)
   int flags;               // bit j: pixel j inside the image; bit 4+j: pixel j belongs to R0 (own)
@@ -135,8 +159,10 @@ DVS_HD void pair_phase_load(const FusedParams& p, const Tile& t, float* sm, int 
   const PairLayout& L = P;
   const int HW = p.H * p.W;
   constexpr bool U8 = (IO & kIoImgU8) != 0;
-  const ImgPtr<U8> tgt = ImgPtr<U8>{p.target}.off((size_t)t.b * 3 * HW);
-  const ImgPtr<U8> sr0 = ImgPtr<U8>{p.src[0]}.off((size_t)t.b * 3 * HW), sr1 = ImgPtr<U8>{p.src[1]}.off((size_t)t.b * 3 * HW);
+  ImgPtr<U8> tgt = ImgPtr<U8>{p.target}.off((size_t)t.b * 3 * HW);
+  tgt.p = opaque_global(tgt.p);
+  const SrcPlanes<U8> im(p, t.b, HW);
+  const ImgPtr<U8> sr0 = im.b0, sr1 = im.b1;
   DVS_NOUNROLL
   for (int k = tid; k < PLANE; k += NT) {
     int ly = k / PW - 1, lx = k % PW - 1;
@@ -343,14 +369,14 @@ DVS_HD void project2(const f2* A, float u, float v, float D, float eps, int H, i
 }
 // the 24 taps of one pixel (both sources, three channels): issue only
 template <bool U8>
-DVS_HD void gather_taps2(ImgPtr<U8> im0, ImgPtr<U8> im1, int o0, int o1, int HW, int W, f2 (*tap)[4]) {
+DVS_HD void gather_taps2(const SrcPlanes<U8>& im, int o0, int o1, int HW, int W, f2 (*tap)[4]) {
   DVS_UNROLL
   for (int ch = 0; ch < 3; ++ch) {
-    const ImgPtr<U8> q0 = im0.off((size_t)(o0 + ch * HW)), q1 = im1.off((size_t)(o1 + ch * HW));
-    tap[ch][0] = f2{q0.at(0), q1.at(0)};
-    tap[ch][1] = f2{q0.at(1), q1.at(1)};
-    tap[ch][2] = f2{q0.at(W), q1.at(W)};
-    tap[ch][3] = f2{q0.at(W + 1), q1.at(W + 1)};
+    const int a0 = o0 + ch * HW, a1 = o1 + ch * HW;
+    tap[ch][0] = f2{im.b0.at(a0), im.b1.at(a1)};
+    tap[ch][1] = f2{im.b0.at(a0 + 1), im.b1.at(a1 + 1)};
+    tap[ch][2] = f2{im.b0.at(a0 + W), im.b1.at(a1 + W)};
+    tap[ch][3] = f2{im.b0.at(a0 + W + 1), im.b1.at(a1 + W + 1)};
   }
 }
 DVS_HD void lerp_store2(float* sm, int x2off, int k, f2 tx, f2 ty, const f2 (*tap)[4]) {
@@ -373,10 +399,10 @@ DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int 
   const int HW = p.H * p.W;
   const int dh = p.dh[s], dw = p.dw[s];
   constexpr bool U8 = (IO & kIoImgU8) != 0, BF = (IO & kIoDispBf16) != 0;
-  const float* d = disp_image<BF>(p.disp[s], (size_t)t.b * dh * dw);
+  const float* d = opaque_global(disp_image<BF>(p.disp[s], (size_t)t.b * dh * dw));
   const bool direct = dh == p.H && dw == p.W;
   const float scy = (float)dh / (float)p.H, scx = (float)dw / (float)p.W;
-  const ImgPtr<U8> im0 = ImgPtr<U8>{p.src[0]}.off((size_t)t.b * 3 * HW), im1 = ImgPtr<U8>{p.src[1]}.off((size_t)t.b * 3 * HW);
+  const SrcPlanes<U8> im(p, t.b, HW);
   const int x2off = P.x2(0);
 
   // R2 coordinates of pixel k = tid + NT it, advanced incrementally (NT = dq PW + dr); the reflected image coordinates
@@ -403,7 +429,7 @@ DVS_HD void pair_phase_warp(const FusedParams& p, const Tile& t, float* sm, int 
     Proj2 pr;
     project2(A, u, v, rcp_fast(fmaf(du, p.disp_range, p.min_disp)), p.eps, p.H, p.W, pr);
     f2 tap[3][4];
-    gather_taps2(im0, im1, pr.o0, pr.o1, HW, p.W, tap);   // all 24 tap loads of the pixel before the first use
+    gather_taps2(im, pr.o0, pr.o1, HW, p.W, tap);   // all 24 tap loads of the pixel before the first use
     lerp_store2(sm, x2off, k, pr.tx, pr.ty, tap);
   }
 }
@@ -589,7 +615,7 @@ DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int 
   }
 
   // chain through the bilinear gather and the projection (taps re-read; they are L1/L2 resident)
-  const ImgPtr<U8> im0 = ImgPtr<U8>{p.src[0]}.off((size_t)t.b * 3 * HW), im1 = ImgPtr<U8>{p.src[1]}.off((size_t)t.b * 3 * HW);
+  const SrcPlanes<U8> im(p, t.b, HW);
   DVS_NOUNROLL
   for (int j = 0; j < 4; ++j) {
     if (!((st.flags >> (4 + j)) & 1)) continue;
@@ -605,7 +631,7 @@ DVS_HD void pair_phase_grad(const FusedParams& p, const Tile& t, float* sm, int 
     Proj2 pr;
     project2(A, u, v, D, p.eps, p.H, p.W, pr);
     f2 tap[3][4];
-    gather_taps2(im0, im1, pr.o0, pr.o1, HW, p.W, tap);
+    gather_taps2(im, pr.o0, pr.o1, HW, p.W, tap);
     f2 gix = f2{0.f, 0.f}, giy = f2{0.f, 0.f};
     DVS_UNROLL
     for (int ch = 0; ch < 3; ++ch) {
