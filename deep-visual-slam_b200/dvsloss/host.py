@@ -22,12 +22,20 @@ from .ops import images_u8_to_f32
 class HostLossPipeline:
     def __init__(self, B: int, H: int, W: int, disp_sizes: Sequence[Sequence[int]], num_sources: int = 2, chunks=4,
                  device=None, uint8_images: bool = False, u8_in_kernel: bool = False, graph: bool = True, **loss_kwargs):
-        """``chunks``: a count (equal chunks) or a sequence of chunk sizes summing to B.  Chunk losses and gradients are combined
-        with the weights B_c / B, so unequal chunks are exact too; tapering the sizes (e.g. 5,4,3,2,2) shortens the part of the
-        step that cannot overlap the copy-in: the kernels and the copy-out of the LAST chunk.
+        """``chunks``: a count (equal chunks), a sequence of chunk sizes summing to B, "taper" or "ramp".  Chunk losses and gradients are
+        combined with the weights B_c / B, so unequal chunks are exact too; tapering the sizes (16 -> 6,4,3,2,1) shortens the part
+        of the step that cannot overlap the copy-in -- the kernels and the copy-out of the LAST chunk -- while keeping the number
+        of copies low (measured: profiles/r02_e2e_chunks.md).
         ``graph``: record the whole step -- every copy, kernel and cross-stream dependency -- as one CUDA graph the first time a
         given set of pinned buffers is seen and replay it afterwards: the step is then bound by the copy engines alone, not by
         ~150 host-side launches (the in-kernel noise counter is a device scalar, so replays keep drawing fresh noise)."""
+        if chunks in ("taper", "ramp"):                            # 16 -> 6, 4, 3, 2, 1: each chunk ~3/8 of what is left
+            sizes, rem = [], B
+            while rem:
+                sizes.append(-(-rem * 3 // 8))
+                rem -= sizes[-1]
+            # copy-bound steps (fp32 frames) want the short chunk LAST, kernel-bound ones (uint8 frames) want it FIRST
+            chunks = sizes if chunks == "taper" else sizes[::-1]
         if isinstance(chunks, int):
             if B % chunks:
                 raise ValueError("the batch must split into equal chunks (or give the chunk sizes)")
@@ -48,12 +56,20 @@ class HostLossPipeline:
         self.kw.setdefault("noise", "kernel")
         d = self.dev
         mk = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=d)
+        # the small operands (intrinsics, poses, every disparity map below a quarter of the image) cross in ONE copy each for the whole
+        # batch ahead of the first chunk; the chunks' tensors are slices of these buffers.  A copy has a fixed cost of a few
+        # microseconds on the copy engine whatever its size: 7 copies per chunk instead of 11+.
+        self.full = dict(K=mk(B, 4, 4), inv_K=mk(B, 4, 4), Ts=[mk(B, 4, 4) for _ in range(num_sources)],
+                         disps=[mk(B, 1, h, w) if 4 * h * w <= H * W else None for h, w in disp_sizes])
         self.sets: List[Dict] = []
-        for Bc in sizes:                                           # one staging set per chunk: H2D never waits for a free set
+        for st0, Bc in zip(self.starts, sizes):                    # one staging set per chunk: H2D never waits for a free set
+            sl = slice(st0, st0 + Bc)
+            leaf = lambda t: t[sl].detach().requires_grad_(True)
             self.sets.append(dict(
                 target=mk(Bc, 3, H, W), sources=[mk(Bc, 3, H, W) for _ in range(num_sources)],
-                disps=[mk(Bc, 1, h, w).requires_grad_(True) for h, w in disp_sizes], K=mk(Bc, 4, 4), inv_K=mk(Bc, 4, 4),
-                Ts=[mk(Bc, 4, 4).requires_grad_(True) for _ in range(num_sources)], losses=mk(1 + self.S),
+                disps=[(mk(Bc, 1, h, w).requires_grad_(True) if f is None else leaf(f))
+                       for (h, w), f in zip(disp_sizes, self.full["disps"])],
+                K=self.full["K"][sl], inv_K=self.full["inv_K"][sl], Ts=[leaf(t) for t in self.full["Ts"]], losses=mk(1 + self.S),
                 raw=[torch.empty(Bc, 3, H, W, dtype=torch.uint8, device=d) for _ in range(1 + num_sources)] if uint8_images else None))
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(d) for _ in range(3))
         self.graph_enabled = bool(graph)
@@ -98,6 +114,12 @@ class HostLossPipeline:
             st.wait_stream(cur)
         parts = []
         with torch.cuda.stream(self.s_in), torch.no_grad():
+            F = self.full
+            F["K"].copy_(h_in["K"], non_blocking=True)
+            F["inv_K"].copy_(h_in["inv_K"], non_blocking=True)
+            for a, b in zip(F["Ts"] + F["disps"], h_in["Ts"] + h_in["disps"]):
+                if a is not None:
+                    a.copy_(b, non_blocking=True)
             for c in range(C):
                 S_ = self.sets[c]
                 sl = slice(self.starts[c], self.starts[c] + self.sizes[c])
@@ -111,10 +133,9 @@ class HostLossPipeline:
                     S_["target"].copy_(h_in["target"][sl], non_blocking=True)
                     for a, b in zip(S_["sources"], h_in["sources"]):
                         a.copy_(b[sl], non_blocking=True)
-                S_["K"].copy_(h_in["K"][sl], non_blocking=True)
-                S_["inv_K"].copy_(h_in["inv_K"][sl], non_blocking=True)
-                for a, b in zip(S_["disps"] + S_["Ts"], h_in["disps"] + h_in["Ts"]):
-                    a.copy_(b[sl], non_blocking=True)
+                for a, b, f in zip(S_["disps"], h_in["disps"], F["disps"]):
+                    if f is None:                                  # the large disparity maps travel with their chunk
+                        a.copy_(b[sl], non_blocking=True)
                 self.ev_in[c].record(self.s_in)
         for c in range(C):
             S_ = self.sets[c]

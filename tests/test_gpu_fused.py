@@ -502,14 +502,15 @@ def test_host_pipeline_unequal_chunks_are_exact():
     h_in = dict(target=pin(p["target"]), sources=[pin(s) for s in p["sources"]], disps=[pin(d) for d in p["disps"]],
                 K=pin(p["K"]), inv_K=pin(p["inv_K"]), Ts=[pin(T) for T in Ts])
     outs = []
-    for chunks in (1, [5, 2, 1]):
+    for chunks in (1, [5, 2, 1], "taper", "ramp"):
         h_out = dict(loss=torch.empty(5).pin_memory(), gd=[torch.empty_like(d).pin_memory() for d in h_in["disps"]],
                      gT=[torch.empty_like(T).pin_memory() for T in h_in["Ts"]])
         HostLossPipeline(B, H, W, [tuple(d.shape[2:]) for d in h_in["disps"]], 2, chunks=chunks, device=dev, noise=None).run(h_in, h_out)
         outs.append(h_out)
-    np.testing.assert_allclose(outs[1]["loss"].numpy(), outs[0]["loss"].numpy(), rtol=2e-6)
-    for a, b in zip(outs[1]["gd"] + outs[1]["gT"], outs[0]["gd"] + outs[0]["gT"]):
-        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())      # the weights 5/8, 2/8, 1/8 round once more
+    for o in outs[1:]:
+        np.testing.assert_allclose(o["loss"].numpy(), outs[0]["loss"].numpy(), rtol=2e-6)
+        for a, b in zip(o["gd"] + o["gT"], outs[0]["gd"] + outs[0]["gT"]):
+            assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())      # the weights 5/8, 2/8, 1/8 round once more
 
 
 def test_host_pipeline_graph_replay_matches_eager_enqueue():
