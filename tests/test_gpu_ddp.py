@@ -86,3 +86,29 @@ def test_two_rank_nccl_training_matches_single_rank_global_batch(tmp_path):
     scale = float(ref.abs().max())
     assert float((got["grads"] - ref).abs().max()) <= 1e-4 * scale, float((got["grads"] - ref).abs().max()) / scale
     assert torch.isfinite(torch.tensor(got["loss"])) and torch.isfinite(torch.tensor(loss))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_two_devices_in_one_process_give_the_same_bits():
+    """The library keeps its per-kernel set-up (dynamic shared-memory opt-in) and its workspaces per device ordinal: the
+    fused loss called on cuda:0 and then on cuda:1 from ONE process gives bit-identical losses and gradients."""
+    from dvsloss import view_synthesis_loss
+    from dvsloss.synthetic import make_problem, pose_matrix
+    B, H, W = 2, 96, 128
+    p = make_problem(B, H, W, 2, 4, seed=21, consistent=True)
+    outs = []
+    for d in (0, 1, 0):
+        dev = torch.device("cuda", d)
+        with torch.cuda.device(dev):
+            mv = lambda v: v.to(dev) if torch.is_tensor(v) else ([mv(t) for t in v] if isinstance(v, (list, tuple)) else v)
+            q = {k: mv(v) for k, v in p.items() if k != "sample"}
+            Ts = [pose_matrix(a.view(B, 3), t.view(B, 3), inv).to(dev).requires_grad_(True)
+                  for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+            disps = [x.clone().requires_grad_(True) for x in q["disps"]]
+            loss, per_scale = view_synthesis_loss(disps, q["target"], q["sources"], q["K"], q["inv_K"], Ts, noise=None)
+            loss.backward()
+            torch.cuda.synchronize(dev)
+            outs.append([loss.detach().cpu(), per_scale.detach().cpu()] + [x.grad.cpu() for x in disps + Ts])
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
