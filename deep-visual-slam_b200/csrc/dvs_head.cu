@@ -292,3 +292,153 @@ extern "C" int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int di
   DVS_CUDA_TRY(cudaGetLastError());
   return DVS_OK;
 }
+
+// ================================================================================================ decoder glue
+// The element-wise tail between the two convolutions of a decoder stage (model/depthnet.py:77-84, model/layers.py:106-117,
+// 196-199): out = cat([nearest_up2(ELU(x)), skip], channel axis), channels-last, one pass.  Stock PyTorch runs ELU, the
+// up-sampling and the concatenation as three kernels with two intermediate tensors; backward likewise (slice copies, the 2x2
+// sum of the up-sampling, the ELU derivative).  Pure HBM streaming: every thread moves one 16-byte vector.
+namespace dvs {
+
+template <bool BF>
+struct Vec16 {
+  uint4 raw;
+  static constexpr int N = BF ? 8 : 4;
+  __device__ float get(int i) const {
+    if (BF) {
+      const unsigned int w = (&raw.x)[i >> 1];
+      return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
+    }
+    return __uint_as_float((&raw.x)[i]);
+  }
+  __device__ void set_all(const float* v) {
+    if (BF) {
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        (&raw.x)[i] = *reinterpret_cast<const unsigned int*>(&h);
+      }
+    } else {
+      for (int i = 0; i < 4; ++i) (&raw.x)[i] = __float_as_uint(v[i]);
+    }
+  }
+};
+
+__device__ __forceinline__ float elu_value(float a) { return a <= 0.f ? expf(a) - 1.f : a; }          // ATen elu_kernel, alpha = scale = 1
+__device__ __forceinline__ float elu_slope(float a) { return a <= 0.f ? expf(a) : 1.f; }              // ATen elu_backward_kernel (is_result = false)
+
+// one thread per 16-byte vector of `out` [B, 2h, 2w, C1 + C2]
+template <bool BF>
+__global__ void __launch_bounds__(256) elu_up2_cat_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip,
+                                                              uint4* __restrict__ out, int h, int w, int v1, int v2,
+                                                              size_t nvec) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nvec) return;
+  const int vt = v1 + v2;
+  const size_t pix = e / vt;
+  const int v = (int)(e - pix * vt);
+  if (v >= v1) {
+    out[e] = skip[pix * v2 + (v - v1)];
+    return;
+  }
+  const int W2 = 2 * w, H2 = 2 * h;
+  const int X = (int)(pix % W2);
+  const size_t r = pix / W2;
+  const int Y = (int)(r % H2);
+  const size_t b = r / H2;
+  Vec16<BF> a;
+  a.raw = x[((b * h + (Y >> 1)) * w + (X >> 1)) * v1 + v];
+  float f[Vec16<BF>::N];
+  for (int i = 0; i < Vec16<BF>::N; ++i) f[i] = elu_value(a.get(i));
+  Vec16<BF> o;
+  o.set_all(f);
+  out[e] = o.raw;
+}
+
+// one thread per 16-byte vector of grad_x [B, h, w, C1]: 2x2 sum of grad_out (fixed order) times ELU'(x)
+template <bool BF>
+__global__ void __launch_bounds__(256) elu_up2_cat_bwd_x_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gout,
+                                                                uint4* __restrict__ gx, int h, int w, int v1, int v2,
+                                                                size_t nvec) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nvec) return;
+  const size_t pix = e / v1;
+  const int v = (int)(e - pix * v1);
+  const int xx = (int)(pix % w);
+  const size_t r = pix / w;
+  const int yy = (int)(r % h);
+  const size_t b = r / h;
+  const int vt = v1 + v2, W2 = 2 * w;
+  const size_t o00 = ((b * 2 * h + 2 * yy) * W2 + 2 * xx) * vt + v;
+  Vec16<BF> g00, g01, g10, g11, a;
+  g00.raw = gout[o00];
+  g01.raw = gout[o00 + vt];
+  g10.raw = gout[o00 + (size_t)W2 * vt];
+  g11.raw = gout[o00 + (size_t)W2 * vt + vt];
+  a.raw = x[e];
+  float f[Vec16<BF>::N];
+  for (int i = 0; i < Vec16<BF>::N; ++i) f[i] = ((g00.get(i) + g01.get(i)) + (g10.get(i) + g11.get(i))) * elu_slope(a.get(i));
+  Vec16<BF> o;
+  o.set_all(f);
+  gx[e] = o.raw;
+}
+
+// one thread per 16-byte vector of grad_skip [B, 2h, 2w, C2]: the channel slice of grad_out
+__global__ void __launch_bounds__(256) cat_bwd_skip_kernel(const uint4* __restrict__ gout, uint4* __restrict__ gskip, int v1,
+                                                           int v2, size_t nvec) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nvec) return;
+  const size_t pix = e / v2;
+  const int v = (int)(e - pix * v2);
+  gskip[e] = gout[pix * (v1 + v2) + v1 + v];
+}
+
+static int glue_check(const void* x, int dtype, int B, int C1, int C2, int h, int w, const void* skip) {
+  if (!x || B < 1 || h < 1 || w < 1 || C1 < 1 || C2 < 0) return DVS_EINVAL;
+  if (dtype != DVS_DTYPE_F32 && dtype != DVS_DTYPE_BF16) return DVS_EINVAL;
+  const int per = dtype == DVS_DTYPE_BF16 ? 8 : 4;
+  if (C1 % per || C2 % per) return DVS_EINVAL;
+  if ((C2 > 0) != (skip != nullptr)) return DVS_EINVAL;
+  if (((uintptr_t)x & 15) || ((uintptr_t)skip & 15)) return DVS_EINVAL;
+  return DVS_OK;
+}
+
+}  // namespace dvs
+
+extern "C" int dvs_elu_up2_cat_fwd(const void* x, const void* skip, void* out, int dtype, int B, int C1, int C2, int h, int w,
+                                   void* stream) {
+  using namespace dvs;
+  int rc = glue_check(x, dtype, B, C1, C2, h, w, skip);
+  if (rc) return rc;
+  if (!out || ((uintptr_t)out & 15)) return DVS_EINVAL;
+  const bool bf = dtype == DVS_DTYPE_BF16;
+  const int per = bf ? 8 : 4, v1 = C1 / per, v2 = C2 / per;
+  const size_t nvec = (size_t)B * 4 * h * w * (v1 + v2);
+  const unsigned int nblk = (unsigned int)((nvec + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bf) elu_up2_cat_fwd_kernel<true><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, (uint4*)out, h, w, v1, v2, nvec);
+  else elu_up2_cat_fwd_kernel<false><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, (uint4*)out, h, w, v1, v2, nvec);
+  DVS_CUDA_TRY(cudaGetLastError());
+  return DVS_OK;
+}
+
+extern "C" int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, void* grad_x, void* grad_skip, int dtype, int B, int C1,
+                                   int C2, int h, int w, void* stream) {
+  using namespace dvs;
+  int rc = glue_check(x, dtype, B, C1, C2, h, w, C2 > 0 ? grad_skip : nullptr);
+  if (rc) return rc;
+  if (!grad_out || !grad_x || ((uintptr_t)grad_out & 15) || ((uintptr_t)grad_x & 15)) return DVS_EINVAL;
+  const bool bf = dtype == DVS_DTYPE_BF16;
+  const int per = bf ? 8 : 4, v1 = C1 / per, v2 = C2 / per;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nx = (size_t)B * h * w * v1;
+  const unsigned int bx = (unsigned int)((nx + 255) / 256);
+  if (bf) elu_up2_cat_bwd_x_kernel<true><<<bx, 256, 0, st>>>((const uint4*)x, (const uint4*)grad_out, (uint4*)grad_x, h, w, v1, v2, nx);
+  else elu_up2_cat_bwd_x_kernel<false><<<bx, 256, 0, st>>>((const uint4*)x, (const uint4*)grad_out, (uint4*)grad_x, h, w, v1, v2, nx);
+  DVS_CUDA_TRY(cudaGetLastError());
+  if (v2 > 0) {
+    const size_t ns = (size_t)B * 4 * h * w * v2;
+    cat_bwd_skip_kernel<<<(unsigned int)((ns + 255) / 256), 256, 0, st>>>((const uint4*)grad_out, (uint4*)grad_skip, v1, v2, ns);
+    DVS_CUDA_TRY(cudaGetLastError());
+  }
+  return DVS_OK;
+}

@@ -413,6 +413,62 @@ def disp_head_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dim() == 4 and x.shape[1] % 8 == 0 and 8 <= x.shape[1] <= 128 and x.shape[2] >= 3 and x.shape[3] >= 3
 
 
+# ---------------------------------------------------------------------------------------------------- DepthNet decoder glue
+class _EluUp2Cat(torch.autograd.Function):
+    """cat([nearest_up2(ELU(x)), skip], 1) in one pass, channels-last (model/depthnet.py:77-84, model/layers.py:106-117,196-199)."""
+
+    @staticmethod
+    def forward(ctx, x, skip):
+        from ._lib import DTYPE_BF16, DTYPE_F32
+        B, C1, h, w = x.shape
+        C2 = 0 if skip is None else skip.shape[1]
+        xc = x.contiguous(memory_format=torch.channels_last)
+        sc = None if skip is None else skip.contiguous(memory_format=torch.channels_last)
+        out = torch.empty(B, C1 + C2, 2 * h, 2 * w, dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        code = DTYPE_BF16 if x.dtype == torch.bfloat16 else DTYPE_F32
+        with torch.cuda.device(x.device):
+            check(lib().dvs_elu_up2_cat_fwd(xc.data_ptr(), 0 if sc is None else sc.data_ptr(), out.data_ptr(), code, B, C1, C2, h, w,
+                                            stream_ptr(x.device)), "dvs_elu_up2_cat_fwd")
+        ctx.save_for_backward(xc)
+        ctx.C2, ctx.code = C2, code
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        B, C1, h, w = xc.shape
+        C2 = ctx.C2
+        g = g.to(xc.dtype).contiguous(memory_format=torch.channels_last)
+        gx = torch.empty_like(xc, memory_format=torch.channels_last)
+        gs = torch.empty(B, C2, 2 * h, 2 * w, dtype=xc.dtype, device=xc.device, memory_format=torch.channels_last) if C2 else None
+        with torch.cuda.device(xc.device):
+            check(lib().dvs_elu_up2_cat_bwd(xc.data_ptr(), g.data_ptr(), gx.data_ptr(), 0 if gs is None else gs.data_ptr(), ctx.code,
+                                            B, C1, C2, h, w, stream_ptr(xc.device)), "dvs_elu_up2_cat_bwd")
+        return gx, gs
+
+
+def elu_up2_cat_supported(x: torch.Tensor, skip=None) -> bool:
+    if not (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16)):
+        return False
+    per = 8 if x.dtype == torch.bfloat16 else 4
+    if x.shape[1] % per:
+        return False
+    if skip is None:
+        return True
+    return (skip.is_cuda and skip.dtype == x.dtype and skip.shape[1] % per == 0 and skip.shape[0] == x.shape[0]
+            and tuple(skip.shape[2:]) == (2 * x.shape[2], 2 * x.shape[3]))
+
+
+def elu_up2_cat(x: torch.Tensor, skip=None) -> torch.Tensor:
+    """``torch.cat([F.interpolate(F.elu(x), scale_factor=2, mode="nearest"), skip], 1)`` (``skip`` optional) as one kernel each
+    way; x [B,C1,h,w] is the decoder convolution's output BEFORE its ELU, skip [B,C2,2h,2w] the encoder feature.  Channels-last
+    memory is read in place; the result is channels-last."""
+    if not elu_up2_cat_supported(x, skip):
+        raise DvsError("elu_up2_cat needs CUDA fp32 / bf16 tensors of one dtype, channels a multiple of 4 (fp32) / 8 (bf16), "
+                       "skip of twice the spatial size")
+    return _EluUp2Cat.apply(x, skip)
+
+
 # ---------------------------------------------------------------------------------------------------- supervised depth
 class _Silog(torch.autograd.Function):
     @staticmethod

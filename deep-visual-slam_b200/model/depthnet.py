@@ -11,13 +11,16 @@ import torch
 import torch.nn as nn
 
 from .layers import Conv3x3, ConvBlock, upsample            # (puts the package root on sys.path for dvsloss)
-from dvsloss.ops import disp_head, disp_head_supported  # noqa: E402
+from dvsloss.ops import disp_head, disp_head_supported, elu_up2_cat, elu_up2_cat_supported  # noqa: E402
 from .resnet_encoder import ResnetEncoder
 
 
 class DepthNet(nn.Module):
     # the ("dispconv", s) + sigmoid tails run as one fused kernel on CUDA (dvsloss.ops.disp_head); False = stock modules
     fused_heads = True
+    # ELU of ("upconv", i, 0) + nearest up-sampling + concatenation with the encoder skip as one kernel each way
+    # (dvsloss.ops.elu_up2_cat); False = the stock three-op sequence
+    fused_glue = True
 
     def __init__(self, num_layers: int = 18, pretrained: bool = True, num_input_images: int = 1, scales=range(4),
                  num_output_channels: int = 1, use_skips: bool = True):
@@ -47,9 +50,15 @@ class DepthNet(nn.Module):
         outputs = {}
         x = feats[-1]
         for i in range(4, -1, -1):
-            x = upsample(self.convs[("upconv", i, 0)](x))
-            if self.use_skips and i > 0:
-                x = torch.cat([x, feats[i - 1]], 1)
+            block = self.convs[("upconv", i, 0)]
+            skip = feats[i - 1] if self.use_skips and i > 0 else None
+            pre = block.conv(x) if self.fused_glue and x.is_cuda else None
+            if pre is not None and elu_up2_cat_supported(pre, skip):
+                x = elu_up2_cat(pre, skip)
+            else:
+                x = upsample(block.nonlin(pre) if pre is not None else block(x))
+                if skip is not None:
+                    x = torch.cat([x, skip], 1)
             x = self.convs[("upconv", i, 1)](x)
             if i in self.scales:
                 head = self.convs[("dispconv", i)]

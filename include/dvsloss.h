@@ -254,6 +254,17 @@ int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int disp_dtype, c
                       const float* weight, void* grad_x, float* grad_weight, float* grad_bias, int B, int C, int H, int W,
                       void* workspace, void* stream);
 
+/* Decoder glue of DepthNet, fused (model/depthnet.py:77-84: ConvBlock's ELU, model/layers.py:106-117; `upsample`,
+ * model/layers.py:196-199; torch.cat with the encoder skip): out = cat([nearest_up2(ELU(x)), skip], channels), one pass.
+ * CHANNELS-LAST tensors of one dtype (fp32 or bf16), 16-byte aligned: x [B,h,w,C1] (the convolution output BEFORE the ELU),
+ * skip [B,2h,2w,C2] (NULL iff C2 == 0), out [B,2h,2w,C1+C2]; C1, C2 multiples of 8 (bf16) / 4 (fp32). */
+int dvs_elu_up2_cat_fwd(const void* x, const void* skip, void* out, int dtype, int B, int C1, int C2, int h, int w,
+                        void* stream);
+/* Backward: grad_out [B,2h,2w,C1+C2] -> grad_x [B,h,w,C1] = ELU'(x) * (2x2 sum of grad_out, fp32, fixed order) and
+ * grad_skip [B,2h,2w,C2] (NULL iff C2 == 0). */
+int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, void* grad_x, void* grad_skip, int dtype, int B, int C1, int C2,
+                        int h, int w, void* stream);
+
 /* Supervised-depth path (depth/depth_learner.py).  SILog loss (:75-95): over the n elements with valid[e] != 0,
  * d = log(max(pred, 1e-6)) - log(target), loss = sqrt(mean(d^2) - variance_focus * mean(d)^2).  stats [4] receives
  * {loss, mean(d), count, mean(d^2)} (kept for the backward); sums in double, fixed order.  The multi-scale loss around it

@@ -90,3 +90,80 @@ def test_depthnet_uses_the_fused_head_and_trains_like_the_stock_net():
     for n, gr in outs[False][1].items():
         scale = float(gr.abs().max()) + 1e-12
         assert float((outs[True][1][n] - gr).abs().max()) <= 1e-3 * scale, n
+
+
+def _stock_glue(x, skip):
+    y = F.interpolate(F.elu(x), scale_factor=2, mode="nearest")
+    return y if skip is None else torch.cat([y, skip], 1)
+
+
+@pytest.mark.parametrize("B,C1,C2,h,w", [(2, 16, 0, 12, 16), (2, 32, 64, 6, 8), (1, 256, 256, 2, 3), (3, 64, 64, 5, 7), (1, 4, 8, 3, 2)])
+@pytest.mark.parametrize("channels_last", [True, False])
+def test_elu_up2_cat_fp32_matches_stock_ops(B, C1, C2, h, w, channels_last):
+    """ConvBlock's ELU + nearest x2 + concatenation with the skip (model/depthnet.py:77-84) as one kernel each way: the
+    forward is a copy of fp32 values and one expf - 1 (ATen's formula); the backward adds four gradients in a fixed order."""
+    from dvsloss.ops import elu_up2_cat
+    torch.manual_seed(C1 + h)
+    dev = torch.device("cuda:0")
+    x = torch.randn(B, C1, h, w, device=dev)
+    skip = torch.randn(B, C2, 2 * h, 2 * w, device=dev) if C2 else None
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+        skip = skip.contiguous(memory_format=torch.channels_last) if skip is not None else None
+    leaves = [t.requires_grad_(True) for t in (x, skip) if t is not None]
+    got = elu_up2_cat(x, skip)
+    ref = _stock_glue(x, skip)
+    assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert float((got - ref).abs().max()) <= 2e-7
+    g = torch.randn_like(ref)
+    gg = torch.autograd.grad(got, leaves, g)
+    gr = torch.autograd.grad(ref, leaves, g)
+    for a, r in zip(gg, gr):
+        assert float((a - r).abs().max()) <= 1e-6 * (float(r.abs().max()) + 1e-30)
+    assert all(torch.equal(a, b_) for a, b_ in zip(gg, torch.autograd.grad(elu_up2_cat(x, skip), leaves, g)))
+
+
+def test_elu_up2_cat_bf16_matches_stock_ops_within_rounding():
+    from dvsloss.ops import elu_up2_cat
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    x = torch.randn(2, 64, 9, 11, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    skip = torch.randn(2, 64, 18, 22, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    got = elu_up2_cat(x, skip)
+    ref = _stock_glue(x, skip)
+    assert got.dtype == torch.bfloat16
+    assert float((got.float() - ref.float()).abs().max()) <= 2 ** -8 * float(ref.float().abs().max())      # one bf16 rounding
+    g = torch.randn_like(ref)
+    gg = torch.autograd.grad(got, (x, skip), g)
+    # oracle: the same chain in float64 on the bf16 inputs
+    xd, sd = x.detach().double().requires_grad_(True), skip.detach().double().requires_grad_(True)
+    gr = torch.autograd.grad(_stock_glue(xd, sd), (xd, sd), g.double())
+    assert torch.equal(gg[1], g[:, 64:])                                                                   # a copy
+    assert float((gg[0].double() - gr[0]).abs().max()) <= 2 ** -7 * float(gr[0].abs().max())               # fp32 sum, one bf16 rounding
+
+
+def test_depthnet_fused_glue_trains_like_the_stock_sequence():
+    from model.depthnet import DepthNet
+    torch.manual_seed(2)
+    dev = torch.device("cuda:0")
+    net = DepthNet(18, False).to(dev).eval().to(memory_format=torch.channels_last)
+    x = torch.rand(2, 3, 64, 96, device=dev).contiguous(memory_format=torch.channels_last)
+    outs = {}
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    for fused in (True, False):
+        DepthNet.fused_glue = fused
+        try:
+            net.zero_grad()
+            o = net(x)
+            sum(v.mean() for v in o.values()).backward()
+            outs[fused] = ({k: v.detach().clone() for k, v in o.items()},
+                           {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None})
+        finally:
+            DepthNet.fused_glue = True
+    torch.backends.cudnn.allow_tf32 = tf32
+    for k in outs[False][0]:
+        assert torch.allclose(outs[True][0][k], outs[False][0][k], rtol=0, atol=5e-6), k
+    for n, gr in outs[False][1].items():
+        scale = float(gr.abs().max()) + 1e-12
+        assert float((outs[True][1][n] - gr).abs().max()) <= 1e-3 * scale, n
