@@ -81,24 +81,73 @@ def upsample(x: torch.Tensor) -> torch.Tensor:
     return F.interpolate(x, scale_factor=2, mode="nearest")
 
 
-def conv3x3_reflect(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
-    """``conv2d(ReflectionPad2d(1)(x), weight, bias)`` without the padded copy of ``x``.
+def _conv_bwd(g, inp, w, padding, mask):
+    return torch.ops.aten.convolution_backward(g, inp, w, None, [1, 1], list(padding), [1, 1], False, [0, 0], 1, [mask[0], mask[1], False])
 
-    The reference pads every decoder activation (model/layers.py:126-136): a full read + write of the tensor forward and a
-    scatter-add pass backward, 12 % of the CUDA time of a training step (profiles/r01 train profile).  The padded
-    convolution equals the ZERO-padded one (cuDNN's native mode, no copy) plus what the reflected ring contributes to the
-    outermost output rows / columns, which are four thin stock convolutions on single rows / columns of ``x``:
+
+class _Conv3x3Reflect(torch.autograd.Function):
+    """``conv2d(ReflectionPad2d(1)(x), weight, bias)`` without the padded copy of ``x`` -- forward AND backward.
+
+    The padded convolution equals the ZERO-padded one (cuDNN's native mode, no copy) plus what the reflected ring contributes
+    to the outermost output rows / columns, which are four thin stock convolutions on single rows / columns of ``x``:
         top row    += conv(reflect_w(x[row 1]),   w[ky = 0])      bottom row   += conv(reflect_w(x[row H-2]), w[ky = 2])
         left col   += conv(x[col 1],   w[kx = 0], zero pad in y)   right col    += conv(x[col W-2], w[kx = 2], zero pad in y)
-    (the corner taps belong to the row strips).  Same weights, same checkpoints; autograd differentiates the strips."""
-    H, W = x.shape[2:]
-    out = F.conv2d(x, weight, bias, padding=1)
-    rw = lambda t: F.pad(t, (1, 1, 0, 0), mode="reflect")
-    out[:, :, 0:1] += F.conv2d(rw(x[:, :, 1:2]), weight[:, :, 0:1])
-    out[:, :, H - 1:H] += F.conv2d(rw(x[:, :, H - 2:H - 1]), weight[:, :, 2:3])
-    out[:, :, :, 0:1] += F.conv2d(x[:, :, :, 1:2], weight[:, :, :, 0:1], padding=(1, 0))
-    out[:, :, :, W - 1:W] += F.conv2d(x[:, :, :, W - 2:W - 1], weight[:, :, :, 2:3], padding=(1, 0))
-    return out
+    (the corner taps belong to the row strips).  The backward is written out the same way -- one full convolution backward
+    plus four thin ones added into single rows / columns of the gradients -- because autograd's own derivative of the
+    slice-and-add formulation materialises a zero-filled full-size tensor and a full-size add for every strip (14 % of the
+    CUDA time of a training step, profiles/r02 train profile)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        if torch.is_autocast_enabled(x.device.type):            # what autocast would feed the convolution
+            dt = torch.get_autocast_dtype(x.device.type)
+            x = x.to(dt)
+        w = weight.to(x.dtype)
+        b = bias.to(x.dtype) if bias is not None else None
+        H, W = x.shape[2:]
+        rw = lambda t: F.pad(t, (1, 1, 0, 0), mode="reflect")
+        out = F.conv2d(x, w, b, padding=1)
+        out[:, :, 0:1] += F.conv2d(rw(x[:, :, 1:2]), w[:, :, 0:1])
+        out[:, :, H - 1:H] += F.conv2d(rw(x[:, :, H - 2:H - 1]), w[:, :, 2:3])
+        out[:, :, :, 0:1] += F.conv2d(x[:, :, :, 1:2], w[:, :, :, 0:1], padding=(1, 0))
+        out[:, :, :, W - 1:W] += F.conv2d(x[:, :, :, W - 2:W - 1], w[:, :, :, 2:3], padding=(1, 0))
+        ctx.save_for_backward(x, w)
+        ctx.wdtype = weight.dtype
+        ctx.bdtype = bias.dtype if bias is not None else None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        H, W = x.shape[2:]
+        need_x, need_w, need_b = ctx.needs_input_grad
+        g = g.to(x.dtype)
+        mask = (need_x, need_w)
+        gx, gw, _ = _conv_bwd(g, x, w, (1, 1), mask)
+        rw = lambda t: F.pad(t, (1, 1, 0, 0), mode="reflect")
+        # row strips: reflect_w's adjoint folds the two pad columns back onto columns 1 and W-2
+        for row, ky, orow in ((1, 0, 0), (H - 2, 2, H - 1)):
+            gi, gk, _ = _conv_bwd(g[:, :, orow:orow + 1], rw(x[:, :, row:row + 1]), w[:, :, ky:ky + 1], (0, 0), mask)
+            if need_x:
+                gi[..., 2] += gi[..., 0]
+                gi[..., W - 1] += gi[..., W + 1]
+                gx[:, :, row:row + 1] += gi[..., 1:W + 1]
+            if need_w:
+                gw[:, :, ky:ky + 1] += gk
+        for col, kx, ocol in ((1, 0, 0), (W - 2, 2, W - 1)):
+            gi, gk, _ = _conv_bwd(g[:, :, :, ocol:ocol + 1], x[:, :, :, col:col + 1], w[:, :, :, kx:kx + 1], (1, 0), mask)
+            if need_x:
+                gx[:, :, :, col:col + 1] += gi
+            if need_w:
+                gw[:, :, :, kx:kx + 1] += gk
+        gb = g.sum((0, 2, 3)).to(ctx.bdtype) if (need_b and ctx.bdtype is not None) else None
+        return gx, (gw.to(ctx.wdtype) if need_w else None), gb
+
+
+def conv3x3_reflect(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
+    """``conv2d(ReflectionPad2d(1)(x), weight, bias)`` (reference: model/layers.py:126-136) without the padded copy; same
+    weights, same checkpoints.  See ``_Conv3x3Reflect``."""
+    return _Conv3x3Reflect.apply(x, weight, bias)
 
 
 class Conv3x3(nn.Module):
