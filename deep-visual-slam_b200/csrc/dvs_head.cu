@@ -213,6 +213,337 @@ __global__ void __launch_bounds__(256) disp_head_reduce_kernel(const float* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ tile kernels
+// C = 8 LP channels with LP a power of two (DepthNet: 16, 32, 64, 128).  A block owns a 32 x 8 tile of pixels; LP lanes of a
+// warp share one pixel, each owning 8 channels, so a warp-wide 128-bit access covers 32 / LP whole pixels contiguously (the
+// thread-per-pixel kernels above stride their lanes by C elements and fetch every activation nine times).  The lane's 72
+// weights (or 72 weight-gradient accumulators) live in registers.
+//   forward : every activation of the tile + halo (34 x 10) is read ONCE and turned into its nine partial dot products
+//             (one per tap) in shared memory; the outputs then add nine scalars each.
+//   backward: d loss / d pre-activation of the tile + halo goes to shared memory once; the nine tap sums of a pixel are then
+//             shared-memory reads.  grad_x and grad_w are separate kernels (72 registers of weights / of accumulators each).
+constexpr int kTileW = 32, kTileH = 8, kHaloW = kTileW + 2, kHaloH = kTileH + 2, kHaloN = kHaloW * kHaloH;
+
+struct HeadTile {
+  int b, y0, x0;
+};
+__device__ __forceinline__ HeadTile head_tile(int t, int tiles_x, int tiles_y) {
+  HeadTile r;
+  r.b = t / (tiles_x * tiles_y);
+  const int q = t - r.b * tiles_x * tiles_y;
+  r.y0 = (q / tiles_x) * kTileH;
+  r.x0 = (q % tiles_x) * kTileW;
+  return r;
+}
+template <int LP>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LP >> 1; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// a lane's 8 channels as loaded (the conversion is deferred so that several loads can be in flight per thread: with one
+// dependent load per warp at a time these kernels ran at 1 TB/s, Little's law on 16 warps per SM)
+template <bool BF>
+struct Raw8 {
+  uint4 a, b;                                                // b: second half of 8 floats; unused for bf16
+};
+template <bool BF>
+__device__ __forceinline__ Raw8<BF> raw_load(const void* base, size_t elem) {
+  Raw8<BF> r;
+  if (BF) {
+    r.a = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + elem);
+    r.b = r.a;
+  } else {
+    r.a = *reinterpret_cast<const uint4*>(static_cast<const float*>(base) + elem);
+    r.b = *reinterpret_cast<const uint4*>(static_cast<const float*>(base) + elem + 4);
+  }
+  return r;
+}
+template <bool BF>
+__device__ __forceinline__ void raw_unpack(const Raw8<BF>& r, float* v) {
+  if (BF) {
+    const unsigned int w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[2 * k] = __uint_as_float(w[k] << 16);
+      v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+  } else {
+    v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+    v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+  }
+}
+// the lane's 72 weights w[c][t], c = 8 sub .. 8 sub + 7: consecutive in the Conv2d weight [1,C,3,3]
+__device__ __forceinline__ void load_lane_weights(const float* __restrict__ w, int sub, float (*wr)[8]) {
+  float f[72];
+  const float* q = w + sub * 72;
+  if (((uintptr_t)w & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      const float4 t = reinterpret_cast<const float4*>(q)[i];
+      f[4 * i] = t.x; f[4 * i + 1] = t.y; f[4 * i + 2] = t.z; f[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 72; ++i) f[i] = q[i];
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[t][k] = f[k * 9 + t];
+}
+
+template <bool XBF, bool DBF, int LP>
+__global__ void __launch_bounds__(kHeadThreads) disp_head_fwd_tile_kernel(const void* __restrict__ x, const float* __restrict__ w,
+                                                                          const float* __restrict__ bias, void* __restrict__ disp,
+                                                                          int H, int W, int tiles_x, int tiles_y) {
+  constexpr int C = 8 * LP, PPI = kHeadThreads / LP;         // pixels per pass of the block
+  constexpr int NPASS = (kHaloN + PPI - 1) / PPI, U = NPASS < 6 ? NPASS : 6;
+  __shared__ float pt[9][kHaloN + 4];
+  const int sub = threadIdx.x & (LP - 1), pl = threadIdx.x / LP;
+  float wr[9][8];
+  load_lane_weights(w, sub, wr);
+  const HeadTile T = head_tile(blockIdx.x, tiles_x, tiles_y);
+  const size_t img = (size_t)T.b * H * W;
+  // partial dot products of the halo region; positions outside the image hold the REFLECTED pixel's values
+#pragma unroll 1
+  for (int p0 = 0; p0 < NPASS; p0 += U) {
+    Raw8<XBF> r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {                             // up to six 16-byte loads in flight per thread
+      const int q = (p0 + u) * PPI + pl;
+      const int qq = q < kHaloN ? q : kHaloN - 1;
+      const int ly = qq / kHaloW, lx = qq - ly * kHaloW;
+      int gy = reflect1(T.y0 + ly - 1, H), gx = reflect1(T.x0 + lx - 1, W);
+      gy = gy < 0 ? 0 : (gy > H - 1 ? H - 1 : gy);            // tiles overhanging the image: any valid address
+      gx = gx < 0 ? 0 : (gx > W - 1 ? W - 1 : gx);
+      r[u] = raw_load<XBF>(x, (img + (size_t)gy * W + gx) * C + sub * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p0 + u >= NPASS) break;                             // block-uniform
+      const int q = (p0 + u) * PPI + pl;
+      float v[8];
+      raw_unpack<XBF>(r[u], v);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a = fmaf(v[k], wr[t][k], a);
+        a = group_sum<LP>(a);
+        if (q < kHaloN && sub == 0) pt[t][q] = a;
+      }
+    }
+  }
+  __syncthreads();
+  const int ox = threadIdx.x & 31, oy = threadIdx.x >> 5;
+  const int yy = T.y0 + oy, xx = T.x0 + ox;
+  if (yy < H && xx < W) {
+    float acc = bias ? bias[0] : 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) acc += pt[ky * 3 + kx][(oy + ky) * kHaloW + ox + kx];
+    store1<DBF>(disp, img + (size_t)yy * W + xx, 1.0f / (1.0f + __expf(-acc)));
+  }
+}
+
+// d loss / d pre-activation of the tile + halo -> shared memory (zero outside the image)
+template <bool GBF, bool DBF>
+__device__ __forceinline__ void stage_gpre(const void* gdisp, const void* disp, const HeadTile& T, size_t img, int H, int W, float* gp) {
+  for (int q = threadIdx.x; q < kHaloN; q += kHeadThreads) {
+    const int ly = q / kHaloW, lx = q - ly * kHaloW;
+    gp[q] = gpre<GBF, DBF>(gdisp, disp, img, T.y0 + ly - 1, T.x0 + lx - 1, H, W);
+  }
+}
+// the same in two steps: the operands of the NEXT tile are fetched into registers while the current tile is processed
+struct GpreRegs {
+  float g[2], d[2];
+};
+template <bool GBF, bool DBF>
+__device__ __forceinline__ void gpre_fetch(const void* gdisp, const void* disp, const HeadTile& T, size_t img, int H, int W, GpreRegs& r) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int q = threadIdx.x + i * kHeadThreads;
+    r.g[i] = 0.f; r.d[i] = 0.f;
+    if (q < kHaloN) {
+      const int ly = q / kHaloW, lx = q - ly * kHaloW;
+      const int yo = T.y0 + ly - 1, xo = T.x0 + lx - 1;
+      if (yo >= 0 && yo < H && xo >= 0 && xo < W) {
+        const size_t o = img + (size_t)yo * W + xo;
+        r.g[i] = load1<GBF>(gdisp, o);
+        r.d[i] = load1<DBF>(disp, o);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void gpre_store(const GpreRegs& r, float* gp) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int q = threadIdx.x + i * kHeadThreads;
+    if (q < kHaloN) gp[q] = r.g[i] * r.d[i] * (1.f - r.d[i]);
+  }
+}
+// the nine sums s[t] over the outputs that read input pixel (yy, xx) = tile position (oy, ox) through tap t: the regular one
+// plus the ones whose pad-ring tap folds here (all within one pixel: the halo)
+__device__ __forceinline__ void tap_sums(const float* gp, int oy, int ox, int yy, int xx, int H, int W, float* s) {
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int ry = oy + 1 - ky + 1;                          // halo row of output yy - ky + 1
+    const int fy = (ky == 0 && yy == 1) ? oy : ((ky == 2 && yy == H - 2) ? oy + 2 : -1);   // halo row of the folded output
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int rx = ox + 1 - kx + 1;
+      const int fx = (kx == 0 && xx == 1) ? ox : ((kx == 2 && xx == W - 2) ? ox + 2 : -1);
+      float a = gp[ry * kHaloW + rx];
+      if (fx >= 0) a += gp[ry * kHaloW + fx];
+      if (fy >= 0) {
+        a += gp[fy * kHaloW + rx];
+        if (fx >= 0) a += gp[fy * kHaloW + fx];
+      }
+      s[ky * 3 + kx] = a;
+    }
+  }
+}
+
+// grad_x[c] = sum_t w[c][t] s[t]; blocks persist over the tiles and fetch the next tile's operands while they work
+template <bool GBF, bool DBF, bool GXBF, int LP>
+__global__ void __launch_bounds__(kHeadThreads) disp_head_bwd_x_tile_kernel(const void* __restrict__ gdisp, const void* __restrict__ disp,
+                                                                            const float* __restrict__ w, void* __restrict__ gx, int H,
+                                                                            int W, int tiles_x, int tiles_y, int ntiles) {
+  constexpr int C = 8 * LP, PPI = kHeadThreads / LP;
+  __shared__ float gp[kHaloN];
+  const int sub = threadIdx.x & (LP - 1), pl = threadIdx.x / LP;
+  float wr[9][8];
+  load_lane_weights(w, sub, wr);
+  GpreRegs pre;
+  if ((int)blockIdx.x < ntiles) {
+    const HeadTile T0 = head_tile(blockIdx.x, tiles_x, tiles_y);
+    gpre_fetch<GBF, DBF>(gdisp, disp, T0, (size_t)T0.b * H * W, H, W, pre);
+  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const HeadTile T = head_tile(tile, tiles_x, tiles_y);
+    const size_t img = (size_t)T.b * H * W;
+    __syncthreads();                                          // the previous tile's readers are done with gp
+    gpre_store(pre, gp);
+    __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) {
+      const HeadTile Tn = head_tile(tile + gridDim.x, tiles_x, tiles_y);
+      gpre_fetch<GBF, DBF>(gdisp, disp, Tn, (size_t)Tn.b * H * W, H, W, pre);
+    }
+#pragma unroll 1
+    for (int q0 = 0; q0 < kTileW * kTileH; q0 += PPI) {
+      const int q = q0 + pl, oy = q / kTileW, ox = q - oy * kTileW;
+      const int yy = T.y0 + oy, xx = T.x0 + ox;
+      if (yy >= H || xx >= W) continue;
+      float s[9];
+      tap_sums(gp, oy, ox, yy, xx, H, W, s);
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float a = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) a = fmaf(wr[t][k], s[t], a);
+        o[k] = a;
+      }
+      store8<GXBF>(gx, (img + (size_t)yy * W + xx) * C + sub * 8, o);
+    }
+  }
+}
+
+// grad_w[c][t] = sum_pixels x[c] s[t], grad_bias = sum_pixels s[centre]: per-lane accumulators over the block's tiles -> fixed-
+// order reduction over the lanes that own the same channels, the warps of the block, and (disp_head_reduce_kernel) the blocks
+template <bool XBF, bool GBF, bool DBF, int LP>
+__global__ void __launch_bounds__(kHeadThreads) disp_head_bwd_w_tile_kernel(const void* __restrict__ gdisp, const void* __restrict__ disp,
+                                                                            const void* __restrict__ x, float* __restrict__ partial,
+                                                                            int H, int W, int tiles_x, int tiles_y, int ntiles) {
+  constexpr int C = 8 * LP, PPI = kHeadThreads / LP, NP = 9 * C + 1, NW = kHeadThreads / 32;
+  constexpr int NPASS = LP, U = NPASS < 4 ? NPASS : 4;       // activation loads in flight per thread
+  extern __shared__ float red[];                       // [NW][NP]; the first kHaloN floats double as the g_pre stage
+  float* gp = red;
+  const int lane = threadIdx.x & 31, sub = threadIdx.x & (LP - 1), pl = threadIdx.x / LP, wid = threadIdx.x >> 5;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  float accb = 0.f;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const HeadTile T = head_tile(tile, tiles_x, tiles_y);
+    const size_t img = (size_t)T.b * H * W;
+    Raw8<XBF> r[U];
+    auto fetch = [&](int p0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = (p0 + u) * PPI + pl, oy = q / kTileW, ox = q - oy * kTileW;
+        int yy = T.y0 + oy, xx = T.x0 + ox;
+        yy = yy > H - 1 ? H - 1 : yy; xx = xx > W - 1 ? W - 1 : xx;
+        r[u] = raw_load<XBF>(x, (img + (size_t)yy * W + xx) * C + sub * 8);
+      }
+    };
+    fetch(0);                                                 // in flight while g_pre is staged
+    __syncthreads();
+    stage_gpre<GBF, DBF>(gdisp, disp, T, img, H, W, gp);
+    __syncthreads();
+#pragma unroll 1
+    for (int p0 = 0; p0 < NPASS; p0 += U) {
+      if (p0) fetch(p0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = (p0 + u) * PPI + pl, oy = q / kTileW, ox = q - oy * kTileW;
+        const int yy = T.y0 + oy, xx = T.x0 + ox;
+        if (yy >= H || xx >= W) continue;
+        float v[8];
+        raw_unpack<XBF>(r[u], v);
+        float s[9];
+        tap_sums(gp, oy, ox, yy, xx, H, W, s);
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(v[k], s[t], acc[t][k]);
+        if (sub == 0) accb += s[4];                    // the centre tap never folds: s[4] is the pixel's own g_pre
+      }
+    }
+  }
+  __syncthreads();
+  // lanes with the same `sub` (different pixels): xor offsets LP .. 16
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a = acc[t][k];
+#pragma unroll
+      for (int o = LP; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      acc[t][k] = a;
+    }
+#pragma unroll
+  for (int o = LP; o < 32; o <<= 1) accb += __shfl_xor_sync(0xffffffffu, accb, o);
+  if (lane < LP) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[wid * NP + (sub * 8 + k) * 9 + t] = acc[t][k];
+    if (lane == 0) red[wid * NP + 9 * C] = accb;
+  }
+  __syncthreads();
+  for (int pair = threadIdx.x; pair < NP; pair += kHeadThreads) {
+    float a = 0.f;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) a += red[q * NP + pair];
+    partial[(size_t)blockIdx.x * NP + pair] = a;
+  }
+}
+
+static bool head_grouped(int C) { return C == 8 || C == 16 || C == 32 || C == 64 || C == 128; }
+static int head_tiles(int B, int H, int W, int* tx, int* ty) {
+  *tx = (W + kTileW - 1) / kTileW;
+  *ty = (H + kTileH - 1) / kTileH;
+  return B * *tx * *ty;
+}
+static int head_w_blocks(int ntiles) { return ntiles < 148 * 2 ? ntiles : 148 * 2; }   // persistent over the tiles: 2 blocks per SM
+
 static int head_check(const void* x, int x_dtype, int B, int C, int H, int W) {
   if (!x || B < 1 || H < 3 || W < 3 || C < 8 || (C & 7) || C > kHeadMaxC) return DVS_EINVAL;
   if (x_dtype != DVS_DTYPE_F32 && x_dtype != DVS_DTYPE_BF16) return DVS_EINVAL;
@@ -234,11 +565,32 @@ extern "C" int dvs_disp_head_fwd(const void* x, int x_dtype, const float* weight
   if (rc) return rc;
   if (!weight || !disp || (disp_dtype != DVS_DTYPE_F32 && disp_dtype != DVS_DTYPE_BF16)) return DVS_EINVAL;
   const size_t P = (size_t)B * H * W;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool xb = x_dtype == DVS_DTYPE_BF16, db = disp_dtype == DVS_DTYPE_BF16;
+  if (head_grouped(C)) {
+    int tx, ty;
+    const int grid = head_tiles(B, H, W, &tx, &ty);
+#define DVS_HEAD_FWD(LP)                                                                                                      \
+  do {                                                                                                                        \
+    if (xb && db) disp_head_fwd_tile_kernel<true, true, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty);  \
+    else if (xb) disp_head_fwd_tile_kernel<true, false, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty);  \
+    else if (db) disp_head_fwd_tile_kernel<false, true, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty);  \
+    else disp_head_fwd_tile_kernel<false, false, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty);         \
+  } while (0)
+    switch (C / 8) {
+      case 1: DVS_HEAD_FWD(1); break;
+      case 2: DVS_HEAD_FWD(2); break;
+      case 4: DVS_HEAD_FWD(4); break;
+      case 8: DVS_HEAD_FWD(8); break;
+      default: DVS_HEAD_FWD(16); break;
+    }
+#undef DVS_HEAD_FWD
+    DVS_CUDA_TRY(cudaGetLastError());
+    return DVS_OK;
+  }
   int grid = (int)((P + kHeadThreads - 1) / kHeadThreads);
   if (grid > 148 * 32) grid = 148 * 32;
   const size_t smem = sizeof(float) * 9 * C;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool xb = x_dtype == DVS_DTYPE_BF16, db = disp_dtype == DVS_DTYPE_BF16;
   if (xb && db) disp_head_fwd_kernel<true, true><<<grid, kHeadThreads, smem, st>>>(x, weight, bias, disp, B, C, H, W);
   else if (xb) disp_head_fwd_kernel<true, false><<<grid, kHeadThreads, smem, st>>>(x, weight, bias, disp, B, C, H, W);
   else if (db) disp_head_fwd_kernel<false, true><<<grid, kHeadThreads, smem, st>>>(x, weight, bias, disp, B, C, H, W);
@@ -251,7 +603,11 @@ extern "C" int dvs_disp_head_bwd_workspace_bytes(int B, int C, int H, int W, siz
   if (!bytes || B < 1 || H < 3 || W < 3 || C < 8 || (C & 7) || C > kHeadMaxC) return DVS_EINVAL;
   const size_t P = (size_t)B * H * W;
   const int chunks = head_chunks(P);
-  const size_t nblk = (P + (size_t)kHeadThreads * chunks - 1) / ((size_t)kHeadThreads * chunks);
+  size_t nblk = (P + (size_t)kHeadThreads * chunks - 1) / ((size_t)kHeadThreads * chunks);
+  if (head_grouped(C)) {
+    int tx, ty;
+    nblk = (size_t)head_w_blocks(head_tiles(B, H, W, &tx, &ty));
+  }
   *bytes = sizeof(float) * nblk * (9 * (size_t)C + 1) + 256;
   return DVS_OK;
 }
@@ -276,18 +632,50 @@ extern "C" int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int di
   if (disp_dtype != DVS_DTYPE_F32 && disp_dtype != DVS_DTYPE_BF16) return DVS_EINVAL;
   if (!workspace || ((uintptr_t)workspace & 255) || ((uintptr_t)grad_x & 15)) return DVS_EWORKSPACE;
   const size_t P = (size_t)B * H * W;
-  const int chunks = head_chunks(P);
-  const int nblk = (int)((P + (size_t)kHeadThreads * chunks - 1) / ((size_t)kHeadThreads * chunks));
-  const size_t smem = sizeof(float) * (9 * (size_t)C + kHeadThreads * 10 + (size_t)kHeadThreads * (C + 1));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
   const bool xb = x_dtype == DVS_DTYPE_BF16, gb = disp_dtype == DVS_DTYPE_BF16;
+  const int npairs = 9 * C + 1;
+  if (head_grouped(C)) {
+    int tx, ty;
+    const int ntiles = head_tiles(B, H, W, &tx, &ty), grid = head_w_blocks(ntiles);
+    const size_t smem_w = sizeof(float) * (kHeadThreads / 32) * npairs;
+#define DVS_HEAD_BWD(XB, GB, LP)                                                                                              \
+  do {                                                                                                                        \
+    disp_head_bwd_x_tile_kernel<GB, GB, XB, LP><<<grid, kHeadThreads, 0, st>>>(grad_disp, disp, weight, grad_x, H, W, tx, ty,     \
+                                                                              ntiles);                                       \
+    disp_head_bwd_w_tile_kernel<XB, GB, GB, LP><<<grid, kHeadThreads, smem_w, st>>>(grad_disp, disp, x, partial, H, W, tx, ty,    \
+                                                                                   ntiles);                                  \
+  } while (0)
+#define DVS_HEAD_BWD_LP(LP)                                                                                                   \
+  do {                                                                                                                        \
+    if (xb && gb) DVS_HEAD_BWD(true, true, LP);                                                                               \
+    else if (xb) DVS_HEAD_BWD(true, false, LP);                                                                               \
+    else if (gb) DVS_HEAD_BWD(false, true, LP);                                                                               \
+    else DVS_HEAD_BWD(false, false, LP);                                                                                      \
+  } while (0)
+    switch (C / 8) {
+      case 1: DVS_HEAD_BWD_LP(1); break;
+      case 2: DVS_HEAD_BWD_LP(2); break;
+      case 4: DVS_HEAD_BWD_LP(4); break;
+      case 8: DVS_HEAD_BWD_LP(8); break;
+      default: DVS_HEAD_BWD_LP(16); break;
+    }
+#undef DVS_HEAD_BWD_LP
+#undef DVS_HEAD_BWD
+    DVS_CUDA_TRY(cudaGetLastError());
+    disp_head_reduce_kernel<<<(npairs + 7) / 8, 256, 0, st>>>(partial, grid, npairs, grad_weight, grad_bias);
+    DVS_CUDA_TRY(cudaGetLastError());
+    return DVS_OK;
+  }
+  const int chunks = head_chunks(P);
+  const int nblk = (int)((P + (size_t)kHeadThreads * chunks - 1) / ((size_t)kHeadThreads * chunks));
+  const size_t smem = sizeof(float) * (9 * (size_t)C + kHeadThreads * 10 + (size_t)kHeadThreads * (C + 1));
   if (xb && gb) rc = head_bwd_launch<true, true>(grad_disp, disp, x, weight, grad_x, partial, B, C, H, W, chunks, nblk, smem, st);
   else if (xb) rc = head_bwd_launch<true, false>(grad_disp, disp, x, weight, grad_x, partial, B, C, H, W, chunks, nblk, smem, st);
   else if (gb) rc = head_bwd_launch<false, true>(grad_disp, disp, x, weight, grad_x, partial, B, C, H, W, chunks, nblk, smem, st);
   else rc = head_bwd_launch<false, false>(grad_disp, disp, x, weight, grad_x, partial, B, C, H, W, chunks, nblk, smem, st);
   if (rc) return rc;
-  const int npairs = 9 * C + 1;
   disp_head_reduce_kernel<<<(npairs + 7) / 8, 256, 0, st>>>(partial, nblk, npairs, grad_weight, grad_bias);
   DVS_CUDA_TRY(cudaGetLastError());
   return DVS_OK;

@@ -26,4 +26,4 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
         tr.train_mono_step(dict(sample))
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=150))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(os.environ.get("ROWS", "40")), max_name_column_width=150))
