@@ -316,10 +316,30 @@ def run_train(args, world, rank, local, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item()) / args.train_steps
     loss = float(total)
+    del total, _                                          # the eager step's autograd graph must be gone before a capture
+    graph = None
+    if world == 1:
+        # the same step recorded as ONE CUDA graph (Trainer.capture_step: zero_grad -> networks -> loss -> backward -> Adam) and
+        # replayed; single process only (DDP's hooks are not captured), so it is reported beside the eager number, not instead
+        try:
+            tr.capture_step(dict(sample))
+            for _ in range(2):
+                tr.train_graph_step(sample)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.train_steps):
+                tr.train_graph_step(sample)
+            e1.record()
+            torch.cuda.synchronize()
+            gdt = e0.elapsed_time(e1) / 1e3 / args.train_steps
+            graph = {"ms_per_step": gdt * 1e3, "value": Bt / gdt, "unit": "triplets/s",
+                     "note": "whole step replayed as one CUDA graph (N = 1 only; the headline train_step number is the eager DDP-capable step)"}
+        except Exception as exc:                                  # keep the bench line if capture is not possible on this box
+            graph = {"unavailable": repr(exc)[:200]}
     del tr
     torch.cuda.empty_cache()
     return {"metric": "train_frames_per_s", "value": world * Bt / dt, "unit": "triplets/s", "ms_per_step": dt * 1e3,
-            "batch_per_gpu": Bt, "steps": args.train_steps, "warmup": 3, "final_loss": loss,
+            "batch_per_gpu": Bt, "steps": args.train_steps, "warmup": 3, "final_loss": loss, "cuda_graph": graph,
             "config": f"ResNet-{layers} DepthNet+PoseNet (stock PyTorch, bf16 autocast, channels_last), fused fp32 view-synthesis "
                       f"loss with {len(fids)} source frames, Adam, {Wt}x{Ht}, batch {Bt}/GPU, DDP over NCCL "
                       f"(BASELINE configs[{3 if big else 2}]); synthetic frames resident in HBM; the only collective is DDP's "

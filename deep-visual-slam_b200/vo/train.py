@@ -165,6 +165,17 @@ class Trainer:
             raise RuntimeError("capture_step does not support DistributedDataParallel")
         self._static = {k: (v.to(self.device).clone() if isinstance(v, torch.Tensor) else v) for k, v in sample.items()}
         sync, self.sync_losses = self.sync_losses, False
+        # Earlier eager steps leave autograd graphs alive (DepthNet keeps its last ``outputs`` and the encoder its last ``features``, as the
+        # reference's do, model/depthnet.py:89, model/resnet_encoder.py); their AccumulateGrad nodes belong to the legacy default stream, and a capture that meets them
+        # fails with cudaErrorStreamCaptureImplicit.  Drop them so that the warm-up below recreates the nodes on a side stream.
+        self.joint._disp, self.joint._poses = None, []
+        for m in self.nets.modules():
+            if isinstance(getattr(m, "outputs", None), dict):
+                m.outputs = {}
+            if isinstance(getattr(m, "features", None), list):    # ResnetEncoder keeps its last feature pyramid
+                m.features = []
+        import gc
+        gc.collect()
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):

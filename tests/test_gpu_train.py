@@ -58,6 +58,11 @@ def test_whole_training_step_replays_from_a_cuda_graph():
     B, H, W = 2, 96, 128
     tr = _trainer(B, H, W, net_dtype=torch.bfloat16, sync_losses=False)
     sample = synthetic_sample(B, H, W, seed=5, device="cuda")
+    # eager steps first (a resumed or warmed-up trainer): the modules then hold the last step's outputs, whose autograd graph
+    # pins gradient accumulators to the legacy stream; capture_step has to drop them or the capture is invalidated
+    for _ in range(2):
+        total, _, _ = tr.train_mono_step(dict(sample))
+    del total, _
     tr.capture_step(sample)
     n0 = dvsloss.noise_state()
     losses = []
