@@ -293,6 +293,60 @@ def test_c_abi_backward_recompute_matches_forward_saved_gradients():
                                                 wsp, stream_ptr(dev)) == -1
 
 
+@pytest.mark.parametrize("B,H,W,N", [(1, 37, 53, 2), (2, 61, 35, 1), (1, 33, 95, 3), (2, 64, 96, 4), (3, 30, 30, 2)])
+def test_c_abi_writes_stay_inside_the_declared_buffers(B, H, W, N):
+    """Real launch geometry (ragged last tiles, 1..4 sources, the workspace carve-up): every output and the workspace sit
+    between guard bands inside one arena; after forward + backward through the raw C ABI the guards are untouched and the
+    outputs are fully written (no NaN left).  compute-sanitizer is closed on this GPU pool; this is the global-memory part of
+    what it would check (the shared-memory part is the block emulator's canaries, tests/emu)."""
+    import ctypes as C
+    from dvsloss import _lib
+    from dvsloss._lib import DvsParams, fptr_array, lib, make_shape, ptr, stream_ptr
+    from dvsloss.synthetic import pose_matrix
+    dev = torch.device("cuda:0")
+    S = 4
+    p = make_problem(B, H, W, N, S, seed=H + N, consistent=True)
+    cut = lambda t: t.to(dev).float().contiguous()
+    disps = [cut(d) for d in p["disps"]]
+    Ts = [cut(pose_matrix(a.view(B, 3), t.view(B, 3), inv)) for a, t, inv in zip(p["axisangle"], p["translation"], p["invert"])]
+    tgt, srcs, K, iK = cut(p["target"]), [cut(s_) for s_ in p["sources"]], cut(p["K"]), cut(p["inv_K"])
+    noise = [cut(n) for n in p["noise"]]
+    shape = make_shape(B, H, W, N, [d.shape[2:] for d in disps])
+    params = DvsParams(0.1, 10.0, 0.85, 1e-3, 1e-7, 1)
+    L = lib()
+    nbytes = C.c_size_t(0)
+    assert L.dvs_loss_workspace_bytes(C.byref(shape), C.byref(nbytes)) == 0
+    GUARD = 4096                                             # floats between consecutive buffers
+    sizes = [d.numel() for d in disps] + [B * 16] * N + [(nbytes.value + 3) // 4]
+    offs, cur = [], GUARD
+    for n in sizes:
+        cur = (cur + 63) // 64 * 64                          # 256-byte alignment (the workspace needs it)
+        offs.append(cur)
+        cur += n + GUARD
+    arena = torch.full((cur,), float("nan"), dtype=torch.float32, device=dev)
+    sentinel = -1234.5
+    arena.fill_(sentinel)
+    views = [arena[o:o + n] for o, n in zip(offs, sizes)]
+    for v in views[:-1]:
+        v.fill_(float("nan"))
+    gd = [v.view_as(d) for v, d in zip(views[:S], disps)]
+    gT = [v.view(B, 4, 4) for v in views[S:S + N]]
+    wsp = views[-1].data_ptr()
+    assert wsp % 256 == 0
+    gvec = torch.tensor([0.7, -0.2, 1.5, 0.25], device=dev)
+    rc = L.dvs_photometric_backward_recompute(C.byref(shape), C.byref(params), fptr_array(disps), ptr(tgt), fptr_array(srcs),
+                                              ptr(K), ptr(iK), fptr_array(Ts), fptr_array(noise), C.c_uint64(0), C.c_uint64(0),
+                                              ptr(gvec), fptr_array(gd), fptr_array(gT), wsp, stream_ptr(dev))
+    _lib.check(rc, "dvs_photometric_backward_recompute")
+    torch.cuda.synchronize()
+    inside = torch.zeros(cur, dtype=torch.bool, device=dev)
+    for o, n in zip(offs, sizes):
+        inside[o:o + n] = True
+    assert bool((arena[~inside] == sentinel).all())          # nothing written outside the declared extents
+    for v in views[:-1]:
+        assert bool(torch.isfinite(v).all())                 # ... and every output element written
+
+
 def test_fused_loss_is_cuda_graph_capturable():
     """the whole loss forward+backward (5 + 1 kernels, no memsets, no host sync) replays from a CUDA graph
     and gives the numbers of the eager call (the reference syncs the host every step, vo/train.py:196-197)."""
