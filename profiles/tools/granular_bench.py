@@ -36,6 +36,30 @@ def timeit(fn, n=10):
     return e0.elapsed_time(e1) / n
 
 
+def timeit_graph(fn, n=20):
+    """Device time alone: the call sequence recorded once as a CUDA graph and replayed (the eager numbers of these small
+    operators are bound by Python / dispatcher overhead on either side, not by their kernels)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
 def fb(f, *leaves):
     def run():
         for t in leaves:
@@ -61,7 +85,13 @@ def main():
 
     def add(name, ours, ref):
         a, b = timeit(ours), timeit(ref)
-        rows.append({"op": name, "ms_b200": a, "ms_eager": b, "speedup": b / a})
+        try:
+            ga, gb = timeit_graph(ours), timeit_graph(ref)
+        except Exception as exc:                               # an op that cannot be captured: keep the eager numbers
+            ga = gb = float("nan")
+            print("# graph timing failed for", name, repr(exc)[:120], file=sys.stderr)
+        rows.append({"op": name, "ms_b200": a, "ms_eager": b, "speedup": b / a, "device_ms_b200": ga, "device_ms_eager": gb,
+                     "device_speedup": gb / ga})
         print(json.dumps(rows[-1]), flush=True)
 
     add("disp_to_depth", fb(lambda: ops.disp_to_depth(disp, 0.1, 10.0), disp),
