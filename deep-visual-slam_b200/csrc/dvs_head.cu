@@ -714,11 +714,37 @@ struct Vec16 {
 __device__ __forceinline__ float elu_value(float a) { return a <= 0.f ? expf(a) - 1.f : a; }          // ATen elu_kernel, alpha = scale = 1
 __device__ __forceinline__ float elu_slope(float a) { return a <= 0.f ? expf(a) : 1.f; }              // ATen elu_backward_kernel (is_result = false)
 
-// one thread per 16-byte vector of `out` [B, 2h, 2w, C1 + C2]
+// Per-channel sums over the pixels (the bias gradients) of the glue kernels: every thread keeps its N channels' sums over a
+// grid-stride walk whose stride is a multiple of the vectors per pixel (so the thread's channels never change), the block
+// adds the threads that own the same channels in thread order, and channel_reduce_kernel adds the blocks in block order.
+constexpr int kGlueThreads = 256;
+template <int N>
+__device__ __forceinline__ void block_channel_sums(const float* acc, int vpp, float* __restrict__ partial, int C) {
+  __shared__ float sh[kGlueThreads * 8];
+#pragma unroll
+  for (int i = 0; i < N; ++i) sh[threadIdx.x * N + i] = acc[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kGlueThreads) {
+    const int v = c / N, i = c - v * N;
+    float a = 0.f;
+    for (int t = v; t < kGlueThreads; t += vpp) a += sh[t * N + i];
+    partial[(size_t)blockIdx.x * C + c] = a;
+  }
+}
+__global__ void __launch_bounds__(256) channel_reduce_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int b = lane; b < nblk; b += 32) a += partial[(size_t)b * C + c];
+  for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[c] = a;
+}
+
+// one thread per 16-byte vector of `out` [B, 2h, 2w, C1 + C2]; bias (fp32 [C1], may be null) is added before the ELU
 template <bool BF>
 __global__ void __launch_bounds__(256) elu_up2_cat_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip,
-                                                              uint4* __restrict__ out, int h, int w, int v1, int v2,
-                                                              size_t nvec) {
+                                                              const float* __restrict__ bias, uint4* __restrict__ out, int h, int w,
+                                                              int v1, int v2, size_t nvec) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nvec) return;
   const int vt = v1 + v2;
@@ -733,41 +759,53 @@ __global__ void __launch_bounds__(256) elu_up2_cat_fwd_kernel(const uint4* __res
   const size_t r = pix / W2;
   const int Y = (int)(r % H2);
   const size_t b = r / H2;
+  constexpr int N = Vec16<BF>::N;
   Vec16<BF> a;
   a.raw = x[((b * h + (Y >> 1)) * w + (X >> 1)) * v1 + v];
-  float f[Vec16<BF>::N];
-  for (int i = 0; i < Vec16<BF>::N; ++i) f[i] = elu_value(a.get(i));
+  float f[N];
+  for (int i = 0; i < N; ++i) f[i] = elu_value(a.get(i) + (bias ? bias[v * N + i] : 0.f));
   Vec16<BF> o;
   o.set_all(f);
   out[e] = o.raw;
 }
 
-// one thread per 16-byte vector of grad_x [B, h, w, C1]: 2x2 sum of grad_out (fixed order) times ELU'(x)
+// grad_x [B, h, w, C1]: 2x2 sum of grad_out (fixed order) times ELU'(x + bias); grid-stride, per-channel sums of grad_x for
+// the bias gradient (partial != null)
 template <bool BF>
-__global__ void __launch_bounds__(256) elu_up2_cat_bwd_x_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gout,
-                                                                uint4* __restrict__ gx, int h, int w, int v1, int v2,
-                                                                size_t nvec) {
-  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nvec) return;
-  const size_t pix = e / v1;
-  const int v = (int)(e - pix * v1);
-  const int xx = (int)(pix % w);
-  const size_t r = pix / w;
-  const int yy = (int)(r % h);
-  const size_t b = r / h;
+__global__ void __launch_bounds__(kGlueThreads) elu_up2_cat_bwd_x_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gout,
+                                                                         const float* __restrict__ bias, uint4* __restrict__ gx,
+                                                                         float* __restrict__ partial, int h, int w, int v1, int v2,
+                                                                         size_t nvec) {
+  constexpr int N = Vec16<BF>::N;
   const int vt = v1 + v2, W2 = 2 * w;
-  const size_t o00 = ((b * 2 * h + 2 * yy) * W2 + 2 * xx) * vt + v;
-  Vec16<BF> g00, g01, g10, g11, a;
-  g00.raw = gout[o00];
-  g01.raw = gout[o00 + vt];
-  g10.raw = gout[o00 + (size_t)W2 * vt];
-  g11.raw = gout[o00 + (size_t)W2 * vt + vt];
-  a.raw = x[e];
-  float f[Vec16<BF>::N];
-  for (int i = 0; i < Vec16<BF>::N; ++i) f[i] = ((g00.get(i) + g01.get(i)) + (g10.get(i) + g11.get(i))) * elu_slope(a.get(i));
-  Vec16<BF> o;
-  o.set_all(f);
-  gx[e] = o.raw;
+  float acc[N], bv[N];
+  const int v = threadIdx.x % v1;                             // constant along the walk: the stride is a multiple of v1
+#pragma unroll
+  for (int i = 0; i < N; ++i) { acc[i] = 0.f; bv[i] = bias ? bias[v * N + i] : 0.f; }
+  for (size_t e = (size_t)blockIdx.x * kGlueThreads + threadIdx.x; e < nvec; e += (size_t)gridDim.x * kGlueThreads) {
+    const size_t pix = e / v1;
+    const int xx = (int)(pix % w);
+    const size_t r = pix / w;
+    const int yy = (int)(r % h);
+    const size_t b = r / h;
+    const size_t o00 = ((b * 2 * h + 2 * yy) * W2 + 2 * xx) * vt + v;
+    Vec16<BF> g00, g01, g10, g11, a;
+    g00.raw = gout[o00];
+    g01.raw = gout[o00 + vt];
+    g10.raw = gout[o00 + (size_t)W2 * vt];
+    g11.raw = gout[o00 + (size_t)W2 * vt + vt];
+    a.raw = x[e];
+    float f[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      f[i] = ((g00.get(i) + g01.get(i)) + (g10.get(i) + g11.get(i))) * elu_slope(a.get(i) + bv[i]);
+      acc[i] += f[i];
+    }
+    Vec16<BF> o;
+    o.set_all(f);
+    gx[e] = o.raw;
+  }
+  if (partial) block_channel_sums<N>(acc, v1, partial, v1 * N);
 }
 
 // one thread per 16-byte vector of grad_skip [B, 2h, 2w, C2]: the channel slice of grad_out
@@ -780,6 +818,51 @@ __global__ void __launch_bounds__(256) cat_bwd_skip_kernel(const uint4* __restri
   gskip[e] = gout[pix * (v1 + v2) + v1 + v];
 }
 
+// y = ELU(x + bias[c]) (ConvBlock: the convolution's bias and its ELU, model/layers.py:106-117), in place if y == x
+template <bool BF>
+__global__ void __launch_bounds__(256) bias_elu_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ bias,
+                                                           uint4* __restrict__ y, int vpp, size_t nvec) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nvec) return;
+  constexpr int N = Vec16<BF>::N;
+  const int v = (int)(e % vpp);
+  Vec16<BF> a;
+  a.raw = x[e];
+  float f[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) f[i] = elu_value(a.get(i) + (bias ? bias[v * N + i] : 0.f));
+  Vec16<BF> o;
+  o.set_all(f);
+  y[e] = o.raw;
+}
+// grad_x = grad_y * ELU'(.) written from the OUTPUT y as ATen's in-place ELU does (y <= 0 ? y + 1 : 1: nn.ELU(inplace=True)
+// keeps only y); per-channel sums of grad_x for the bias gradient
+template <bool BF>
+__global__ void __launch_bounds__(kGlueThreads) bias_elu_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ gy,
+                                                                    uint4* __restrict__ gx, float* __restrict__ partial, int vpp,
+                                                                    size_t nvec) {
+  constexpr int N = Vec16<BF>::N;
+  float acc[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) acc[i] = 0.f;
+  for (size_t e = (size_t)blockIdx.x * kGlueThreads + threadIdx.x; e < nvec; e += (size_t)gridDim.x * kGlueThreads) {
+    Vec16<BF> a, g;
+    a.raw = y[e];
+    g.raw = gy[e];
+    float f[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float yv = a.get(i);
+      f[i] = g.get(i) * (yv <= 0.f ? yv + 1.f : 1.f);
+      acc[i] += f[i];
+    }
+    Vec16<BF> o;
+    o.set_all(f);
+    gx[e] = o.raw;
+  }
+  if (partial) block_channel_sums<N>(acc, vpp, partial, vpp * N);
+}
+
 static int glue_check(const void* x, int dtype, int B, int C1, int C2, int h, int w, const void* skip) {
   if (!x || B < 1 || h < 1 || w < 1 || C1 < 1 || C2 < 0) return DVS_EINVAL;
   if (dtype != DVS_DTYPE_F32 && dtype != DVS_DTYPE_BF16) return DVS_EINVAL;
@@ -789,11 +872,24 @@ static int glue_check(const void* x, int dtype, int B, int C1, int C2, int h, in
   if (((uintptr_t)x & 15) || ((uintptr_t)skip & 15)) return DVS_EINVAL;
   return DVS_OK;
 }
+// grid of the reducing kernels: the walk's stride (grid x 256) must be a multiple of the vectors per pixel (a power of two
+// <= 256 here, else the caller is refused), and at most 8 blocks per SM
+static int glue_reduce_blocks(size_t nvec, int vpp) {
+  if (vpp < 1 || vpp > kGlueThreads || (kGlueThreads % vpp)) return 0;
+  size_t n = (nvec + kGlueThreads - 1) / kGlueThreads;
+  return (int)(n < 1 ? 1 : (n > 148 * 8 ? 148 * 8 : n));
+}
 
 }  // namespace dvs
 
-extern "C" int dvs_elu_up2_cat_fwd(const void* x, const void* skip, void* out, int dtype, int B, int C1, int C2, int h, int w,
-                                   void* stream) {
+extern "C" int dvs_glue_workspace_bytes(int C, size_t* bytes) {
+  if (!bytes || C < 1) return DVS_EINVAL;
+  *bytes = sizeof(float) * (size_t)148 * 8 * C + 256;
+  return DVS_OK;
+}
+
+extern "C" int dvs_elu_up2_cat_fwd(const void* x, const void* skip, const float* bias, void* out, int dtype, int B, int C1, int C2,
+                                   int h, int w, void* stream) {
   using namespace dvs;
   int rc = glue_check(x, dtype, B, C1, C2, h, w, skip);
   if (rc) return rc;
@@ -803,29 +899,76 @@ extern "C" int dvs_elu_up2_cat_fwd(const void* x, const void* skip, void* out, i
   const size_t nvec = (size_t)B * 4 * h * w * (v1 + v2);
   const unsigned int nblk = (unsigned int)((nvec + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bf) elu_up2_cat_fwd_kernel<true><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, (uint4*)out, h, w, v1, v2, nvec);
-  else elu_up2_cat_fwd_kernel<false><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, (uint4*)out, h, w, v1, v2, nvec);
+  if (bf) elu_up2_cat_fwd_kernel<true><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, bias, (uint4*)out, h, w, v1, v2, nvec);
+  else elu_up2_cat_fwd_kernel<false><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, bias, (uint4*)out, h, w, v1, v2, nvec);
   DVS_CUDA_TRY(cudaGetLastError());
   return DVS_OK;
 }
 
-extern "C" int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, void* grad_x, void* grad_skip, int dtype, int B, int C1,
-                                   int C2, int h, int w, void* stream) {
+extern "C" int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, const float* bias, void* grad_x, void* grad_skip,
+                                   float* grad_bias, int dtype, int B, int C1, int C2, int h, int w, void* workspace, void* stream) {
   using namespace dvs;
   int rc = glue_check(x, dtype, B, C1, C2, h, w, C2 > 0 ? grad_skip : nullptr);
   if (rc) return rc;
   if (!grad_out || !grad_x || ((uintptr_t)grad_out & 15) || ((uintptr_t)grad_x & 15)) return DVS_EINVAL;
+  if (grad_bias && (!workspace || ((uintptr_t)workspace & 255))) return DVS_EWORKSPACE;
   const bool bf = dtype == DVS_DTYPE_BF16;
   const int per = bf ? 8 : 4, v1 = C1 / per, v2 = C2 / per;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t nx = (size_t)B * h * w * v1;
-  const unsigned int bx = (unsigned int)((nx + 255) / 256);
-  if (bf) elu_up2_cat_bwd_x_kernel<true><<<bx, 256, 0, st>>>((const uint4*)x, (const uint4*)grad_out, (uint4*)grad_x, h, w, v1, v2, nx);
-  else elu_up2_cat_bwd_x_kernel<false><<<bx, 256, 0, st>>>((const uint4*)x, (const uint4*)grad_out, (uint4*)grad_x, h, w, v1, v2, nx);
+  const int bx = glue_reduce_blocks(nx, v1);
+  if (!bx) return DVS_EINVAL;
+  float* partial = grad_bias ? static_cast<float*>(workspace) : nullptr;
+  if (bf) elu_up2_cat_bwd_x_kernel<true><<<bx, kGlueThreads, 0, st>>>((const uint4*)x, (const uint4*)grad_out, bias, (uint4*)grad_x, partial, h, w, v1, v2, nx);
+  else elu_up2_cat_bwd_x_kernel<false><<<bx, kGlueThreads, 0, st>>>((const uint4*)x, (const uint4*)grad_out, bias, (uint4*)grad_x, partial, h, w, v1, v2, nx);
   DVS_CUDA_TRY(cudaGetLastError());
+  if (grad_bias) {
+    channel_reduce_kernel<<<(C1 + 7) / 8, 256, 0, st>>>(partial, bx, C1, grad_bias);
+    DVS_CUDA_TRY(cudaGetLastError());
+  }
   if (v2 > 0) {
     const size_t ns = (size_t)B * 4 * h * w * v2;
     cat_bwd_skip_kernel<<<(unsigned int)((ns + 255) / 256), 256, 0, st>>>((const uint4*)grad_out, (uint4*)grad_skip, v1, v2, ns);
+    DVS_CUDA_TRY(cudaGetLastError());
+  }
+  return DVS_OK;
+}
+
+extern "C" int dvs_bias_elu_fwd(const void* x, const float* bias, void* y, int dtype, int B, int C, int H, int W, void* stream) {
+  using namespace dvs;
+  int rc = glue_check(x, dtype, B, C, 0, H, W, nullptr);
+  if (rc) return rc;
+  if (!y || ((uintptr_t)y & 15)) return DVS_EINVAL;
+  const bool bf = dtype == DVS_DTYPE_BF16;
+  const int vpp = C / (bf ? 8 : 4);
+  const size_t nvec = (size_t)B * H * W * vpp;
+  const unsigned int nblk = (unsigned int)((nvec + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bf) bias_elu_fwd_kernel<true><<<nblk, 256, 0, st>>>((const uint4*)x, bias, (uint4*)y, vpp, nvec);
+  else bias_elu_fwd_kernel<false><<<nblk, 256, 0, st>>>((const uint4*)x, bias, (uint4*)y, vpp, nvec);
+  DVS_CUDA_TRY(cudaGetLastError());
+  return DVS_OK;
+}
+
+extern "C" int dvs_bias_elu_bwd(const void* y, const void* grad_y, void* grad_x, float* grad_bias, int dtype, int B, int C, int H,
+                                int W, void* workspace, void* stream) {
+  using namespace dvs;
+  int rc = glue_check(y, dtype, B, C, 0, H, W, nullptr);
+  if (rc) return rc;
+  if (!grad_y || !grad_x || ((uintptr_t)grad_y & 15) || ((uintptr_t)grad_x & 15)) return DVS_EINVAL;
+  if (grad_bias && (!workspace || ((uintptr_t)workspace & 255))) return DVS_EWORKSPACE;
+  const bool bf = dtype == DVS_DTYPE_BF16;
+  const int vpp = C / (bf ? 8 : 4);
+  const size_t nvec = (size_t)B * H * W * vpp;
+  const int nblk = glue_reduce_blocks(nvec, vpp);
+  if (!nblk) return DVS_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = grad_bias ? static_cast<float*>(workspace) : nullptr;
+  if (bf) bias_elu_bwd_kernel<true><<<nblk, kGlueThreads, 0, st>>>((const uint4*)y, (const uint4*)grad_y, (uint4*)grad_x, partial, vpp, nvec);
+  else bias_elu_bwd_kernel<false><<<nblk, kGlueThreads, 0, st>>>((const uint4*)y, (const uint4*)grad_y, (uint4*)grad_x, partial, vpp, nvec);
+  DVS_CUDA_TRY(cudaGetLastError());
+  if (grad_bias) {
+    channel_reduce_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, C, grad_bias);
     DVS_CUDA_TRY(cudaGetLastError());
   }
   return DVS_OK;

@@ -414,59 +414,126 @@ def disp_head_supported(x: torch.Tensor) -> bool:
 
 
 # ---------------------------------------------------------------------------------------------------- DepthNet decoder glue
+def _glue_ws(Cc: int, device) -> torch.Tensor:
+    import ctypes as C
+    n = C.c_size_t(0)
+    check(lib().dvs_glue_workspace_bytes(Cc, C.byref(n)), "dvs_glue_workspace_bytes")
+    return torch.empty(n.value + 256, dtype=torch.uint8, device=device)
+
+
+def _al256(t: torch.Tensor) -> int:
+    return (t.data_ptr() + 255) // 256 * 256
+
+
 class _EluUp2Cat(torch.autograd.Function):
-    """cat([nearest_up2(ELU(x)), skip], 1) in one pass, channels-last (model/depthnet.py:77-84, model/layers.py:106-117,196-199)."""
+    """cat([nearest_up2(ELU(x + bias)), skip], 1) in one pass, channels-last (model/depthnet.py:77-84, model/layers.py:106-117,196-199)."""
 
     @staticmethod
-    def forward(ctx, x, skip):
+    def forward(ctx, x, skip, bias):
         from ._lib import DTYPE_BF16, DTYPE_F32
         B, C1, h, w = x.shape
         C2 = 0 if skip is None else skip.shape[1]
         xc = x.contiguous(memory_format=torch.channels_last)
         sc = None if skip is None else skip.contiguous(memory_format=torch.channels_last)
+        bc = None if bias is None else bias.detach().float().contiguous()
         out = torch.empty(B, C1 + C2, 2 * h, 2 * w, dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         code = DTYPE_BF16 if x.dtype == torch.bfloat16 else DTYPE_F32
         with torch.cuda.device(x.device):
-            check(lib().dvs_elu_up2_cat_fwd(xc.data_ptr(), 0 if sc is None else sc.data_ptr(), out.data_ptr(), code, B, C1, C2, h, w,
-                                            stream_ptr(x.device)), "dvs_elu_up2_cat_fwd")
-        ctx.save_for_backward(xc)
+            check(lib().dvs_elu_up2_cat_fwd(xc.data_ptr(), 0 if sc is None else sc.data_ptr(), ptr(bc), out.data_ptr(), code, B, C1, C2,
+                                            h, w, stream_ptr(x.device)), "dvs_elu_up2_cat_fwd")
+        ctx.save_for_backward(xc, bc)
         ctx.C2, ctx.code = C2, code
+        ctx.bdtype = None if bias is None else bias.dtype
         return out
 
     @staticmethod
     def backward(ctx, g):
-        (xc,) = ctx.saved_tensors
+        xc, bc = ctx.saved_tensors
         B, C1, h, w = xc.shape
         C2 = ctx.C2
         g = g.to(xc.dtype).contiguous(memory_format=torch.channels_last)
         gx = torch.empty_like(xc, memory_format=torch.channels_last)
         gs = torch.empty(B, C2, 2 * h, 2 * w, dtype=xc.dtype, device=xc.device, memory_format=torch.channels_last) if C2 else None
+        want_b = bc is not None and ctx.needs_input_grad[2]
+        gb = torch.empty(C1, dtype=torch.float32, device=xc.device) if want_b else None
+        ws = _glue_ws(C1, xc.device) if want_b else None
         with torch.cuda.device(xc.device):
-            check(lib().dvs_elu_up2_cat_bwd(xc.data_ptr(), g.data_ptr(), gx.data_ptr(), 0 if gs is None else gs.data_ptr(), ctx.code,
-                                            B, C1, C2, h, w, stream_ptr(xc.device)), "dvs_elu_up2_cat_bwd")
-        return gx, gs
+            check(lib().dvs_elu_up2_cat_bwd(xc.data_ptr(), g.data_ptr(), ptr(bc), gx.data_ptr(), 0 if gs is None else gs.data_ptr(),
+                                            ptr(gb), ctx.code, B, C1, C2, h, w, 0 if ws is None else _al256(ws),
+                                            stream_ptr(xc.device)), "dvs_elu_up2_cat_bwd")
+        return gx, gs, (gb.to(ctx.bdtype) if gb is not None else None)
+
+
+def _glue_channels_ok(x: torch.Tensor) -> bool:
+    per = 8 if x.dtype == torch.bfloat16 else 4
+    v = x.shape[1] // per
+    return x.shape[1] % per == 0 and 1 <= v <= 256 and (v & (v - 1)) == 0          # the bias-gradient reduction wants a power of two
 
 
 def elu_up2_cat_supported(x: torch.Tensor, skip=None) -> bool:
-    if not (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16)):
+    if not (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16) and _glue_channels_ok(x)):
         return False
     per = 8 if x.dtype == torch.bfloat16 else 4
-    if x.shape[1] % per:
-        return False
     if skip is None:
         return True
     return (skip.is_cuda and skip.dtype == x.dtype and skip.shape[1] % per == 0 and skip.shape[0] == x.shape[0]
             and tuple(skip.shape[2:]) == (2 * x.shape[2], 2 * x.shape[3]))
 
 
-def elu_up2_cat(x: torch.Tensor, skip=None) -> torch.Tensor:
-    """``torch.cat([F.interpolate(F.elu(x), scale_factor=2, mode="nearest"), skip], 1)`` (``skip`` optional) as one kernel each
-    way; x [B,C1,h,w] is the decoder convolution's output BEFORE its ELU, skip [B,C2,2h,2w] the encoder feature.  Channels-last
-    memory is read in place; the result is channels-last."""
+def elu_up2_cat(x: torch.Tensor, skip=None, bias=None) -> torch.Tensor:
+    """``torch.cat([F.interpolate(F.elu(x + bias), scale_factor=2, mode="nearest"), skip], 1)`` (``skip``, ``bias`` optional) as
+    one kernel each way; x [B,C1,h,w] is the decoder convolution's output BEFORE its bias and ELU (run the convolution without
+    bias and hand the bias here: one pass over the activation less each way), skip [B,C2,2h,2w] the encoder feature.
+    Channels-last memory is read in place; the result is channels-last."""
     if not elu_up2_cat_supported(x, skip):
-        raise DvsError("elu_up2_cat needs CUDA fp32 / bf16 tensors of one dtype, channels a multiple of 4 (fp32) / 8 (bf16), "
+        raise DvsError("elu_up2_cat needs CUDA fp32 / bf16 tensors of one dtype, channels / 4 (fp32) or / 8 (bf16) a power of two, "
                        "skip of twice the spatial size")
-    return _EluUp2Cat.apply(x, skip)
+    return _EluUp2Cat.apply(x, skip, bias)
+
+
+class _BiasElu(torch.autograd.Function):
+    """ELU(x + bias) in one pass (ConvBlock = Conv3x3 + ELU, model/layers.py:106-117; the Conv2d bias of :131 folded in)."""
+
+    @staticmethod
+    def forward(ctx, x, bias):
+        from ._lib import DTYPE_BF16, DTYPE_F32
+        B, Cc, H, W = x.shape
+        xc = x.contiguous(memory_format=torch.channels_last)
+        bc = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty_like(xc, memory_format=torch.channels_last)
+        code = DTYPE_BF16 if x.dtype == torch.bfloat16 else DTYPE_F32
+        with torch.cuda.device(x.device):
+            check(lib().dvs_bias_elu_fwd(xc.data_ptr(), ptr(bc), y.data_ptr(), code, B, Cc, H, W, stream_ptr(x.device)), "dvs_bias_elu_fwd")
+        ctx.save_for_backward(y)
+        ctx.code = code
+        ctx.bdtype = None if bias is None else bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        B, Cc, H, W = y.shape
+        g = g.to(y.dtype).contiguous(memory_format=torch.channels_last)
+        gx = torch.empty_like(y, memory_format=torch.channels_last)
+        want_b = ctx.bdtype is not None and ctx.needs_input_grad[1]
+        gb = torch.empty(Cc, dtype=torch.float32, device=y.device) if want_b else None
+        ws = _glue_ws(Cc, y.device) if want_b else None
+        with torch.cuda.device(y.device):
+            check(lib().dvs_bias_elu_bwd(y.data_ptr(), g.data_ptr(), gx.data_ptr(), ptr(gb), ctx.code, B, Cc, H, W,
+                                         0 if ws is None else _al256(ws), stream_ptr(y.device)), "dvs_bias_elu_bwd")
+        return gx, (gb.to(ctx.bdtype) if gb is not None else None)
+
+
+def bias_elu_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16) and _glue_channels_ok(x)
+
+
+def bias_elu(x: torch.Tensor, bias=None) -> torch.Tensor:
+    """``F.elu(x + bias.view(1, -1, 1, 1))`` as one kernel each way (the backward also yields the bias gradient); x is the
+    convolution's output without its bias, channels-last memory is read in place."""
+    if not bias_elu_supported(x):
+        raise DvsError("bias_elu needs a CUDA fp32 / bf16 [B,C,H,W] tensor with C / 4 (fp32) or C / 8 (bf16) a power of two")
+    return _BiasElu.apply(x, bias)
 
 
 # ---------------------------------------------------------------------------------------------------- supervised depth

@@ -52,11 +52,13 @@ class DepthNet(nn.Module):
         for i in range(4, -1, -1):
             block = self.convs[("upconv", i, 0)]
             skip = feats[i - 1] if self.use_skips and i > 0 else None
-            pre = block.conv(x) if self.fused_glue and x.is_cuda else None
+            pre = block.conv(x, with_bias=False) if self.fused_glue and x.is_cuda else None
             if pre is not None and elu_up2_cat_supported(pre, skip):
-                x = elu_up2_cat(pre, skip)
+                x = elu_up2_cat(pre, skip, block.conv.conv.bias)          # the convolution's bias rides along
             else:
-                x = upsample(block.nonlin(pre) if pre is not None else block(x))
+                if pre is not None:
+                    pre = block.nonlin(pre + block.conv.conv.bias.to(pre.dtype).view(1, -1, 1, 1))
+                x = upsample(pre if pre is not None else block(x))
                 if skip is not None:
                     x = torch.cat([x, skip], 1)
             x = self.convs[("upconv", i, 1)](x)

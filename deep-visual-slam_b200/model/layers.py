@@ -163,21 +163,32 @@ class Conv3x3(nn.Module):
         self.pad = nn.ReflectionPad2d(1) if use_refl else nn.ZeroPad2d(1)
         self.conv = nn.Conv2d(int(in_channels), int(out_channels), 3)
 
-    def forward(self, x):
+    def forward(self, x, with_bias: bool = True):
+        """``with_bias=False``: the convolution alone -- the caller folds ``self.conv.bias`` into the kernel that consumes the
+        result (``dvsloss.ops.bias_elu`` / ``elu_up2_cat``), saving the separate bias pass cuDNN's path runs."""
+        bias = self.conv.bias if with_bias else None
         if self.use_refl and self.fast_reflect and x.shape[2] >= 3 and x.shape[3] >= 3:
-            return conv3x3_reflect(x, self.conv.weight, self.conv.bias)
-        return self.conv(self.pad(x))
+            return conv3x3_reflect(x, self.conv.weight, bias)
+        return F.conv2d(self.pad(x), self.conv.weight, bias)
 
 
 class ConvBlock(nn.Module):
-    """Conv3x3 + ELU of the decoder -- stock PyTorch."""
+    """Conv3x3 + ELU of the decoder (reference: model/layers.py:106-117): stock convolution; on CUDA the convolution's bias
+    and the ELU run as one fused kernel each way."""
 
     def __init__(self, in_channels: int, out_channels: int):
         super().__init__()
         self.conv = Conv3x3(in_channels, out_channels)
         self.nonlin = nn.ELU(inplace=True)
 
+    fused_bias_elu = True       # CUDA: convolution without bias, then bias + ELU as one kernel each way (dvsloss.ops.bias_elu)
+
     def forward(self, x):
+        if self.fused_bias_elu and x.is_cuda and self.conv.conv.out_channels % 8 == 0:
+            pre = self.conv(x, with_bias=False)
+            if _ops.bias_elu_supported(pre):
+                return _ops.bias_elu(pre, self.conv.conv.bias)
+            return self.nonlin(pre + self.conv.conv.bias.to(pre.dtype).view(1, -1, 1, 1))
         return self.nonlin(self.conv(x))
 
 

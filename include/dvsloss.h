@@ -255,15 +255,25 @@ int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int disp_dtype, c
                       void* workspace, void* stream);
 
 /* Decoder glue of DepthNet, fused (model/depthnet.py:77-84: ConvBlock's ELU, model/layers.py:106-117; `upsample`,
- * model/layers.py:196-199; torch.cat with the encoder skip): out = cat([nearest_up2(ELU(x)), skip], channels), one pass.
- * CHANNELS-LAST tensors of one dtype (fp32 or bf16), 16-byte aligned: x [B,h,w,C1] (the convolution output BEFORE the ELU),
- * skip [B,2h,2w,C2] (NULL iff C2 == 0), out [B,2h,2w,C1+C2]; C1, C2 multiples of 8 (bf16) / 4 (fp32). */
-int dvs_elu_up2_cat_fwd(const void* x, const void* skip, void* out, int dtype, int B, int C1, int C2, int h, int w,
-                        void* stream);
-/* Backward: grad_out [B,2h,2w,C1+C2] -> grad_x [B,h,w,C1] = ELU'(x) * (2x2 sum of grad_out, fp32, fixed order) and
- * grad_skip [B,2h,2w,C2] (NULL iff C2 == 0). */
-int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, void* grad_x, void* grad_skip, int dtype, int B, int C1, int C2,
+ * model/layers.py:196-199; torch.cat with the encoder skip): out = cat([nearest_up2(ELU(x + bias)), skip], channels), one pass.
+ * CHANNELS-LAST tensors of one dtype (fp32 or bf16), 16-byte aligned: x [B,h,w,C1] (the convolution output BEFORE bias and
+ * ELU; bias fp32 [C1] or NULL: the Conv2d bias, model/layers.py:131, folded in so that the convolution runs without its
+ * separate bias pass), skip [B,2h,2w,C2] (NULL iff C2 == 0), out [B,2h,2w,C1+C2]; C1, C2 multiples of 8 (bf16) / 4 (fp32). */
+int dvs_elu_up2_cat_fwd(const void* x, const void* skip, const float* bias, void* out, int dtype, int B, int C1, int C2,
                         int h, int w, void* stream);
+/* Backward: grad_out [B,2h,2w,C1+C2] -> grad_x [B,h,w,C1] = ELU'(x + bias) * (2x2 sum of grad_out, fp32, fixed order),
+ * grad_skip [B,2h,2w,C2] (NULL iff C2 == 0) and, if grad_bias != NULL, grad_bias [C1] fp32 = the per-channel sums of grad_x
+ * (two-stage fixed-order reduction; needs `workspace` of dvs_glue_workspace_bytes(C1) bytes, 256-byte aligned, and C1 / 8
+ * (bf16) or C1 / 4 (fp32) a power of two <= 256). */
+int dvs_glue_workspace_bytes(int C, size_t* bytes);
+int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, const float* bias, void* grad_x, void* grad_skip, float* grad_bias,
+                        int dtype, int B, int C1, int C2, int h, int w, void* workspace, void* stream);
+/* ConvBlock's bias + ELU (model/layers.py:106-117 with the Conv2d bias of :131) in one pass: y = ELU(x + bias[c]),
+ * channels-last [B,H,W,C], y may alias x.  Backward from the OUTPUT, as nn.ELU(inplace=True) does: grad_x = grad_y *
+ * (y <= 0 ? y + 1 : 1); grad_bias [C] fp32 (optional) as above. */
+int dvs_bias_elu_fwd(const void* x, const float* bias, void* y, int dtype, int B, int C, int H, int W, void* stream);
+int dvs_bias_elu_bwd(const void* y, const void* grad_y, void* grad_x, float* grad_bias, int dtype, int B, int C, int H, int W,
+                     void* workspace, void* stream);
 
 /* Supervised-depth path (depth/depth_learner.py).  SILog loss (:75-95): over the n elements with valid[e] != 0,
  * d = log(max(pred, 1e-6)) - log(target), loss = sqrt(mean(d^2) - variance_focus * mean(d)^2).  stats [4] receives

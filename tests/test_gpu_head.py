@@ -92,7 +92,9 @@ def test_depthnet_uses_the_fused_head_and_trains_like_the_stock_net():
         assert float((outs[True][1][n] - gr).abs().max()) <= 1e-3 * scale, n
 
 
-def _stock_glue(x, skip):
+def _stock_glue(x, skip, bias=None):
+    if bias is not None:
+        x = x + bias.to(x.dtype).view(1, -1, 1, 1)
     y = F.interpolate(F.elu(x), scale_factor=2, mode="nearest")
     return y if skip is None else torch.cat([y, skip], 1)
 
@@ -110,17 +112,18 @@ def test_elu_up2_cat_fp32_matches_stock_ops(B, C1, C2, h, w, channels_last):
     if channels_last:
         x = x.contiguous(memory_format=torch.channels_last)
         skip = skip.contiguous(memory_format=torch.channels_last) if skip is not None else None
-    leaves = [t.requires_grad_(True) for t in (x, skip) if t is not None]
-    got = elu_up2_cat(x, skip)
-    ref = _stock_glue(x, skip)
+    bias = torch.randn(C1, device=dev) if (h + C1) % 2 else None            # the convolution's bias folded in, or not
+    leaves = [t.requires_grad_(True) for t in (x, skip, bias) if t is not None]
+    got = elu_up2_cat(x, skip, bias)
+    ref = _stock_glue(x, skip, bias)
     assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
-    assert float((got - ref).abs().max()) <= 2e-7
+    assert float((got - ref).abs().max()) <= 4e-7
     g = torch.randn_like(ref)
     gg = torch.autograd.grad(got, leaves, g)
     gr = torch.autograd.grad(ref, leaves, g)
     for a, r in zip(gg, gr):
-        assert float((a - r).abs().max()) <= 1e-6 * (float(r.abs().max()) + 1e-30)
-    assert all(torch.equal(a, b_) for a, b_ in zip(gg, torch.autograd.grad(elu_up2_cat(x, skip), leaves, g)))
+        assert float((a - r).abs().max()) <= 2e-6 * (float(r.abs().max()) + 1e-30)
+    assert all(torch.equal(a, b_) for a, b_ in zip(gg, torch.autograd.grad(elu_up2_cat(x, skip, bias), leaves, g)))   # fixed-order sums
 
 
 def test_elu_up2_cat_bf16_matches_stock_ops_within_rounding():
@@ -142,6 +145,30 @@ def test_elu_up2_cat_bf16_matches_stock_ops_within_rounding():
     assert float((gg[0].double() - gr[0]).abs().max()) <= 2 ** -7 * float(gr[0].abs().max())               # fp32 sum, one bf16 rounding
 
 
+@pytest.mark.parametrize("B,C,H,W,dtype", [(2, 16, 12, 20, torch.float32), (1, 256, 3, 5, torch.float32), (3, 64, 9, 7, torch.bfloat16),
+                                            (2, 32, 33, 17, torch.bfloat16)])
+def test_bias_elu_matches_stock_ops(B, C, H, W, dtype):
+    """ConvBlock's bias + ELU as one kernel each way; the backward is written from the output like nn.ELU(inplace=True)."""
+    from dvsloss.ops import bias_elu
+    torch.manual_seed(C + W)
+    dev = torch.device("cuda:0")
+    x = torch.randn(B, C, H, W, device=dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    bias = torch.randn(C, device=dev).requires_grad_(True)
+    got = bias_elu(x, bias)
+    xd, bd = x.detach().double().requires_grad_(True), bias.detach().double().requires_grad_(True)
+    ref = F.elu(xd + bd.view(1, -1, 1, 1))
+    tol = 2e-7 if dtype == torch.float32 else 2 ** -8
+    assert got.dtype == dtype and float((got.double() - ref).abs().max()) <= tol * (1 + float(ref.abs().max()))
+    g = torch.randn(B, C, H, W, device=dev).to(dtype)
+    gx, gb = torch.autograd.grad(got, (x, bias), g)
+    rx, rb = torch.autograd.grad(ref, (xd, bd), g.double())
+    gtol = 2e-6 if dtype == torch.float32 else 2 ** -6                       # bf16: y + 1 is rounded once more, as in ATen's in-place ELU
+    assert float((gx.double() - rx).abs().max()) <= gtol * float(rx.abs().max())
+    assert float((gb.double() - rb).abs().max()) <= gtol * float(rb.abs().max()) * (1 if dtype == torch.float32 else 4)
+    gx2, gb2 = torch.autograd.grad(bias_elu(x, bias), (x, bias), g)
+    assert torch.equal(gx, gx2) and torch.equal(gb, gb2)                     # fixed-order reduction
+
+
 def test_depthnet_fused_glue_trains_like_the_stock_sequence():
     from model.depthnet import DepthNet
     torch.manual_seed(2)
@@ -151,8 +178,9 @@ def test_depthnet_fused_glue_trains_like_the_stock_sequence():
     outs = {}
     tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
+    from model.layers import ConvBlock
     for fused in (True, False):
-        DepthNet.fused_glue = fused
+        DepthNet.fused_glue = ConvBlock.fused_bias_elu = fused
         try:
             net.zero_grad()
             o = net(x)
@@ -160,7 +188,7 @@ def test_depthnet_fused_glue_trains_like_the_stock_sequence():
             outs[fused] = ({k: v.detach().clone() for k, v in o.items()},
                            {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None})
         finally:
-            DepthNet.fused_glue = True
+            DepthNet.fused_glue = ConvBlock.fused_bias_elu = True
     torch.backends.cudnn.allow_tf32 = tf32
     for k in outs[False][0]:
         assert torch.allclose(outs[True][0][k], outs[False][0][k], rtol=0, atol=5e-6), k
