@@ -5,6 +5,7 @@
 //
 // All kernels are HBM-bound elementwise / stencil / gather passes: coalesced along W, no atomics,
 // reductions are two-stage in a fixed order (run-to-run reproducible).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -888,5 +889,114 @@ extern "C" int dvs_depth_to_pointcloud(const float* depth, const float* inv_K, c
   if (gx > 148 * 8) gx = 148 * 8;
   pointcloud_kernel<<<gx, 256, 0, ST(stream)>>>(depth, inv_K, T, points, valid, H, W);
   LAUNCH_CHECK();
+  return DVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ network inputs
+// What the training step does to a batch before the first convolutions, in one pass: the channels-last copies of the three
+// frames (vo/train.py feeds NCHW fp32 tensors from the loader, vo/dataset/common.py:77), the concatenated pose pairs
+// [source, target] / [target, source] (vo/learner_new.py:110-123), the encoders' (x - 0.45) / 0.225 (model/resnet_encoder.py
+// forward) and the cast autocast applies at conv1.  Reads each frame once, writes the target [B,H,W,3] and one [B,H,W,6] pair per
+// source.  The arithmetic is the stock one on CUDA (fp32 subtract, multiply by the fp32 reciprocal of 0.225 -- ATen's tensor / scalar --,
+// one round-to-nearest bf16 conversion): same bits.
+namespace dvs {
+namespace {
+template <bool OBF, int N>
+__device__ __forceinline__ void store_px(void* base, size_t elem, const float* v) {      // N consecutive elements, 16-byte aligned
+  if (OBF) {
+    uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + elem);
+#pragma unroll
+    for (int q = 0; q < N / 8; ++q) {
+      unsigned int w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[q * 8 + 2 * k], v[q * 8 + 2 * k + 1]);
+        w[k] = *reinterpret_cast<const unsigned int*>(&h);
+      }
+      o[q] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+    float4* o = reinterpret_cast<float4*>(static_cast<float*>(base) + elem);
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+// one thread = 8 consecutive pixels of one image row
+template <bool OBF>
+__global__ void __launch_bounds__(256) pack_net_inputs_kernel(const float* __restrict__ target, const float* const* __restrict__ dummy,
+                                                              const float* s0, const float* s1, const float* s2, const float* s3,
+                                                              int nsrc, unsigned int src_first_mask, int normalize, void* out_target,
+                                                              void* p0, void* p1, void* p2, void* p3, int HW, size_t ngroups) {
+  (void)dummy;
+  const size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= ngroups) return;
+  const size_t per_img = (size_t)HW / 8;
+  const size_t b = gidx / per_img;
+  const size_t pix0 = (gidx - b * per_img) * 8;                    // first pixel of the group inside the image
+  const float* srcs[4] = {s0, s1, s2, s3};
+  void* pairs[4] = {p0, p1, p2, p3};
+  auto load8 = [&](const float* img, int c, float* v) {
+    const float4* q = reinterpret_cast<const float4*>(img + (b * 3 + c) * (size_t)HW + pix0);
+    const float4 a = q[0], d = q[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
+    if (normalize)
+      for (int i = 0; i < 8; ++i) v[i] = (v[i] - 0.45f) * (1.0f / 0.225f);   // ATen's CUDA tensor / scalar: times the fp32 reciprocal
+  };
+  float t[3][8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) load8(target, c, t[c]);
+  {
+    float o[24];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[i * 3 + c] = t[c][i];
+    store_px<OBF, 24>(out_target, (b * HW + pix0) * 3, o);
+  }
+  for (int k = 0; k < nsrc; ++k) {
+    float s[3][8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) load8(srcs[k], c, s[c]);
+    const bool first = (src_first_mask >> k) & 1u;
+    float o[48];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        o[i * 6 + c] = first ? s[c][i] : t[c][i];
+        o[i * 6 + 3 + c] = first ? t[c][i] : s[c][i];
+      }
+    store_px<OBF, 48>(pairs[k], (b * HW + pix0) * 6, o);
+  }
+}
+}  // namespace
+}  // namespace dvs
+
+extern "C" int dvs_pack_net_inputs(const float* target, const float* const* sources, int num_sources, unsigned int src_first_mask,
+                                   int normalize, void* out_target, void* const* out_pairs, int out_dtype, int B, int H, int W,
+                                   void* stream) {
+  using namespace dvs;
+  if (!target || !sources || !out_target || !out_pairs || num_sources < 1 || num_sources > 4 || B < 1 || H < 1 || W < 1)
+    return DVS_EINVAL;
+  if (out_dtype != DVS_DTYPE_F32 && out_dtype != DVS_DTYPE_BF16) return DVS_EINVAL;
+  if (((size_t)H * W) % 8) return DVS_EINVAL;                          // groups of 8 pixels must not straddle images
+  if ((uintptr_t)target & 15) return DVS_EINVAL;
+  const float* s[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int k = 0; k < num_sources; ++k) {
+    s[k] = sources[k];
+    p[k] = out_pairs[k];
+    if (!s[k] || !p[k] || ((uintptr_t)s[k] & 15)) return DVS_EINVAL;
+  }
+  const size_t ngroups = (size_t)B * H * W / 8;
+  const unsigned int nblk = (unsigned int)((ngroups + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (out_dtype == DVS_DTYPE_BF16)
+    pack_net_inputs_kernel<true><<<nblk, 256, 0, st>>>(target, nullptr, s[0], s[1], s[2], s[3], num_sources, src_first_mask, normalize,
+                                                       out_target, p[0], p[1], p[2], p[3], H * W, ngroups);
+  else
+    pack_net_inputs_kernel<false><<<nblk, 256, 0, st>>>(target, nullptr, s[0], s[1], s[2], s[3], num_sources, src_first_mask, normalize,
+                                                        out_target, p[0], p[1], p[2], p[3], H * W, ngroups);
+  DVS_CUDA_TRY(cudaGetLastError());
   return DVS_OK;
 }

@@ -96,6 +96,7 @@ _SIGNATURES = {
     "dvs_silog_fwd": [_vp, _vp, _vp, C.c_int64, C.c_float, _vp, _vp, _vp],
     "dvs_silog_bwd": [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_float, _vp, _vp],
     "dvs_depth_to_pointcloud": [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp],
+    "dvs_pack_net_inputs": [_vp, _vp, C.c_int, C.c_uint, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     "dvs_gather_triplets_u8": [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
 }
 _RESTYPES = {"dvs_error_string": C.c_char_p}

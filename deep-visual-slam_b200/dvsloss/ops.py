@@ -536,6 +536,39 @@ def bias_elu(x: torch.Tensor, bias=None) -> torch.Tensor:
     return _BiasElu.apply(x, bias)
 
 
+# ---------------------------------------------------------------------------------------------------- network inputs
+def pack_net_inputs_supported(target: torch.Tensor, sources) -> bool:
+    ok = lambda t: t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] == 3 and t.is_contiguous()
+    return (ok(target) and 1 <= len(sources) <= 4 and all(ok(s) and s.shape == target.shape for s in sources)
+            and (target.shape[2] * target.shape[3]) % 8 == 0)
+
+
+def pack_net_inputs(target: torch.Tensor, sources, src_first, dtype=torch.float32, normalize: bool = True):
+    """One pass from the sample dict's NCHW fp32 frames to the first convolutions' inputs: the channels-last target
+    [B,3,H,W] and per source the pose pair [B,6,H,W] (``cat([source, target], 1)`` where ``src_first[k]`` else
+    ``cat([target, source], 1)``, vo/learner_new.py:110-123), normalised ``(x - 0.45) / 0.225`` like the encoders do
+    (model/resnet_encoder.py) and cast to ``dtype`` (bf16: what autocast hands conv1).  Same bits as the stock sequence."""
+    import ctypes as C
+    from ._lib import DTYPE_BF16, DTYPE_F32
+    if not pack_net_inputs_supported(target, sources):
+        raise DvsError("pack_net_inputs needs contiguous CUDA fp32 [B,3,H,W] frames with H*W a multiple of 8, 1..4 sources")
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise DvsError("pack_net_inputs writes float32 or bfloat16")
+    B, _, H, W = target.shape
+    dev = target.device
+    out_t = torch.empty(B, 3, H, W, dtype=dtype, device=dev, memory_format=torch.channels_last)
+    pairs = [torch.empty(B, 6, H, W, dtype=dtype, device=dev, memory_format=torch.channels_last) for _ in sources]
+    mask = sum(1 << k for k, f in enumerate(src_first) if f)
+    VP = C.c_void_p
+    parr = (VP * len(pairs))(*[VP(p.data_ptr()) for p in pairs])
+    from ._lib import fptr_array
+    with torch.cuda.device(dev):
+        check(lib().dvs_pack_net_inputs(ptr(target), fptr_array(list(sources)), len(sources), mask, int(bool(normalize)), out_t.data_ptr(),
+                                        parr, DTYPE_BF16 if dtype == torch.bfloat16 else DTYPE_F32, B, H, W, stream_ptr(dev)),
+              "dvs_pack_net_inputs")
+    return out_t, pairs
+
+
 # ---------------------------------------------------------------------------------------------------- supervised depth
 class _Silog(torch.autograd.Function):
     @staticmethod

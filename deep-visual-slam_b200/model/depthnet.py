@@ -45,8 +45,8 @@ class DepthNet(nn.Module):
             self.convs[("dispconv", s)] = Conv3x3(self.num_ch_dec[s], num_output_channels)
         self.decoder = nn.ModuleList(self.convs.values())
 
-    def forward(self, input_data: torch.Tensor) -> dict:
-        feats = self.encoder(input_data)
+    def forward(self, input_data: torch.Tensor, normalized: bool = False) -> dict:
+        feats = self.encoder(input_data, normalized) if normalized else self.encoder(input_data)
         outputs = {}
         x = feats[-1]
         for i in range(4, -1, -1):

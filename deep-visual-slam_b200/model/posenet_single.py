@@ -21,9 +21,10 @@ class PoseNet(nn.Module):
         self.net = nn.ModuleList([nn.Conv2d(int(self.num_ch_enc[-1]), 256, 1), nn.Conv2d(256, 256, 3, stride, 1),
                                   nn.Conv2d(256, 256, 3, stride, 1), nn.Conv2d(256, 6, 1)])
 
-    def forward(self, input_images: torch.Tensor):
+    def forward(self, input_images: torch.Tensor, normalized: bool = False):
         squeeze, pose0, pose1, pose2 = self.net
-        x = torch.relu(squeeze(self.encoder(input_images)[-1]))
+        feats = self.encoder(input_images, normalized) if normalized else self.encoder(input_images)
+        x = torch.relu(squeeze(feats[-1]))
         x = torch.relu(pose0(x))
         x = torch.relu(pose1(x))
         out = 0.01 * pose2(x).mean(3).mean(2).view(-1, 1, 1, 6)

@@ -42,9 +42,11 @@ class ResnetEncoder(nn.Module):
             self.num_ch_enc[1:] *= 4
         self.encoder = _build(num_layers, pretrained, num_input_images)
 
-    def forward(self, input_image: torch.Tensor):
+    def forward(self, input_image: torch.Tensor, normalized: bool = False):
+        """``normalized=True``: the input already went through ``(x - 0.45) / 0.225`` (dvsloss.ops.pack_net_inputs does it
+        while it builds the channels-last network inputs)."""
         e = self.encoder
-        x = (input_image - 0.45) / 0.225
+        x = input_image if normalized else (input_image - 0.45) / 0.225
         f0 = e.relu(e.bn1(e.conv1(x)))
         f1 = e.layer1(e.maxpool(f0))
         f2 = e.layer2(f1)

@@ -52,7 +52,9 @@ class VoNets(nn.Module):
         super().__init__()
         self.depth_net, self.pose_net = depth_net, pose_net
 
-    def forward(self, target: torch.Tensor, pairs):
+    def forward(self, target: torch.Tensor, pairs, normalized: bool = False):
+        if normalized:                                   # inputs built by dvsloss.ops.pack_net_inputs
+            return self.depth_net(target, True), [self.pose_net(p, True) for p in pairs]
         disp = self.depth_net(target)
         poses = [self.pose_net(p) for p in pairs]
         return disp, poses
@@ -77,16 +79,28 @@ class _Bound:
 class JointForward:
     """Runs VoNets once per step and hands the results to the learner's separate network calls."""
 
-    def __init__(self, module: nn.Module, frame_ids=(-1, 1)):
-        self.module, self.frame_ids = module, list(frame_ids)
+    def __init__(self, module: nn.Module, frame_ids=(-1, 1), channels_last: bool = False):
+        self.module, self.frame_ids, self.channels_last = module, list(frame_ids), channels_last
         self._disp, self._poses = None, []
+
+    pack_inputs = True       # CUDA: one kernel builds the channels-last, normalised, autocast-dtype network inputs
 
     def run(self, sample: Dict) -> None:
         tgt = sample[("target_image", 0)]
-        pairs = []
-        for f in self.frame_ids:
-            src = sample[("source_left", 0) if f == -1 else ("source_right", 0) if f == 1 else ("source", f)]
-            pairs.append(torch.cat([src, tgt], 1) if f < 0 else torch.cat([tgt, src], 1))
+        srcs = [sample[("source_left", 0) if f == -1 else ("source_right", 0) if f == 1 else ("source", f)] for f in self.frame_ids]
+        if self.pack_inputs and self.channels_last and tgt.is_cuda:       # the packed inputs are channels-last
+            from dvsloss import ops
+            if ops.pack_net_inputs_supported(tgt, srcs):
+                dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
+                if dt in (torch.float32, torch.bfloat16):
+                    t_in, pairs = ops.pack_net_inputs(tgt, srcs, [f < 0 for f in self.frame_ids], dt)
+                    self._disp, poses = self.module(t_in, pairs, True)
+                    self._poses = list(poses)
+                    return
+        if self.channels_last:
+            tgt = tgt.contiguous(memory_format=torch.channels_last)
+            srcs = [s.contiguous(memory_format=torch.channels_last) for s in srcs]
+        pairs = [torch.cat([src, tgt], 1) if f < 0 else torch.cat([tgt, src], 1) for f, src in zip(self.frame_ids, srcs)]
         self._disp, poses = self.module(tgt, pairs)
         self._poses = list(poses)
 
@@ -127,7 +141,7 @@ class Trainer:
         self._graph = None
         self.scheduler = PolynomialLR(self.optimizer, total_iters=tr["epoch"], power=0.9)
         self.frame_ids = list(frame_ids)
-        self.joint = JointForward(module, self.frame_ids)
+        self.joint = JointForward(module, self.frame_ids, self.channels_last)
         self.learner = MonodepthTrainer(_Bound(self.joint, "depth"), _Bound(self.joint, "pose"), self.config, self.device,
                                         frame_ids=self.frame_ids, noise=noise)
 
@@ -139,9 +153,9 @@ class Trainer:
                 sample[key] = val.to(self.device, non_blocking=True)
         if self.net_dtype is not None:
             with torch.autocast(self.device.type, dtype=self.net_dtype):
-                self.joint.run(self._images(sample))
+                self.joint.run(sample)
         else:
-            self.joint.run(self._images(sample))
+            self.joint.run(sample)
         outputs, losses = self.learner.process_batch(sample)
         total = losses["loss"]
         total.backward()

@@ -300,6 +300,16 @@ int dvs_depth_to_pointcloud(const float* depth, const float* inv_K, const float*
 int dvs_gather_triplets_u8(const uint8_t* frames, int frames_hwc, const int32_t* idx, void* out_left, void* out_target,
                            void* out_right, int out_dtype, int B, int H, int W, void* stream);
 
+/* Network inputs of a training step in one pass: from the NCHW fp32 frames of the sample dict (vo/dataset/common.py:77) to
+ * what the first convolutions of DepthNet / PoseNet read -- the channels-last target [B,H,W,3] and, per source k, the
+ * concatenated pose pair [B,H,W,6] ([source, target] if bit k of src_first_mask is set, as for the frames before the target,
+ * else [target, source]; vo/learner_new.py:110-123), optionally normalised as the encoders do, (x - 0.45) / 0.225
+ * (model/resnet_encoder.py forward), in out_dtype (fp32, or bf16 = autocast's cast at conv1).  H * W must be a multiple of 8;
+ * inputs 16-byte aligned.  Same arithmetic as the stock sequence on CUDA (fp32 subtract, times the fp32 reciprocal of 0.225 as
+ * ATen's tensor / scalar does, one rounding to bf16). */
+int dvs_pack_net_inputs(const float* target, const float* const* sources, int num_sources, unsigned int src_first_mask,
+                        int normalize, void* out_target, void* const* out_pairs, int out_dtype, int B, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

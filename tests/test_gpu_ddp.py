@@ -32,7 +32,7 @@ def _exact_convs():
 def _one_backward(tr, sample):
     """forward + backward of the training step without the optimizer update (so the gradients can be compared)."""
     tr.optimizer.zero_grad(set_to_none=True)
-    tr.joint.run(tr._images(sample))
+    tr.joint.run(sample)
     _, losses = tr.learner.process_batch(sample)
     losses["loss"].backward()
     return float(losses["loss"])

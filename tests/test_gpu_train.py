@@ -107,3 +107,41 @@ def test_pose_parameters_inside_the_loss_match_the_matrix_path():
         assert torch.equal(a, b)
     for a, b in zip(ga1 + gt1, ga2 + gt2):
         assert a.shape == b.shape and float((a - b).abs().max()) <= 1e-6 * float(b.abs().max()) + 1e-12
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pack_net_inputs_gives_the_bits_of_the_stock_sequence(dtype):
+    """channels-last copies + pose-pair concatenation + (x - 0.45) / 0.225 + autocast's cast at conv1, as one kernel."""
+    from dvsloss import ops
+    torch.manual_seed(0)
+    B, H, W = 3, 20, 28
+    tgt, s0, s1, s2 = (torch.rand(B, 3, H, W, device="cuda") for _ in range(4))
+    t_in, pairs = ops.pack_net_inputs(tgt, [s0, s1, s2], [True, False, True], dtype)
+    norm = lambda x: ((x - 0.45) / 0.225)
+    ref_t = norm(tgt).to(dtype)
+    refs = [norm(torch.cat([s0, tgt], 1)).to(dtype), norm(torch.cat([tgt, s1], 1)).to(dtype), norm(torch.cat([s2, tgt], 1)).to(dtype)]
+    assert t_in.is_contiguous(memory_format=torch.channels_last) and torch.equal(t_in, ref_t)
+    for p, r in zip(pairs, refs):
+        assert p.shape == (B, 6, H, W) and p.is_contiguous(memory_format=torch.channels_last) and torch.equal(p, r)
+    raw_t, raw_p = ops.pack_net_inputs(tgt, [s0], [False], torch.float32, normalize=False)
+    assert torch.equal(raw_t, tgt) and torch.equal(raw_p[0], torch.cat([tgt, s0], 1))
+    assert not ops.pack_net_inputs_supported(tgt[:, :, :, :27].contiguous()[:, :, :19].contiguous(), [s0])      # 19 * 27 is odd
+    with pytest.raises(Exception):
+        ops.pack_net_inputs(tgt.cpu(), [s0.cpu()], [True])
+
+
+def test_training_step_with_packed_inputs_equals_the_stock_input_path():
+    from vo.train import JointForward, synthetic_sample
+    B, H, W = 2, 96, 128
+    sample = synthetic_sample(B, H, W, seed=7, device="cuda")
+    out = {}
+    for packed in (True, False):
+        JointForward.pack_inputs = packed
+        try:
+            torch.manual_seed(3)
+            tr = _trainer(B, H, W, net_dtype=torch.bfloat16, sync_losses=False, noise=None)
+            total, _, losses = tr.train_mono_step(dict(sample))
+            out[packed] = (float(total), [float(losses[f"loss/{s}"]) for s in range(4)])
+        finally:
+            JointForward.pack_inputs = True
+    assert out[True] == out[False]                                # the networks read the same bits either way
