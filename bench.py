@@ -338,7 +338,11 @@ def run_train(args, world, rank, local, dev):
             graph = {"unavailable": repr(exc)[:200]}
     del tr
     torch.cuda.empty_cache()
+    peak, _how = measured_peak_gbs()
+    alg = bytes_alg(Bt, Ht, Wt, len(fids), NSCALE)
     return {"metric": "train_frames_per_s", "value": world * Bt / dt, "unit": "triplets/s", "ms_per_step": dt * 1e3,
+            "hbm_frac_of_loss_bytes": alg / dt / 1e9 / peak,        # north_star: "as a fraction of the HBM roofline" -- the loss path's
+            # algorithmic bytes over the WHOLE step time; the step is bound by the stock networks, not by these bytes
             "batch_per_gpu": Bt, "steps": args.train_steps, "warmup": 3, "final_loss": loss, "cuda_graph": graph,
             "config": f"ResNet-{layers} DepthNet+PoseNet (stock PyTorch, bf16 autocast, channels_last), fused fp32 view-synthesis "
                       f"loss with {len(fids)} source frames, Adam, {Wt}x{Ht}, batch {Bt}/GPU, DDP over NCCL "
