@@ -298,9 +298,10 @@ __device__ __forceinline__ void load_lane_weights(const float* __restrict__ w, i
 template <bool XBF, bool DBF, int LP>
 __global__ void __launch_bounds__(kHeadThreads) disp_head_fwd_tile_kernel(const void* __restrict__ x, const float* __restrict__ w,
                                                                           const float* __restrict__ bias, void* __restrict__ disp,
-                                                                          int H, int W, int tiles_x, int tiles_y) {
+                                                                          int H, int W, int tiles_x, int tiles_y, int xpad) {
   constexpr int C = 8 * LP, PPI = kHeadThreads / LP;         // pixels per pass of the block
   constexpr int NPASS = (kHaloN + PPI - 1) / PPI, U = NPASS < 6 ? NPASS : 6;
+  const int Hp = H + 2 * xpad, Wp = W + 2 * xpad;            // x may carry a reflected ring (then only its interior is read)
   __shared__ float pt[9][kHaloN + 4];
   const int sub = threadIdx.x & (LP - 1), pl = threadIdx.x / LP;
   float wr[9][8];
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(kHeadThreads) disp_head_fwd_tile_kernel(const 
       int gy = reflect1(T.y0 + ly - 1, H), gx = reflect1(T.x0 + lx - 1, W);
       gy = gy < 0 ? 0 : (gy > H - 1 ? H - 1 : gy);            // tiles overhanging the image: any valid address
       gx = gx < 0 ? 0 : (gx > W - 1 ? W - 1 : gx);
-      r[u] = raw_load<XBF>(x, (img + (size_t)gy * W + gx) * C + sub * 8);
+      r[u] = raw_load<XBF>(x, (((size_t)T.b * Hp + gy + xpad) * Wp + gx + xpad) * C + sub * 8);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -412,8 +413,9 @@ __device__ __forceinline__ void tap_sums(const float* gp, int oy, int ox, int yy
 template <bool GBF, bool DBF, bool GXBF, int LP>
 __global__ void __launch_bounds__(kHeadThreads) disp_head_bwd_x_tile_kernel(const void* __restrict__ gdisp, const void* __restrict__ disp,
                                                                             const float* __restrict__ w, void* __restrict__ gx, int H,
-                                                                            int W, int tiles_x, int tiles_y, int ntiles) {
+                                                                            int W, int tiles_x, int tiles_y, int ntiles, int xpad) {
   constexpr int C = 8 * LP, PPI = kHeadThreads / LP;
+  const int Hp = H + 2 * xpad, Wp = W + 2 * xpad;            // grad_x in x's layout (the ring, if any, is zeroed by the caller)
   __shared__ float gp[kHaloN];
   const int sub = threadIdx.x & (LP - 1), pl = threadIdx.x / LP;
   float wr[9][8];
@@ -448,7 +450,7 @@ __global__ void __launch_bounds__(kHeadThreads) disp_head_bwd_x_tile_kernel(cons
         for (int t = 0; t < 9; ++t) a = fmaf(wr[t][k], s[t], a);
         o[k] = a;
       }
-      store8<GXBF>(gx, (img + (size_t)yy * W + xx) * C + sub * 8, o);
+      store8<GXBF>(gx, (((size_t)T.b * Hp + yy + xpad) * Wp + xx + xpad) * C + sub * 8, o);
     }
   }
 }
@@ -458,9 +460,10 @@ __global__ void __launch_bounds__(kHeadThreads) disp_head_bwd_x_tile_kernel(cons
 template <bool XBF, bool GBF, bool DBF, int LP>
 __global__ void __launch_bounds__(kHeadThreads) disp_head_bwd_w_tile_kernel(const void* __restrict__ gdisp, const void* __restrict__ disp,
                                                                             const void* __restrict__ x, float* __restrict__ partial,
-                                                                            int H, int W, int tiles_x, int tiles_y, int ntiles) {
+                                                                            int H, int W, int tiles_x, int tiles_y, int ntiles, int xpad) {
   constexpr int C = 8 * LP, PPI = kHeadThreads / LP, NP = 9 * C + 1, NW = kHeadThreads / 32;
   constexpr int NPASS = LP, U = NPASS < 4 ? NPASS : 4;       // activation loads in flight per thread
+  const int Hp = H + 2 * xpad, Wp = W + 2 * xpad;
   extern __shared__ float red[];                       // [NW][NP]; the first kHaloN floats double as the g_pre stage
   float* gp = red;
   const int lane = threadIdx.x & 31, sub = threadIdx.x & (LP - 1), pl = threadIdx.x / LP, wid = threadIdx.x >> 5;
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(kHeadThreads) disp_head_bwd_w_tile_kernel(cons
         const int q = (p0 + u) * PPI + pl, oy = q / kTileW, ox = q - oy * kTileW;
         int yy = T.y0 + oy, xx = T.x0 + ox;
         yy = yy > H - 1 ? H - 1 : yy; xx = xx > W - 1 ? W - 1 : xx;
-        r[u] = raw_load<XBF>(x, (img + (size_t)yy * W + xx) * C + sub * 8);
+        r[u] = raw_load<XBF>(x, (((size_t)T.b * Hp + yy + xpad) * Wp + xx + xpad) * C + sub * 8);
       }
     };
     fetch(0);                                                 // in flight while g_pre is staged
@@ -559,10 +562,11 @@ static int head_chunks(size_t P) {        // pixels per block = 256 * chunks: ab
 
 using namespace dvs;
 
-extern "C" int dvs_disp_head_fwd(const void* x, int x_dtype, const float* weight, const float* bias, void* disp, int disp_dtype,
-                                 int B, int C, int H, int W, void* stream) {
+extern "C" int dvs_disp_head_fwd(const void* x, int x_dtype, int x_pad, const float* weight, const float* bias, void* disp,
+                                 int disp_dtype, int B, int C, int H, int W, void* stream) {
   int rc = head_check(x, x_dtype, B, C, H, W);
   if (rc) return rc;
+  if (x_pad < 0 || x_pad > 1 || (x_pad && !head_grouped(C))) return DVS_EINVAL;
   if (!weight || !disp || (disp_dtype != DVS_DTYPE_F32 && disp_dtype != DVS_DTYPE_BF16)) return DVS_EINVAL;
   const size_t P = (size_t)B * H * W;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -572,10 +576,10 @@ extern "C" int dvs_disp_head_fwd(const void* x, int x_dtype, const float* weight
     const int grid = head_tiles(B, H, W, &tx, &ty);
 #define DVS_HEAD_FWD(LP)                                                                                                      \
   do {                                                                                                                        \
-    if (xb && db) disp_head_fwd_tile_kernel<true, true, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty);  \
-    else if (xb) disp_head_fwd_tile_kernel<true, false, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty);  \
-    else if (db) disp_head_fwd_tile_kernel<false, true, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty);  \
-    else disp_head_fwd_tile_kernel<false, false, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty);         \
+    if (xb && db) disp_head_fwd_tile_kernel<true, true, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty, x_pad);  \
+    else if (xb) disp_head_fwd_tile_kernel<true, false, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty, x_pad);  \
+    else if (db) disp_head_fwd_tile_kernel<false, true, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty, x_pad);  \
+    else disp_head_fwd_tile_kernel<false, false, LP><<<grid, kHeadThreads, 0, st>>>(x, weight, bias, disp, H, W, tx, ty, x_pad);         \
   } while (0)
     switch (C / 8) {
       case 1: DVS_HEAD_FWD(1); break;
@@ -623,11 +627,12 @@ static int head_bwd_launch(const void* gdisp, const void* disp, const void* x, c
   return DVS_OK;
 }
 
-extern "C" int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int disp_dtype, const void* x, int x_dtype,
+extern "C" int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int disp_dtype, const void* x, int x_dtype, int x_pad,
                                  const float* weight, void* grad_x, float* grad_weight, float* grad_bias, int B, int C, int H,
                                  int W, void* workspace, void* stream) {
   int rc = head_check(x, x_dtype, B, C, H, W);
   if (rc) return rc;
+  if (x_pad < 0 || x_pad > 1 || (x_pad && !head_grouped(C))) return DVS_EINVAL;
   if (!grad_disp || !disp || !weight || !grad_x || !grad_weight) return DVS_EINVAL;
   if (disp_dtype != DVS_DTYPE_F32 && disp_dtype != DVS_DTYPE_BF16) return DVS_EINVAL;
   if (!workspace || ((uintptr_t)workspace & 255) || ((uintptr_t)grad_x & 15)) return DVS_EWORKSPACE;
@@ -643,9 +648,9 @@ extern "C" int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int di
 #define DVS_HEAD_BWD(XB, GB, LP)                                                                                              \
   do {                                                                                                                        \
     disp_head_bwd_x_tile_kernel<GB, GB, XB, LP><<<grid, kHeadThreads, 0, st>>>(grad_disp, disp, weight, grad_x, H, W, tx, ty,     \
-                                                                              ntiles);                                       \
+                                                                              ntiles, x_pad);                                       \
     disp_head_bwd_w_tile_kernel<XB, GB, GB, LP><<<grid, kHeadThreads, smem_w, st>>>(grad_disp, disp, x, partial, H, W, tx, ty,    \
-                                                                                   ntiles);                                  \
+                                                                                   ntiles, x_pad);                                  \
   } while (0)
 #define DVS_HEAD_BWD_LP(LP)                                                                                                   \
   do {                                                                                                                        \
@@ -714,6 +719,46 @@ struct Vec16 {
 __device__ __forceinline__ float elu_value(float a) { return a <= 0.f ? expf(a) - 1.f : a; }          // ATen elu_kernel, alpha = scale = 1
 __device__ __forceinline__ float elu_slope(float a) { return a <= 0.f ? expf(a) : 1.f; }              // ATen elu_backward_kernel (is_result = false)
 
+// Activations with a reflected ring.  The decoder's convolutions are reflection-padded (model/layers.py:126-136); the kernels
+// that PRODUCE their inputs can write the one-pixel ring themselves (pad = 1: tensor [B, H+2, W+2, C], ring row -1 = row 1,
+// row H = row H-2, columns alike), so that the stock convolution runs un-padded on that buffer -- no padded copy and no border
+// fix-up convolutions -- and the kernels that consume the convolution's input gradient fold the ring's gradients back.
+__device__ __forceinline__ size_t pvec(size_t b, int y, int x, int H, int W, int pad, int vpp, int v) {
+  return ((b * (size_t)(H + 2 * pad) + (size_t)(y + pad)) * (size_t)(W + 2 * pad) + (size_t)(x + pad)) * vpp + v;
+}
+// the rows (columns) that hold pixel row y: itself, and the ring rows that mirror it
+__device__ __forceinline__ int ring_coords(int y, int H, int pad, int* ys) {
+  int n = 0;
+  ys[n++] = y;
+  if (pad) {
+    if (y == 1) ys[n++] = -1;
+    if (y == H - 2) ys[n++] = H;
+  }
+  return n;
+}
+__device__ __forceinline__ void store_with_ring(uint4* out, uint4 val, size_t b, int y, int x, int H, int W, int pad, int vpp, int v) {
+  int ys[3], xs[3];
+  const int ny = ring_coords(y, H, pad, ys), nx = ring_coords(x, W, pad, xs);
+  for (int i = 0; i < ny; ++i)
+    for (int j = 0; j < nx; ++j) out[pvec(b, ys[i], xs[j], H, W, pad, vpp, v)] = val;
+}
+// gradient reaching pixel (y, x): its own entry plus those of the ring positions that mirror it (fixed order), in fp32
+template <bool BF>
+__device__ __forceinline__ void load_folded(const uint4* g, size_t b, int y, int x, int H, int W, int pad, int vpp, int v, float* f) {
+  constexpr int N = BF ? 8 : 4;
+  int ys[3], xs[3];
+  const int ny = ring_coords(y, H, pad, ys), nx = ring_coords(x, W, pad, xs);
+#pragma unroll
+  for (int k = 0; k < N; ++k) f[k] = 0.f;
+  for (int i = 0; i < ny; ++i)
+    for (int j = 0; j < nx; ++j) {
+      Vec16<BF> q;
+      q.raw = g[pvec(b, ys[i], xs[j], H, W, pad, vpp, v)];
+#pragma unroll
+      for (int k = 0; k < N; ++k) f[k] += q.get(k);
+    }
+}
+
 // Per-channel sums over the pixels (the bias gradients) of the glue kernels: every thread keeps its N channels' sums over a
 // grid-stride walk whose stride is a multiple of the vectors per pixel (so the thread's channels never change), the block
 // adds the threads that own the same channels in thread order, and channel_reduce_kernel adds the blocks in block order.
@@ -740,44 +785,47 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const float* __rest
   if (lane == 0) out[c] = a;
 }
 
-// one thread per 16-byte vector of `out` [B, 2h, 2w, C1 + C2]; bias (fp32 [C1], may be null) is added before the ELU
+// one thread per 16-byte vector of `out` [B, 2h, 2w, C1 + C2] (+ ring if pad); bias (fp32 [C1], may be null) is added before
+// the ELU
 template <bool BF>
 __global__ void __launch_bounds__(256) elu_up2_cat_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip,
                                                               const float* __restrict__ bias, uint4* __restrict__ out, int h, int w,
-                                                              int v1, int v2, size_t nvec) {
+                                                              int v1, int v2, int pad, size_t nvec) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nvec) return;
   const int vt = v1 + v2;
   const size_t pix = e / vt;
   const int v = (int)(e - pix * vt);
-  if (v >= v1) {
-    out[e] = skip[pix * v2 + (v - v1)];
-    return;
-  }
   const int W2 = 2 * w, H2 = 2 * h;
   const int X = (int)(pix % W2);
   const size_t r = pix / W2;
   const int Y = (int)(r % H2);
   const size_t b = r / H2;
-  constexpr int N = Vec16<BF>::N;
-  Vec16<BF> a;
-  a.raw = x[((b * h + (Y >> 1)) * w + (X >> 1)) * v1 + v];
-  float f[N];
-  for (int i = 0; i < N; ++i) f[i] = elu_value(a.get(i) + (bias ? bias[v * N + i] : 0.f));
-  Vec16<BF> o;
-  o.set_all(f);
-  out[e] = o.raw;
+  uint4 val;
+  if (v >= v1) {
+    val = skip[pix * v2 + (v - v1)];
+  } else {
+    constexpr int N = Vec16<BF>::N;
+    Vec16<BF> a;
+    a.raw = x[((b * h + (Y >> 1)) * w + (X >> 1)) * v1 + v];
+    float f[N];
+    for (int i = 0; i < N; ++i) f[i] = elu_value(a.get(i) + (bias ? bias[v * N + i] : 0.f));
+    Vec16<BF> o;
+    o.set_all(f);
+    val = o.raw;
+  }
+  store_with_ring(out, val, b, Y, X, H2, W2, pad, vt, v);
 }
 
-// grad_x [B, h, w, C1]: 2x2 sum of grad_out (fixed order) times ELU'(x + bias); grid-stride, per-channel sums of grad_x for
-// the bias gradient (partial != null)
+// grad_x [B, h, w, C1]: 2x2 sum of grad_out (fixed order; ring gradients folded in if pad) times ELU'(x + bias); grid-stride,
+// per-channel sums of grad_x for the bias gradient (partial != null)
 template <bool BF>
 __global__ void __launch_bounds__(kGlueThreads) elu_up2_cat_bwd_x_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gout,
                                                                          const float* __restrict__ bias, uint4* __restrict__ gx,
                                                                          float* __restrict__ partial, int h, int w, int v1, int v2,
-                                                                         size_t nvec) {
+                                                                         int pad, size_t nvec) {
   constexpr int N = Vec16<BF>::N;
-  const int vt = v1 + v2, W2 = 2 * w;
+  const int vt = v1 + v2, W2 = 2 * w, H2 = 2 * h;
   float acc[N], bv[N];
   const int v = threadIdx.x % v1;                             // constant along the walk: the stride is a multiple of v1
 #pragma unroll
@@ -788,17 +836,17 @@ __global__ void __launch_bounds__(kGlueThreads) elu_up2_cat_bwd_x_kernel(const u
     const size_t r = pix / w;
     const int yy = (int)(r % h);
     const size_t b = r / h;
-    const size_t o00 = ((b * 2 * h + 2 * yy) * W2 + 2 * xx) * vt + v;
-    Vec16<BF> g00, g01, g10, g11, a;
-    g00.raw = gout[o00];
-    g01.raw = gout[o00 + vt];
-    g10.raw = gout[o00 + (size_t)W2 * vt];
-    g11.raw = gout[o00 + (size_t)W2 * vt + vt];
+    float g00[N], g01[N], g10[N], g11[N];
+    load_folded<BF>(gout, b, 2 * yy, 2 * xx, H2, W2, pad, vt, v, g00);
+    load_folded<BF>(gout, b, 2 * yy, 2 * xx + 1, H2, W2, pad, vt, v, g01);
+    load_folded<BF>(gout, b, 2 * yy + 1, 2 * xx, H2, W2, pad, vt, v, g10);
+    load_folded<BF>(gout, b, 2 * yy + 1, 2 * xx + 1, H2, W2, pad, vt, v, g11);
+    Vec16<BF> a;
     a.raw = x[e];
     float f[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      f[i] = ((g00.get(i) + g01.get(i)) + (g10.get(i) + g11.get(i))) * elu_slope(a.get(i) + bv[i]);
+      f[i] = ((g00[i] + g01[i]) + (g10[i] + g11[i])) * elu_slope(a.get(i) + bv[i]);
       acc[i] += f[i];
     }
     Vec16<BF> o;
@@ -808,24 +856,39 @@ __global__ void __launch_bounds__(kGlueThreads) elu_up2_cat_bwd_x_kernel(const u
   if (partial) block_channel_sums<N>(acc, v1, partial, v1 * N);
 }
 
-// one thread per 16-byte vector of grad_skip [B, 2h, 2w, C2]: the channel slice of grad_out
-__global__ void __launch_bounds__(256) cat_bwd_skip_kernel(const uint4* __restrict__ gout, uint4* __restrict__ gskip, int v1,
-                                                           int v2, size_t nvec) {
+// one thread per 16-byte vector of grad_skip [B, 2h, 2w, C2]: the channel slice of grad_out (ring gradients folded in if pad)
+template <bool BF>
+__global__ void __launch_bounds__(256) cat_bwd_skip_kernel(const uint4* __restrict__ gout, uint4* __restrict__ gskip, int H2, int W2,
+                                                           int v1, int v2, int pad, size_t nvec) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nvec) return;
   const size_t pix = e / v2;
   const int v = (int)(e - pix * v2);
-  gskip[e] = gout[pix * (v1 + v2) + v1 + v];
+  if (!pad) {
+    gskip[e] = gout[pix * (v1 + v2) + v1 + v];
+    return;
+  }
+  const int X = (int)(pix % W2);
+  const size_t r = pix / W2;
+  const int Y = (int)(r % H2);
+  const size_t b = r / H2;
+  float f[Vec16<BF>::N];
+  load_folded<BF>(gout, b, Y, X, H2, W2, pad, v1 + v2, v1 + v, f);
+  Vec16<BF> o;
+  o.set_all(f);
+  gskip[e] = o.raw;
 }
 
-// y = ELU(x + bias[c]) (ConvBlock: the convolution's bias and its ELU, model/layers.py:106-117), in place if y == x
+// y = ELU(x + bias[c]) (ConvBlock: the convolution's bias and its ELU, model/layers.py:106-117); y gets the reflected ring if
+// pad (then y is [B, H+2, W+2, C]); without pad y may alias x
 template <bool BF>
 __global__ void __launch_bounds__(256) bias_elu_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ bias,
-                                                           uint4* __restrict__ y, int vpp, size_t nvec) {
+                                                           uint4* __restrict__ y, int H, int W, int vpp, int pad, size_t nvec) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nvec) return;
   constexpr int N = Vec16<BF>::N;
-  const int v = (int)(e % vpp);
+  const size_t pix = e / vpp;
+  const int v = (int)(e - pix * vpp);
   Vec16<BF> a;
   a.raw = x[e];
   float f[N];
@@ -833,27 +896,39 @@ __global__ void __launch_bounds__(256) bias_elu_fwd_kernel(const uint4* __restri
   for (int i = 0; i < N; ++i) f[i] = elu_value(a.get(i) + (bias ? bias[v * N + i] : 0.f));
   Vec16<BF> o;
   o.set_all(f);
-  y[e] = o.raw;
+  if (!pad) {
+    y[e] = o.raw;
+    return;
+  }
+  const int xx = (int)(pix % W);
+  const size_t r = pix / W;
+  store_with_ring(y, o.raw, r / H, (int)(r % H), xx, H, W, pad, vpp, v);
 }
 // grad_x = grad_y * ELU'(.) written from the OUTPUT y as ATen's in-place ELU does (y <= 0 ? y + 1 : 1: nn.ELU(inplace=True)
-// keeps only y); per-channel sums of grad_x for the bias gradient
+// keeps only y); ring gradients folded in if pad; per-channel sums of grad_x for the bias gradient
 template <bool BF>
 __global__ void __launch_bounds__(kGlueThreads) bias_elu_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ gy,
-                                                                    uint4* __restrict__ gx, float* __restrict__ partial, int vpp,
-                                                                    size_t nvec) {
+                                                                    uint4* __restrict__ gx, float* __restrict__ partial, int H, int W,
+                                                                    int vpp, int pad, size_t nvec) {
   constexpr int N = Vec16<BF>::N;
   float acc[N];
+  const int v = threadIdx.x % vpp;
 #pragma unroll
   for (int i = 0; i < N; ++i) acc[i] = 0.f;
   for (size_t e = (size_t)blockIdx.x * kGlueThreads + threadIdx.x; e < nvec; e += (size_t)gridDim.x * kGlueThreads) {
-    Vec16<BF> a, g;
-    a.raw = y[e];
-    g.raw = gy[e];
-    float f[N];
+    const size_t pix = e / vpp;
+    const int xx = (int)(pix % W);
+    const size_t r = pix / W;
+    const int yy = (int)(r % H);
+    const size_t b = r / H;
+    Vec16<BF> a;
+    a.raw = y[pvec(b, yy, xx, H, W, pad, vpp, v)];
+    float g[N], f[N];
+    load_folded<BF>(gy, b, yy, xx, H, W, pad, vpp, v, g);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const float yv = a.get(i);
-      f[i] = g.get(i) * (yv <= 0.f ? yv + 1.f : 1.f);
+      f[i] = g[i] * (yv <= 0.f ? yv + 1.f : 1.f);
       acc[i] += f[i];
     }
     Vec16<BF> o;
@@ -889,28 +964,29 @@ extern "C" int dvs_glue_workspace_bytes(int C, size_t* bytes) {
 }
 
 extern "C" int dvs_elu_up2_cat_fwd(const void* x, const void* skip, const float* bias, void* out, int dtype, int B, int C1, int C2,
-                                   int h, int w, void* stream) {
+                                   int h, int w, int pad, void* stream) {
   using namespace dvs;
   int rc = glue_check(x, dtype, B, C1, C2, h, w, skip);
   if (rc) return rc;
-  if (!out || ((uintptr_t)out & 15)) return DVS_EINVAL;
+  if (!out || ((uintptr_t)out & 15) || pad < 0 || pad > 1 || (pad && (2 * h < 3 || 2 * w < 3))) return DVS_EINVAL;
   const bool bf = dtype == DVS_DTYPE_BF16;
   const int per = bf ? 8 : 4, v1 = C1 / per, v2 = C2 / per;
   const size_t nvec = (size_t)B * 4 * h * w * (v1 + v2);
   const unsigned int nblk = (unsigned int)((nvec + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bf) elu_up2_cat_fwd_kernel<true><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, bias, (uint4*)out, h, w, v1, v2, nvec);
-  else elu_up2_cat_fwd_kernel<false><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, bias, (uint4*)out, h, w, v1, v2, nvec);
+  if (bf) elu_up2_cat_fwd_kernel<true><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, bias, (uint4*)out, h, w, v1, v2, pad, nvec);
+  else elu_up2_cat_fwd_kernel<false><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, bias, (uint4*)out, h, w, v1, v2, pad, nvec);
   DVS_CUDA_TRY(cudaGetLastError());
   return DVS_OK;
 }
 
 extern "C" int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, const float* bias, void* grad_x, void* grad_skip,
-                                   float* grad_bias, int dtype, int B, int C1, int C2, int h, int w, void* workspace, void* stream) {
+                                   float* grad_bias, int dtype, int B, int C1, int C2, int h, int w, int pad, void* workspace,
+                                   void* stream) {
   using namespace dvs;
   int rc = glue_check(x, dtype, B, C1, C2, h, w, C2 > 0 ? grad_skip : nullptr);
   if (rc) return rc;
-  if (!grad_out || !grad_x || ((uintptr_t)grad_out & 15) || ((uintptr_t)grad_x & 15)) return DVS_EINVAL;
+  if (!grad_out || !grad_x || ((uintptr_t)grad_out & 15) || ((uintptr_t)grad_x & 15) || pad < 0 || pad > 1) return DVS_EINVAL;
   if (grad_bias && (!workspace || ((uintptr_t)workspace & 255))) return DVS_EWORKSPACE;
   const bool bf = dtype == DVS_DTYPE_BF16;
   const int per = bf ? 8 : 4, v1 = C1 / per, v2 = C2 / per;
@@ -919,8 +995,8 @@ extern "C" int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, const fl
   const int bx = glue_reduce_blocks(nx, v1);
   if (!bx) return DVS_EINVAL;
   float* partial = grad_bias ? static_cast<float*>(workspace) : nullptr;
-  if (bf) elu_up2_cat_bwd_x_kernel<true><<<bx, kGlueThreads, 0, st>>>((const uint4*)x, (const uint4*)grad_out, bias, (uint4*)grad_x, partial, h, w, v1, v2, nx);
-  else elu_up2_cat_bwd_x_kernel<false><<<bx, kGlueThreads, 0, st>>>((const uint4*)x, (const uint4*)grad_out, bias, (uint4*)grad_x, partial, h, w, v1, v2, nx);
+  if (bf) elu_up2_cat_bwd_x_kernel<true><<<bx, kGlueThreads, 0, st>>>((const uint4*)x, (const uint4*)grad_out, bias, (uint4*)grad_x, partial, h, w, v1, v2, pad, nx);
+  else elu_up2_cat_bwd_x_kernel<false><<<bx, kGlueThreads, 0, st>>>((const uint4*)x, (const uint4*)grad_out, bias, (uint4*)grad_x, partial, h, w, v1, v2, pad, nx);
   DVS_CUDA_TRY(cudaGetLastError());
   if (grad_bias) {
     channel_reduce_kernel<<<(C1 + 7) / 8, 256, 0, st>>>(partial, bx, C1, grad_bias);
@@ -928,34 +1004,37 @@ extern "C" int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, const fl
   }
   if (v2 > 0) {
     const size_t ns = (size_t)B * 4 * h * w * v2;
-    cat_bwd_skip_kernel<<<(unsigned int)((ns + 255) / 256), 256, 0, st>>>((const uint4*)grad_out, (uint4*)grad_skip, v1, v2, ns);
+    const unsigned int nb = (unsigned int)((ns + 255) / 256);
+    if (bf) cat_bwd_skip_kernel<true><<<nb, 256, 0, st>>>((const uint4*)grad_out, (uint4*)grad_skip, 2 * h, 2 * w, v1, v2, pad, ns);
+    else cat_bwd_skip_kernel<false><<<nb, 256, 0, st>>>((const uint4*)grad_out, (uint4*)grad_skip, 2 * h, 2 * w, v1, v2, pad, ns);
     DVS_CUDA_TRY(cudaGetLastError());
   }
   return DVS_OK;
 }
 
-extern "C" int dvs_bias_elu_fwd(const void* x, const float* bias, void* y, int dtype, int B, int C, int H, int W, void* stream) {
+extern "C" int dvs_bias_elu_fwd(const void* x, const float* bias, void* y, int dtype, int B, int C, int H, int W, int pad,
+                                void* stream) {
   using namespace dvs;
   int rc = glue_check(x, dtype, B, C, 0, H, W, nullptr);
   if (rc) return rc;
-  if (!y || ((uintptr_t)y & 15)) return DVS_EINVAL;
+  if (!y || ((uintptr_t)y & 15) || pad < 0 || pad > 1 || (pad && (H < 3 || W < 3 || y == x))) return DVS_EINVAL;
   const bool bf = dtype == DVS_DTYPE_BF16;
   const int vpp = C / (bf ? 8 : 4);
   const size_t nvec = (size_t)B * H * W * vpp;
   const unsigned int nblk = (unsigned int)((nvec + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bf) bias_elu_fwd_kernel<true><<<nblk, 256, 0, st>>>((const uint4*)x, bias, (uint4*)y, vpp, nvec);
-  else bias_elu_fwd_kernel<false><<<nblk, 256, 0, st>>>((const uint4*)x, bias, (uint4*)y, vpp, nvec);
+  if (bf) bias_elu_fwd_kernel<true><<<nblk, 256, 0, st>>>((const uint4*)x, bias, (uint4*)y, H, W, vpp, pad, nvec);
+  else bias_elu_fwd_kernel<false><<<nblk, 256, 0, st>>>((const uint4*)x, bias, (uint4*)y, H, W, vpp, pad, nvec);
   DVS_CUDA_TRY(cudaGetLastError());
   return DVS_OK;
 }
 
 extern "C" int dvs_bias_elu_bwd(const void* y, const void* grad_y, void* grad_x, float* grad_bias, int dtype, int B, int C, int H,
-                                int W, void* workspace, void* stream) {
+                                int W, int pad, void* workspace, void* stream) {
   using namespace dvs;
   int rc = glue_check(y, dtype, B, C, 0, H, W, nullptr);
   if (rc) return rc;
-  if (!grad_y || !grad_x || ((uintptr_t)grad_y & 15) || ((uintptr_t)grad_x & 15)) return DVS_EINVAL;
+  if (!grad_y || !grad_x || ((uintptr_t)grad_y & 15) || ((uintptr_t)grad_x & 15) || pad < 0 || pad > 1) return DVS_EINVAL;
   if (grad_bias && (!workspace || ((uintptr_t)workspace & 255))) return DVS_EWORKSPACE;
   const bool bf = dtype == DVS_DTYPE_BF16;
   const int vpp = C / (bf ? 8 : 4);
@@ -964,8 +1043,8 @@ extern "C" int dvs_bias_elu_bwd(const void* y, const void* grad_y, void* grad_x,
   if (!nblk) return DVS_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = grad_bias ? static_cast<float*>(workspace) : nullptr;
-  if (bf) bias_elu_bwd_kernel<true><<<nblk, kGlueThreads, 0, st>>>((const uint4*)y, (const uint4*)grad_y, (uint4*)grad_x, partial, vpp, nvec);
-  else bias_elu_bwd_kernel<false><<<nblk, kGlueThreads, 0, st>>>((const uint4*)y, (const uint4*)grad_y, (uint4*)grad_x, partial, vpp, nvec);
+  if (bf) bias_elu_bwd_kernel<true><<<nblk, kGlueThreads, 0, st>>>((const uint4*)y, (const uint4*)grad_y, (uint4*)grad_x, partial, H, W, vpp, pad, nvec);
+  else bias_elu_bwd_kernel<false><<<nblk, kGlueThreads, 0, st>>>((const uint4*)y, (const uint4*)grad_y, (uint4*)grad_x, partial, H, W, vpp, pad, nvec);
   DVS_CUDA_TRY(cudaGetLastError());
   if (grad_bias) {
     channel_reduce_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, C, grad_bias);

@@ -84,14 +84,14 @@ _SIGNATURES = {
     "dvs_pose_matrix_fwd": [_vp, _vp, _vp, C.c_int, C.c_int, _vp],
     "dvs_pose_matrix_bwd": [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp],
     "dvs_u8_to_f32": [_vp, _vp, C.c_int64, _vp],
-    "dvs_disp_head_fwd": [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
-    "dvs_elu_up2_cat_fwd": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
+    "dvs_disp_head_fwd": [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
+    "dvs_elu_up2_cat_fwd": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
     "dvs_glue_workspace_bytes": [C.c_int, C.POINTER(C.c_size_t)],
-    "dvs_elu_up2_cat_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp],
-    "dvs_bias_elu_fwd": [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
-    "dvs_bias_elu_bwd": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp],
+    "dvs_elu_up2_cat_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp],
+    "dvs_bias_elu_fwd": [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp],
+    "dvs_bias_elu_bwd": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp],
     "dvs_disp_head_bwd_workspace_bytes": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)],
-    "dvs_disp_head_bwd": [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp],
+    "dvs_disp_head_bwd": [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp],
     "dvs_silog_workspace_bytes": [C.c_int64, C.POINTER(C.c_size_t)],
     "dvs_silog_fwd": [_vp, _vp, _vp, C.c_int64, C.c_float, _vp, _vp, _vp],
     "dvs_silog_bwd": [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_float, _vp, _vp],

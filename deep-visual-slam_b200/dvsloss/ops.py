@@ -356,24 +356,27 @@ class _DispHead(torch.autograd.Function):
     """ReflectionPad2d(1) + Conv2d(C, 1, 3) + Sigmoid in one kernel (model/depthnet.py:57-58,87-88; model/layers.py:120-136)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, out_dtype):
+    def forward(ctx, x, weight, bias, out_dtype, padded):
         from ._lib import DTYPE_BF16, DTYPE_F32
         if not x.is_cuda:
             raise DvsError("disp_head runs on CUDA tensors only (no CPU fallback by design)")
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
-        B, Cc, H, W = x.shape
+        pad = 1 if padded else 0
+        B, Cc = x.shape[:2]
+        H, W = x.shape[2] - 2 * pad, x.shape[3] - 2 * pad
         xc = x.contiguous(memory_format=torch.channels_last)            # no copy when the decoder already runs channels-last
         w = weight.detach().float().contiguous()
         b = bias.detach().float().contiguous() if bias is not None else None
         disp = torch.empty(B, 1, H, W, dtype=out_dtype, device=x.device)
         code = lambda dt: DTYPE_BF16 if dt == torch.bfloat16 else DTYPE_F32
         with torch.cuda.device(x.device):
-            check(lib().dvs_disp_head_fwd(xc.data_ptr(), code(xc.dtype), w.data_ptr(), ptr(b), disp.data_ptr(), code(out_dtype),
+            check(lib().dvs_disp_head_fwd(xc.data_ptr(), code(xc.dtype), pad, w.data_ptr(), ptr(b), disp.data_ptr(), code(out_dtype),
                                           B, Cc, H, W, stream_ptr(x.device)), "dvs_disp_head_fwd")
         ctx.save_for_backward(xc, w, disp)
         ctx.has_bias = bias is not None
         ctx.wdtype = weight.dtype
+        ctx.pad = pad
         return disp
 
     @staticmethod
@@ -381,9 +384,12 @@ class _DispHead(torch.autograd.Function):
         import ctypes as C
         from ._lib import DTYPE_BF16, DTYPE_F32
         xc, w, disp = ctx.saved_tensors
-        B, Cc, H, W = xc.shape
+        pad = ctx.pad
+        B, Cc = xc.shape[:2]
+        H, W = xc.shape[2] - 2 * pad, xc.shape[3] - 2 * pad
         g = g.to(disp.dtype).contiguous()
-        gx = torch.empty_like(xc, memory_format=torch.channels_last)
+        # with a padded activation the gradient has the padded layout too; the kernel leaves the ring alone: zero it here
+        gx = (torch.zeros_like if pad else torch.empty_like)(xc, memory_format=torch.channels_last)
         gw = torch.empty_like(w)
         gb = torch.empty(1, dtype=torch.float32, device=xc.device) if ctx.has_bias else None
         n = C.c_size_t(0)
@@ -392,21 +398,24 @@ class _DispHead(torch.autograd.Function):
         ws = torch.empty(n.value + 256, dtype=torch.uint8, device=xc.device)
         code = lambda dt: DTYPE_BF16 if dt == torch.bfloat16 else DTYPE_F32
         with torch.cuda.device(xc.device):
-            check(L.dvs_disp_head_bwd(g.data_ptr(), disp.data_ptr(), code(disp.dtype), xc.data_ptr(), code(xc.dtype), w.data_ptr(),
+            check(L.dvs_disp_head_bwd(g.data_ptr(), disp.data_ptr(), code(disp.dtype), xc.data_ptr(), code(xc.dtype), pad, w.data_ptr(),
                                       gx.data_ptr(), gw.data_ptr(), ptr(gb), B, Cc, H, W, (ws.data_ptr() + 255) // 256 * 256,
                                       stream_ptr(xc.device)), "dvs_disp_head_bwd")
-        return gx, gw.to(ctx.wdtype), (gb.to(ctx.wdtype) if gb is not None else None), None
+        return gx, gw.to(ctx.wdtype), (gb.to(ctx.wdtype) if gb is not None else None), None, None
 
 
-def disp_head(x: torch.Tensor, weight: torch.Tensor, bias, out_dtype=None) -> torch.Tensor:
+def disp_head(x: torch.Tensor, weight: torch.Tensor, bias, out_dtype=None, padded: bool = False) -> torch.Tensor:
     """sigmoid(conv3x3(reflection_pad(x))) with one output channel: x [B,C,H,W] (fp32 / bf16; channels-last memory is read in
     place), weight [1,C,3,3], bias [1] or None -> disparity [B,1,H,W] in ``out_dtype`` (default: x's dtype, which is what the
-    stock modules produce under autocast)."""
+    stock modules produce under autocast).  ``padded``: x is [B,C,H+2,W+2] and already carries its reflected ring
+    (``bias_elu(..., pad=True)``); the result is the same."""
     if weight.dim() != 4 or weight.shape[0] != 1 or tuple(weight.shape[2:]) != (3, 3) or weight.shape[1] != x.shape[1]:
         raise DvsError(f"disp_head needs a [1,C,3,3] weight for a [B,C,H,W] input, got {tuple(weight.shape)} / {tuple(x.shape)}")
+    if padded and x.shape[1] not in (8, 16, 32, 64, 128):
+        raise DvsError("disp_head(padded=True) needs 8, 16, 32, 64 or 128 channels")
     if out_dtype is None:
         out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
-    return _DispHead.apply(x, weight, bias, out_dtype)
+    return _DispHead.apply(x, weight, bias, out_dtype, padded)
 
 
 def disp_head_supported(x: torch.Tensor) -> bool:
@@ -429,20 +438,21 @@ class _EluUp2Cat(torch.autograd.Function):
     """cat([nearest_up2(ELU(x + bias)), skip], 1) in one pass, channels-last (model/depthnet.py:77-84, model/layers.py:106-117,196-199)."""
 
     @staticmethod
-    def forward(ctx, x, skip, bias):
+    def forward(ctx, x, skip, bias, pad):
         from ._lib import DTYPE_BF16, DTYPE_F32
         B, C1, h, w = x.shape
         C2 = 0 if skip is None else skip.shape[1]
+        pad = 1 if pad else 0
         xc = x.contiguous(memory_format=torch.channels_last)
         sc = None if skip is None else skip.contiguous(memory_format=torch.channels_last)
         bc = None if bias is None else bias.detach().float().contiguous()
-        out = torch.empty(B, C1 + C2, 2 * h, 2 * w, dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        out = torch.empty(B, C1 + C2, 2 * h + 2 * pad, 2 * w + 2 * pad, dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         code = DTYPE_BF16 if x.dtype == torch.bfloat16 else DTYPE_F32
         with torch.cuda.device(x.device):
             check(lib().dvs_elu_up2_cat_fwd(xc.data_ptr(), 0 if sc is None else sc.data_ptr(), ptr(bc), out.data_ptr(), code, B, C1, C2,
-                                            h, w, stream_ptr(x.device)), "dvs_elu_up2_cat_fwd")
+                                            h, w, pad, stream_ptr(x.device)), "dvs_elu_up2_cat_fwd")
         ctx.save_for_backward(xc, bc)
-        ctx.C2, ctx.code = C2, code
+        ctx.C2, ctx.code, ctx.pad = C2, code, pad
         ctx.bdtype = None if bias is None else bias.dtype
         return out
 
@@ -459,9 +469,9 @@ class _EluUp2Cat(torch.autograd.Function):
         ws = _glue_ws(C1, xc.device) if want_b else None
         with torch.cuda.device(xc.device):
             check(lib().dvs_elu_up2_cat_bwd(xc.data_ptr(), g.data_ptr(), ptr(bc), gx.data_ptr(), 0 if gs is None else gs.data_ptr(),
-                                            ptr(gb), ctx.code, B, C1, C2, h, w, 0 if ws is None else _al256(ws),
+                                            ptr(gb), ctx.code, B, C1, C2, h, w, ctx.pad, 0 if ws is None else _al256(ws),
                                             stream_ptr(xc.device)), "dvs_elu_up2_cat_bwd")
-        return gx, gs, (gb.to(ctx.bdtype) if gb is not None else None)
+        return gx, gs, (gb.to(ctx.bdtype) if gb is not None else None), None
 
 
 def _glue_channels_ok(x: torch.Tensor) -> bool:
@@ -480,60 +490,69 @@ def elu_up2_cat_supported(x: torch.Tensor, skip=None) -> bool:
             and tuple(skip.shape[2:]) == (2 * x.shape[2], 2 * x.shape[3]))
 
 
-def elu_up2_cat(x: torch.Tensor, skip=None, bias=None) -> torch.Tensor:
+def elu_up2_cat(x: torch.Tensor, skip=None, bias=None, pad: bool = False) -> torch.Tensor:
     """``torch.cat([F.interpolate(F.elu(x + bias), scale_factor=2, mode="nearest"), skip], 1)`` (``skip``, ``bias`` optional) as
     one kernel each way; x [B,C1,h,w] is the decoder convolution's output BEFORE its bias and ELU (run the convolution without
     bias and hand the bias here: one pass over the activation less each way), skip [B,C2,2h,2w] the encoder feature.
-    Channels-last memory is read in place; the result is channels-last."""
+    Channels-last memory is read in place; the result is channels-last.  ``pad``: the result is ``ReflectionPad2d(1)`` of the
+    above ([B,C1+C2,2h+2,2w+2]) -- the next Conv3x3 then runs as a plain un-padded convolution on it, and this op's backward
+    folds the ring's gradients back."""
     if not elu_up2_cat_supported(x, skip):
         raise DvsError("elu_up2_cat needs CUDA fp32 / bf16 tensors of one dtype, channels / 4 (fp32) or / 8 (bf16) a power of two, "
                        "skip of twice the spatial size")
-    return _EluUp2Cat.apply(x, skip, bias)
+    return _EluUp2Cat.apply(x, skip, bias, pad)
 
 
 class _BiasElu(torch.autograd.Function):
     """ELU(x + bias) in one pass (ConvBlock = Conv3x3 + ELU, model/layers.py:106-117; the Conv2d bias of :131 folded in)."""
 
     @staticmethod
-    def forward(ctx, x, bias):
+    def forward(ctx, x, bias, pad):
         from ._lib import DTYPE_BF16, DTYPE_F32
         B, Cc, H, W = x.shape
+        pad = 1 if pad else 0
         xc = x.contiguous(memory_format=torch.channels_last)
         bc = None if bias is None else bias.detach().float().contiguous()
-        y = torch.empty_like(xc, memory_format=torch.channels_last)
+        y = torch.empty(B, Cc, H + 2 * pad, W + 2 * pad, dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         code = DTYPE_BF16 if x.dtype == torch.bfloat16 else DTYPE_F32
         with torch.cuda.device(x.device):
-            check(lib().dvs_bias_elu_fwd(xc.data_ptr(), ptr(bc), y.data_ptr(), code, B, Cc, H, W, stream_ptr(x.device)), "dvs_bias_elu_fwd")
+            check(lib().dvs_bias_elu_fwd(xc.data_ptr(), ptr(bc), y.data_ptr(), code, B, Cc, H, W, pad, stream_ptr(x.device)),
+                  "dvs_bias_elu_fwd")
         ctx.save_for_backward(y)
-        ctx.code = code
+        ctx.code, ctx.pad = code, pad
         ctx.bdtype = None if bias is None else bias.dtype
         return y
 
     @staticmethod
     def backward(ctx, g):
         (y,) = ctx.saved_tensors
-        B, Cc, H, W = y.shape
+        pad = ctx.pad
+        B, Cc = y.shape[:2]
+        H, W = y.shape[2] - 2 * pad, y.shape[3] - 2 * pad
         g = g.to(y.dtype).contiguous(memory_format=torch.channels_last)
-        gx = torch.empty_like(y, memory_format=torch.channels_last)
+        gx = torch.empty(B, Cc, H, W, dtype=y.dtype, device=y.device, memory_format=torch.channels_last)
         want_b = ctx.bdtype is not None and ctx.needs_input_grad[1]
         gb = torch.empty(Cc, dtype=torch.float32, device=y.device) if want_b else None
         ws = _glue_ws(Cc, y.device) if want_b else None
         with torch.cuda.device(y.device):
-            check(lib().dvs_bias_elu_bwd(y.data_ptr(), g.data_ptr(), gx.data_ptr(), ptr(gb), ctx.code, B, Cc, H, W,
+            check(lib().dvs_bias_elu_bwd(y.data_ptr(), g.data_ptr(), gx.data_ptr(), ptr(gb), ctx.code, B, Cc, H, W, pad,
                                          0 if ws is None else _al256(ws), stream_ptr(y.device)), "dvs_bias_elu_bwd")
-        return gx, (gb.to(ctx.bdtype) if gb is not None else None)
+        return gx, (gb.to(ctx.bdtype) if gb is not None else None), None
 
 
 def bias_elu_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16) and _glue_channels_ok(x)
 
 
-def bias_elu(x: torch.Tensor, bias=None) -> torch.Tensor:
+def bias_elu(x: torch.Tensor, bias=None, pad: bool = False) -> torch.Tensor:
     """``F.elu(x + bias.view(1, -1, 1, 1))`` as one kernel each way (the backward also yields the bias gradient); x is the
-    convolution's output without its bias, channels-last memory is read in place."""
+    convolution's output without its bias, channels-last memory is read in place.  ``pad``: the result is
+    ``ReflectionPad2d(1)`` of the above ([B,C,H+2,W+2]), see ``elu_up2_cat``."""
     if not bias_elu_supported(x):
         raise DvsError("bias_elu needs a CUDA fp32 / bf16 [B,C,H,W] tensor with C / 4 (fp32) or C / 8 (bf16) a power of two")
-    return _BiasElu.apply(x, bias)
+    if pad and (x.shape[2] < 3 or x.shape[3] < 3):
+        raise DvsError("a reflected ring needs at least 3 x 3 pixels")
+    return _BiasElu.apply(x, bias, pad)
 
 
 # ---------------------------------------------------------------------------------------------------- network inputs

@@ -163,10 +163,14 @@ class Conv3x3(nn.Module):
         self.pad = nn.ReflectionPad2d(1) if use_refl else nn.ZeroPad2d(1)
         self.conv = nn.Conv2d(int(in_channels), int(out_channels), 3)
 
-    def forward(self, x, with_bias: bool = True):
+    def forward(self, x, with_bias: bool = True, padded: bool = False):
         """``with_bias=False``: the convolution alone -- the caller folds ``self.conv.bias`` into the kernel that consumes the
-        result (``dvsloss.ops.bias_elu`` / ``elu_up2_cat``), saving the separate bias pass cuDNN's path runs."""
+        result (``dvsloss.ops.bias_elu`` / ``elu_up2_cat``), saving the separate bias pass cuDNN's path runs.
+        ``padded=True``: ``x`` already carries the reflected ring (it came from one of those kernels with ``pad=True``): the
+        reference's pad-then-convolve (model/layers.py:131-136) is then the plain un-padded stock convolution."""
         bias = self.conv.bias if with_bias else None
+        if padded:
+            return F.conv2d(x, self.conv.weight, bias)
         if self.use_refl and self.fast_reflect and x.shape[2] >= 3 and x.shape[3] >= 3:
             return conv3x3_reflect(x, self.conv.weight, bias)
         return F.conv2d(self.pad(x), self.conv.weight, bias)
@@ -190,6 +194,10 @@ class ConvBlock(nn.Module):
                 return _ops.bias_elu(pre, self.conv.conv.bias)
             return self.nonlin(pre + self.conv.conv.bias.to(pre.dtype).view(1, -1, 1, 1))
         return self.nonlin(self.conv(x))
+
+    def pre_activation(self, x, padded: bool = False):
+        """The convolution without bias and ELU (for the fused glue kernels); ``padded``: x carries its reflected ring."""
+        return self.conv(x, with_bias=False, padded=padded)
 
 
 def compute_depth_errors(gt: torch.Tensor, pred: torch.Tensor):

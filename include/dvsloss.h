@@ -244,13 +244,16 @@ int dvs_u8_to_f32(const uint8_t* src, float* dst, int64_t n, void* stream);
 /* Disparity head of DepthNet, fused: ReflectionPad2d(1) + Conv2d(C, 1, 3) + Sigmoid (the ("dispconv", s) blocks,
  * model/depthnet.py:57-58,87-88; Conv3x3 = model/layers.py:120-136) in one pass, writing disp_s in the dtype the loss
  * kernel reads.  x: the decoder activation, CHANNELS-LAST [B,H,W,C] (C a multiple of 8, <= 128; 16-byte aligned), fp32 or
- * bf16; weight: the Conv2d weight [1,C,3,3] fp32 as stored; bias [1] fp32 (may be NULL); disp [B,1,H,W] fp32 or bf16. */
-int dvs_disp_head_fwd(const void* x, int x_dtype, const float* weight, const float* bias, void* disp, int disp_dtype,
+ * bf16; weight: the Conv2d weight [1,C,3,3] fp32 as stored; bias [1] fp32 (may be NULL); disp [B,1,H,W] fp32 or bf16.
+ * x_pad = 1: x carries the reflected one-pixel ring written by dvs_bias_elu_fwd(pad = 1) ([B,H+2,W+2,C]; only its interior is
+ * read); needs C in {8, 16, 32, 64, 128}. */
+int dvs_disp_head_fwd(const void* x, int x_dtype, int x_pad, const float* weight, const float* bias, void* disp, int disp_dtype,
                       int B, int C, int H, int W, void* stream);
 /* Backward: grad_disp and disp (the saved forward output) [B,1,H,W] in disp_dtype; grad_x channels-last in x_dtype;
- * grad_weight [1,C,3,3] and grad_bias [1] (may be NULL) fp32, fixed-order reductions (bit-reproducible). */
+ * grad_weight [1,C,3,3] and grad_bias [1] (may be NULL) fp32, fixed-order reductions (bit-reproducible).  With x_pad = 1 grad_x
+ * has x's padded layout; its ring is NOT written (the caller zeroes it). */
 int dvs_disp_head_bwd_workspace_bytes(int B, int C, int H, int W, size_t* bytes);
-int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int disp_dtype, const void* x, int x_dtype,
+int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int disp_dtype, const void* x, int x_dtype, int x_pad,
                       const float* weight, void* grad_x, float* grad_weight, float* grad_bias, int B, int C, int H, int W,
                       void* workspace, void* stream);
 
@@ -258,22 +261,26 @@ int dvs_disp_head_bwd(const void* grad_disp, const void* disp, int disp_dtype, c
  * model/layers.py:196-199; torch.cat with the encoder skip): out = cat([nearest_up2(ELU(x + bias)), skip], channels), one pass.
  * CHANNELS-LAST tensors of one dtype (fp32 or bf16), 16-byte aligned: x [B,h,w,C1] (the convolution output BEFORE bias and
  * ELU; bias fp32 [C1] or NULL: the Conv2d bias, model/layers.py:131, folded in so that the convolution runs without its
- * separate bias pass), skip [B,2h,2w,C2] (NULL iff C2 == 0), out [B,2h,2w,C1+C2]; C1, C2 multiples of 8 (bf16) / 4 (fp32). */
+ * separate bias pass), skip [B,2h,2w,C2] (NULL iff C2 == 0), out [B,2h,2w,C1+C2]; C1, C2 multiples of 8 (bf16) / 4 (fp32).
+ * pad = 1: out is [B,2h+2,2w+2,C1+C2] with the reflected one-pixel ring of nn.ReflectionPad2d(1) (model/layers.py:126) filled
+ * in, so that the next Conv3x3 runs as an un-padded stock convolution on it. */
 int dvs_elu_up2_cat_fwd(const void* x, const void* skip, const float* bias, void* out, int dtype, int B, int C1, int C2,
-                        int h, int w, void* stream);
+                        int h, int w, int pad, void* stream);
 /* Backward: grad_out [B,2h,2w,C1+C2] -> grad_x [B,h,w,C1] = ELU'(x + bias) * (2x2 sum of grad_out, fp32, fixed order),
  * grad_skip [B,2h,2w,C2] (NULL iff C2 == 0) and, if grad_bias != NULL, grad_bias [C1] fp32 = the per-channel sums of grad_x
  * (two-stage fixed-order reduction; needs `workspace` of dvs_glue_workspace_bytes(C1) bytes, 256-byte aligned, and C1 / 8
- * (bf16) or C1 / 4 (fp32) a power of two <= 256). */
+ * (bf16) or C1 / 4 (fp32) a power of two <= 256).  pad = 1: grad_out has the padded layout and the gradients of the ring
+ * positions are folded onto the pixels they mirror. */
 int dvs_glue_workspace_bytes(int C, size_t* bytes);
 int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, const float* bias, void* grad_x, void* grad_skip, float* grad_bias,
-                        int dtype, int B, int C1, int C2, int h, int w, void* workspace, void* stream);
+                        int dtype, int B, int C1, int C2, int h, int w, int pad, void* workspace, void* stream);
 /* ConvBlock's bias + ELU (model/layers.py:106-117 with the Conv2d bias of :131) in one pass: y = ELU(x + bias[c]),
  * channels-last [B,H,W,C], y may alias x.  Backward from the OUTPUT, as nn.ELU(inplace=True) does: grad_x = grad_y *
- * (y <= 0 ? y + 1 : 1); grad_bias [C] fp32 (optional) as above. */
-int dvs_bias_elu_fwd(const void* x, const float* bias, void* y, int dtype, int B, int C, int H, int W, void* stream);
+ * (y <= 0 ? y + 1 : 1); grad_bias [C] fp32 (optional) as above.  pad = 1: y and grad_y are [B,H+2,W+2,C] with the reflected ring
+ * (written / folded as for dvs_elu_up2_cat_*); x and grad_x stay [B,H,W,C]. */
+int dvs_bias_elu_fwd(const void* x, const float* bias, void* y, int dtype, int B, int C, int H, int W, int pad, void* stream);
 int dvs_bias_elu_bwd(const void* y, const void* grad_y, void* grad_x, float* grad_bias, int dtype, int B, int C, int H, int W,
-                     void* workspace, void* stream);
+                     int pad, void* workspace, void* stream);
 
 /* Supervised-depth path (depth/depth_learner.py).  SILog loss (:75-95): over the n elements with valid[e] != 0,
  * d = log(max(pred, 1e-6)) - log(target), loss = sqrt(mean(d^2) - variance_focus * mean(d)^2).  stats [4] receives

@@ -1,4 +1,6 @@
-"""What do the four border-strip convolutions of the decoder Conv3x3 cost in a training step?  Times the step as shipped and\nwith a zero-padded convolution alone (timing only: wrong border values).  (GPU box)"""
+"""What does the reflection padding of the decoder's Conv3x3 cost in a training step?  Times the step with ring-carrying
+activations (DepthNet.padded_mask variants, PAD_MASKS=0x1FF,0x1EE,...), with border strips everywhere, and with a zero-padded
+convolution alone (timing only: wrong border values).  (GPU box)"""
 import copy, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "deep-visual-slam_b200")):
@@ -24,6 +26,12 @@ def run(tag):
     e1.record(); torch.cuda.synchronize()
     print(tag, e0.elapsed_time(e1) / 10, "ms/step", flush=True)
     del tr; torch.cuda.empty_cache()
-run("border strips (shipped)")
+from model.depthnet import DepthNet
+for mask in [int(v, 0) for v in os.environ.get("PAD_MASKS", "0x1EE").split(",")]:
+    DepthNet.padded_mask = mask
+    run(f"padded_mask {mask:#05x}")
+DepthNet.padded_mask = 0x1EE
+DepthNet.padded_activations = False
+run("border strips everywhere")
 ML.conv3x3_reflect = lambda x, w, b: F.conv2d(x, w, b, padding=1)      # timing only: zero padding, wrong border values
 run("zero-padded convolution only")

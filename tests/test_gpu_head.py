@@ -195,3 +195,59 @@ def test_depthnet_fused_glue_trains_like_the_stock_sequence():
     for n, gr in outs[False][1].items():
         scale = float(gr.abs().max()) + 1e-12
         assert float((outs[True][1][n] - gr).abs().max()) <= 1e-3 * scale, n
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,C1,C2,h,w", [(2, 16, 0, 6, 9), (1, 32, 64, 2, 2), (2, 64, 64, 5, 3), (1, 8, 16, 3, 7)])
+def test_glue_kernels_write_and_fold_the_reflected_ring(B, C1, C2, h, w, dtype):
+    """pad=True: the outputs of elu_up2_cat / bias_elu ARE ReflectionPad2d(1)(stock result), and their backward folds the ring's
+    gradients onto the mirrored pixels -- what lets every later decoder convolution run un-padded (model/layers.py:126-136)."""
+    from dvsloss.ops import bias_elu, elu_up2_cat
+    if dtype == torch.float32 and (C1 % 4 or (C1 // 4) & (C1 // 4 - 1)):
+        pytest.skip("channel count not supported in fp32")
+    torch.manual_seed(C1 + h + w)
+    dev = torch.device("cuda:0")
+    mk = lambda *s: torch.randn(*s, device=dev).to(dtype).contiguous(memory_format=torch.channels_last)
+    x = mk(B, C1, h, w).requires_grad_(True)
+    skip = mk(B, C2, 2 * h, 2 * w).requires_grad_(True) if C2 else None
+    bias = torch.randn(C1, device=dev).requires_grad_(True)
+    leaves = [t for t in (x, skip, bias) if t is not None]
+    got = elu_up2_cat(x, skip, bias, pad=True)
+    dense = elu_up2_cat(x, skip, bias)
+    ref = F.pad(dense, (1, 1, 1, 1), mode="reflect")
+    assert got.shape == ref.shape and torch.equal(got, ref)                       # the ring is a copy of computed values
+    g = torch.randn_like(ref)
+    gg = torch.autograd.grad(got, leaves, g)
+    gr = torch.autograd.grad(ref, leaves, g)
+    tol = 2e-6 if dtype == torch.float32 else 2 ** -6
+    for a, r in zip(gg, gr):
+        assert float((a.double() - r.double()).abs().max()) <= tol * (float(r.double().abs().max()) + 1e-30)
+    # bias + ELU with the ring
+    C = C1
+    z = mk(B, C, 2 * h + 1, 2 * w + 1).requires_grad_(True)
+    got2 = bias_elu(z, bias, pad=True)
+    ref2 = F.pad(bias_elu(z, bias), (1, 1, 1, 1), mode="reflect")
+    assert torch.equal(got2, ref2)
+    g2 = torch.randn_like(ref2)
+    for a, r in zip(torch.autograd.grad(got2, (z, bias), g2), torch.autograd.grad(ref2, (z, bias), g2)):
+        assert float((a.double() - r.double()).abs().max()) <= tol * (float(r.double().abs().max()) + 1e-30)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_disp_head_reads_a_ring_carrying_activation(dtype):
+    from dvsloss.ops import bias_elu, disp_head
+    torch.manual_seed(5)
+    dev = torch.device("cuda:0")
+    B, C, H, W = 2, 32, 11, 37
+    pre = torch.randn(B, C, H, W, device=dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = (torch.randn(1, C, 3, 3, device=dev) / 30).requires_grad_(True)
+    b = torch.randn(1, device=dev).requires_grad_(True)
+    outs = []
+    for pad in (True, False):
+        y = bias_elu(pre, None, pad=pad)
+        d = disp_head(y, w, b, padded=pad)
+        g = torch.autograd.grad(d, (pre, w, b), torch.ones_like(d) * 0.3)
+        outs.append((d, g))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, r in zip(outs[0][1], outs[1][1]):
+        assert float((a.double() - r.double()).abs().max()) <= (1e-6 if dtype == torch.float32 else 2 ** -7) * float(r.double().abs().max())
