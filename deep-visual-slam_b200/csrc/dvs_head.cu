@@ -723,8 +723,11 @@ __device__ __forceinline__ float elu_slope(float a) { return a <= 0.f ? expf(a) 
 // that PRODUCE their inputs can write the one-pixel ring themselves (pad = 1: tensor [B, H+2, W+2, C], ring row -1 = row 1,
 // row H = row H-2, columns alike), so that the stock convolution runs un-padded on that buffer -- no padded copy and no border
 // fix-up convolutions -- and the kernels that consume the convolution's input gradient fold the ring's gradients back.
-__device__ __forceinline__ size_t pvec(size_t b, int y, int x, int H, int W, int pad, int vpp, int v) {
-  return ((b * (size_t)(H + 2 * pad) + (size_t)(y + pad)) * (size_t)(W + 2 * pad) + (size_t)(x + pad)) * vpp + v;
+// IDX: 32-bit index arithmetic when the tensors have fewer than 2^31 vectors (the 64-bit divisions of the pixel decomposition
+// cost more than the memory access they address), 64-bit otherwise
+template <class IDX>
+__device__ __forceinline__ IDX pvec(IDX b, int y, int x, int H, int W, int pad, int vpp, int v) {
+  return ((b * (IDX)(H + 2 * pad) + (IDX)(y + pad)) * (IDX)(W + 2 * pad) + (IDX)(x + pad)) * (IDX)vpp + (IDX)v;
 }
 // the rows (columns) that hold pixel row y: itself, and the ring rows that mirror it
 __device__ __forceinline__ int ring_coords(int y, int H, int pad, int* ys) {
@@ -736,15 +739,16 @@ __device__ __forceinline__ int ring_coords(int y, int H, int pad, int* ys) {
   }
   return n;
 }
-__device__ __forceinline__ void store_with_ring(uint4* out, uint4 val, size_t b, int y, int x, int H, int W, int pad, int vpp, int v) {
+template <class IDX>
+__device__ __forceinline__ void store_with_ring(uint4* out, uint4 val, IDX b, int y, int x, int H, int W, int pad, int vpp, int v) {
   int ys[3], xs[3];
   const int ny = ring_coords(y, H, pad, ys), nx = ring_coords(x, W, pad, xs);
   for (int i = 0; i < ny; ++i)
-    for (int j = 0; j < nx; ++j) out[pvec(b, ys[i], xs[j], H, W, pad, vpp, v)] = val;
+    for (int j = 0; j < nx; ++j) out[pvec<IDX>(b, ys[i], xs[j], H, W, pad, vpp, v)] = val;
 }
 // gradient reaching pixel (y, x): its own entry plus those of the ring positions that mirror it (fixed order), in fp32
-template <bool BF>
-__device__ __forceinline__ void load_folded(const uint4* g, size_t b, int y, int x, int H, int W, int pad, int vpp, int v, float* f) {
+template <bool BF, class IDX>
+__device__ __forceinline__ void load_folded(const uint4* g, IDX b, int y, int x, int H, int W, int pad, int vpp, int v, float* f) {
   constexpr int N = BF ? 8 : 4;
   int ys[3], xs[3];
   const int ny = ring_coords(y, H, pad, ys), nx = ring_coords(x, W, pad, xs);
@@ -753,7 +757,7 @@ __device__ __forceinline__ void load_folded(const uint4* g, size_t b, int y, int
   for (int i = 0; i < ny; ++i)
     for (int j = 0; j < nx; ++j) {
       Vec16<BF> q;
-      q.raw = g[pvec(b, ys[i], xs[j], H, W, pad, vpp, v)];
+      q.raw = g[pvec<IDX>(b, ys[i], xs[j], H, W, pad, vpp, v)];
 #pragma unroll
       for (int k = 0; k < N; ++k) f[k] += q.get(k);
     }
@@ -787,20 +791,20 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const float* __rest
 
 // one thread per 16-byte vector of `out` [B, 2h, 2w, C1 + C2] (+ ring if pad); bias (fp32 [C1], may be null) is added before
 // the ELU
-template <bool BF>
+template <bool BF, class IDX>
 __global__ void __launch_bounds__(256) elu_up2_cat_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip,
                                                               const float* __restrict__ bias, uint4* __restrict__ out, int h, int w,
-                                                              int v1, int v2, int pad, size_t nvec) {
-  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                              int v1, int v2, int pad, IDX nvec) {
+  const IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nvec) return;
   const int vt = v1 + v2;
-  const size_t pix = e / vt;
+  const IDX pix = e / vt;
   const int v = (int)(e - pix * vt);
   const int W2 = 2 * w, H2 = 2 * h;
   const int X = (int)(pix % W2);
-  const size_t r = pix / W2;
+  const IDX r = pix / W2;
   const int Y = (int)(r % H2);
-  const size_t b = r / H2;
+  const IDX b = r / H2;
   uint4 val;
   if (v >= v1) {
     val = skip[pix * v2 + (v - v1)];
@@ -814,33 +818,33 @@ __global__ void __launch_bounds__(256) elu_up2_cat_fwd_kernel(const uint4* __res
     o.set_all(f);
     val = o.raw;
   }
-  store_with_ring(out, val, b, Y, X, H2, W2, pad, vt, v);
+  store_with_ring<IDX>(out, val, b, Y, X, H2, W2, pad, vt, v);
 }
 
 // grad_x [B, h, w, C1]: 2x2 sum of grad_out (fixed order; ring gradients folded in if pad) times ELU'(x + bias); grid-stride,
 // per-channel sums of grad_x for the bias gradient (partial != null)
-template <bool BF>
+template <bool BF, class IDX>
 __global__ void __launch_bounds__(kGlueThreads) elu_up2_cat_bwd_x_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gout,
                                                                          const float* __restrict__ bias, uint4* __restrict__ gx,
                                                                          float* __restrict__ partial, int h, int w, int v1, int v2,
-                                                                         int pad, size_t nvec) {
+                                                                         int pad, IDX nvec) {
   constexpr int N = Vec16<BF>::N;
   const int vt = v1 + v2, W2 = 2 * w, H2 = 2 * h;
   float acc[N], bv[N];
   const int v = threadIdx.x % v1;                             // constant along the walk: the stride is a multiple of v1
 #pragma unroll
   for (int i = 0; i < N; ++i) { acc[i] = 0.f; bv[i] = bias ? bias[v * N + i] : 0.f; }
-  for (size_t e = (size_t)blockIdx.x * kGlueThreads + threadIdx.x; e < nvec; e += (size_t)gridDim.x * kGlueThreads) {
-    const size_t pix = e / v1;
+  for (IDX e = (IDX)blockIdx.x * kGlueThreads + threadIdx.x; e < nvec; e += (IDX)gridDim.x * kGlueThreads) {
+    const IDX pix = e / v1;
     const int xx = (int)(pix % w);
-    const size_t r = pix / w;
+    const IDX r = pix / w;
     const int yy = (int)(r % h);
-    const size_t b = r / h;
+    const IDX b = r / h;
     float g00[N], g01[N], g10[N], g11[N];
-    load_folded<BF>(gout, b, 2 * yy, 2 * xx, H2, W2, pad, vt, v, g00);
-    load_folded<BF>(gout, b, 2 * yy, 2 * xx + 1, H2, W2, pad, vt, v, g01);
-    load_folded<BF>(gout, b, 2 * yy + 1, 2 * xx, H2, W2, pad, vt, v, g10);
-    load_folded<BF>(gout, b, 2 * yy + 1, 2 * xx + 1, H2, W2, pad, vt, v, g11);
+    load_folded<BF, IDX>(gout, b, 2 * yy, 2 * xx, H2, W2, pad, vt, v, g00);
+    load_folded<BF, IDX>(gout, b, 2 * yy, 2 * xx + 1, H2, W2, pad, vt, v, g01);
+    load_folded<BF, IDX>(gout, b, 2 * yy + 1, 2 * xx, H2, W2, pad, vt, v, g10);
+    load_folded<BF, IDX>(gout, b, 2 * yy + 1, 2 * xx + 1, H2, W2, pad, vt, v, g11);
     Vec16<BF> a;
     a.raw = x[e];
     float f[N];
@@ -857,23 +861,23 @@ __global__ void __launch_bounds__(kGlueThreads) elu_up2_cat_bwd_x_kernel(const u
 }
 
 // one thread per 16-byte vector of grad_skip [B, 2h, 2w, C2]: the channel slice of grad_out (ring gradients folded in if pad)
-template <bool BF>
+template <bool BF, class IDX>
 __global__ void __launch_bounds__(256) cat_bwd_skip_kernel(const uint4* __restrict__ gout, uint4* __restrict__ gskip, int H2, int W2,
-                                                           int v1, int v2, int pad, size_t nvec) {
-  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                           int v1, int v2, int pad, IDX nvec) {
+  const IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nvec) return;
-  const size_t pix = e / v2;
+  const IDX pix = e / v2;
   const int v = (int)(e - pix * v2);
   if (!pad) {
     gskip[e] = gout[pix * (v1 + v2) + v1 + v];
     return;
   }
   const int X = (int)(pix % W2);
-  const size_t r = pix / W2;
+  const IDX r = pix / W2;
   const int Y = (int)(r % H2);
-  const size_t b = r / H2;
+  const IDX b = r / H2;
   float f[Vec16<BF>::N];
-  load_folded<BF>(gout, b, Y, X, H2, W2, pad, v1 + v2, v1 + v, f);
+  load_folded<BF, IDX>(gout, b, Y, X, H2, W2, pad, v1 + v2, v1 + v, f);
   Vec16<BF> o;
   o.set_all(f);
   gskip[e] = o.raw;
@@ -881,13 +885,13 @@ __global__ void __launch_bounds__(256) cat_bwd_skip_kernel(const uint4* __restri
 
 // y = ELU(x + bias[c]) (ConvBlock: the convolution's bias and its ELU, model/layers.py:106-117); y gets the reflected ring if
 // pad (then y is [B, H+2, W+2, C]); without pad y may alias x
-template <bool BF>
+template <bool BF, class IDX>
 __global__ void __launch_bounds__(256) bias_elu_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ bias,
-                                                           uint4* __restrict__ y, int H, int W, int vpp, int pad, size_t nvec) {
-  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                           uint4* __restrict__ y, int H, int W, int vpp, int pad, IDX nvec) {
+  const IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nvec) return;
   constexpr int N = Vec16<BF>::N;
-  const size_t pix = e / vpp;
+  const IDX pix = e / vpp;
   const int v = (int)(e - pix * vpp);
   Vec16<BF> a;
   a.raw = x[e];
@@ -901,30 +905,30 @@ __global__ void __launch_bounds__(256) bias_elu_fwd_kernel(const uint4* __restri
     return;
   }
   const int xx = (int)(pix % W);
-  const size_t r = pix / W;
-  store_with_ring(y, o.raw, r / H, (int)(r % H), xx, H, W, pad, vpp, v);
+  const IDX r = pix / W;
+  store_with_ring<IDX>(y, o.raw, r / H, (int)(r % H), xx, H, W, pad, vpp, v);
 }
 // grad_x = grad_y * ELU'(.) written from the OUTPUT y as ATen's in-place ELU does (y <= 0 ? y + 1 : 1: nn.ELU(inplace=True)
 // keeps only y); ring gradients folded in if pad; per-channel sums of grad_x for the bias gradient
-template <bool BF>
+template <bool BF, class IDX>
 __global__ void __launch_bounds__(kGlueThreads) bias_elu_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ gy,
                                                                     uint4* __restrict__ gx, float* __restrict__ partial, int H, int W,
-                                                                    int vpp, int pad, size_t nvec) {
+                                                                    int vpp, int pad, IDX nvec) {
   constexpr int N = Vec16<BF>::N;
   float acc[N];
   const int v = threadIdx.x % vpp;
 #pragma unroll
   for (int i = 0; i < N; ++i) acc[i] = 0.f;
-  for (size_t e = (size_t)blockIdx.x * kGlueThreads + threadIdx.x; e < nvec; e += (size_t)gridDim.x * kGlueThreads) {
-    const size_t pix = e / vpp;
+  for (IDX e = (IDX)blockIdx.x * kGlueThreads + threadIdx.x; e < nvec; e += (IDX)gridDim.x * kGlueThreads) {
+    const IDX pix = e / vpp;
     const int xx = (int)(pix % W);
-    const size_t r = pix / W;
+    const IDX r = pix / W;
     const int yy = (int)(r % H);
-    const size_t b = r / H;
+    const IDX b = r / H;
     Vec16<BF> a;
-    a.raw = y[pvec(b, yy, xx, H, W, pad, vpp, v)];
+    a.raw = y[pvec<IDX>(b, yy, xx, H, W, pad, vpp, v)];
     float g[N], f[N];
-    load_folded<BF>(gy, b, yy, xx, H, W, pad, vpp, v, g);
+    load_folded<BF, IDX>(gy, b, yy, xx, H, W, pad, vpp, v, g);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const float yv = a.get(i);
@@ -949,6 +953,7 @@ static int glue_check(const void* x, int dtype, int B, int C1, int C2, int h, in
 }
 // grid of the reducing kernels: the walk's stride (grid x 256) must be a multiple of the vectors per pixel (a power of two
 // <= 256 here, else the caller is refused), and at most 8 blocks per SM
+static bool glue_small(size_t padded_vectors) { return padded_vectors + (size_t)148 * 8 * 256 < ((size_t)1 << 31); }   // incl. the grid-stride overshoot
 static int glue_reduce_blocks(size_t nvec, int vpp) {
   if (vpp < 1 || vpp > kGlueThreads || (kGlueThreads % vpp)) return 0;
   size_t n = (nvec + kGlueThreads - 1) / kGlueThreads;
@@ -974,8 +979,15 @@ extern "C" int dvs_elu_up2_cat_fwd(const void* x, const void* skip, const float*
   const size_t nvec = (size_t)B * 4 * h * w * (v1 + v2);
   const unsigned int nblk = (unsigned int)((nvec + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bf) elu_up2_cat_fwd_kernel<true><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, bias, (uint4*)out, h, w, v1, v2, pad, nvec);
-  else elu_up2_cat_fwd_kernel<false><<<nblk, 256, 0, st>>>((const uint4*)x, (const uint4*)skip, bias, (uint4*)out, h, w, v1, v2, pad, nvec);
+#define DVS_GLUE_LAUNCH(K, GRID, BLOCK, ...)                                                                     \
+  do {                                                                                                          \
+    if (small && bf) K<true, unsigned int><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                                 \
+    else if (small) K<false, unsigned int><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                                 \
+    else if (bf) K<true, size_t><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                                           \
+    else K<false, size_t><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                                                  \
+  } while (0)
+  const bool small = glue_small((size_t)B * (2 * h + 2) * (2 * w + 2) * (v1 + v2));
+  DVS_GLUE_LAUNCH(elu_up2_cat_fwd_kernel, nblk, 256, (const uint4*)x, (const uint4*)skip, bias, (uint4*)out, h, w, v1, v2, pad, nvec);
   DVS_CUDA_TRY(cudaGetLastError());
   return DVS_OK;
 }
@@ -995,8 +1007,8 @@ extern "C" int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, const fl
   const int bx = glue_reduce_blocks(nx, v1);
   if (!bx) return DVS_EINVAL;
   float* partial = grad_bias ? static_cast<float*>(workspace) : nullptr;
-  if (bf) elu_up2_cat_bwd_x_kernel<true><<<bx, kGlueThreads, 0, st>>>((const uint4*)x, (const uint4*)grad_out, bias, (uint4*)grad_x, partial, h, w, v1, v2, pad, nx);
-  else elu_up2_cat_bwd_x_kernel<false><<<bx, kGlueThreads, 0, st>>>((const uint4*)x, (const uint4*)grad_out, bias, (uint4*)grad_x, partial, h, w, v1, v2, pad, nx);
+  const bool small = glue_small((size_t)B * (2 * h + 2) * (2 * w + 2) * (v1 + v2));
+  DVS_GLUE_LAUNCH(elu_up2_cat_bwd_x_kernel, bx, kGlueThreads, (const uint4*)x, (const uint4*)grad_out, bias, (uint4*)grad_x, partial, h, w, v1, v2, pad, nx);
   DVS_CUDA_TRY(cudaGetLastError());
   if (grad_bias) {
     channel_reduce_kernel<<<(C1 + 7) / 8, 256, 0, st>>>(partial, bx, C1, grad_bias);
@@ -1005,8 +1017,7 @@ extern "C" int dvs_elu_up2_cat_bwd(const void* x, const void* grad_out, const fl
   if (v2 > 0) {
     const size_t ns = (size_t)B * 4 * h * w * v2;
     const unsigned int nb = (unsigned int)((ns + 255) / 256);
-    if (bf) cat_bwd_skip_kernel<true><<<nb, 256, 0, st>>>((const uint4*)grad_out, (uint4*)grad_skip, 2 * h, 2 * w, v1, v2, pad, ns);
-    else cat_bwd_skip_kernel<false><<<nb, 256, 0, st>>>((const uint4*)grad_out, (uint4*)grad_skip, 2 * h, 2 * w, v1, v2, pad, ns);
+    DVS_GLUE_LAUNCH(cat_bwd_skip_kernel, nb, 256, (const uint4*)grad_out, (uint4*)grad_skip, 2 * h, 2 * w, v1, v2, pad, ns);
     DVS_CUDA_TRY(cudaGetLastError());
   }
   return DVS_OK;
@@ -1023,8 +1034,8 @@ extern "C" int dvs_bias_elu_fwd(const void* x, const float* bias, void* y, int d
   const size_t nvec = (size_t)B * H * W * vpp;
   const unsigned int nblk = (unsigned int)((nvec + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (bf) bias_elu_fwd_kernel<true><<<nblk, 256, 0, st>>>((const uint4*)x, bias, (uint4*)y, H, W, vpp, pad, nvec);
-  else bias_elu_fwd_kernel<false><<<nblk, 256, 0, st>>>((const uint4*)x, bias, (uint4*)y, H, W, vpp, pad, nvec);
+  const bool small = glue_small((size_t)B * (H + 2) * (W + 2) * vpp);
+  DVS_GLUE_LAUNCH(bias_elu_fwd_kernel, nblk, 256, (const uint4*)x, bias, (uint4*)y, H, W, vpp, pad, nvec);
   DVS_CUDA_TRY(cudaGetLastError());
   return DVS_OK;
 }
@@ -1043,8 +1054,8 @@ extern "C" int dvs_bias_elu_bwd(const void* y, const void* grad_y, void* grad_x,
   if (!nblk) return DVS_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = grad_bias ? static_cast<float*>(workspace) : nullptr;
-  if (bf) bias_elu_bwd_kernel<true><<<nblk, kGlueThreads, 0, st>>>((const uint4*)y, (const uint4*)grad_y, (uint4*)grad_x, partial, H, W, vpp, pad, nvec);
-  else bias_elu_bwd_kernel<false><<<nblk, kGlueThreads, 0, st>>>((const uint4*)y, (const uint4*)grad_y, (uint4*)grad_x, partial, H, W, vpp, pad, nvec);
+  const bool small = glue_small((size_t)B * (H + 2) * (W + 2) * vpp);
+  DVS_GLUE_LAUNCH(bias_elu_bwd_kernel, nblk, kGlueThreads, (const uint4*)y, (const uint4*)grad_y, (uint4*)grad_x, partial, H, W, vpp, pad, nvec);
   DVS_CUDA_TRY(cudaGetLastError());
   if (grad_bias) {
     channel_reduce_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, C, grad_bias);
