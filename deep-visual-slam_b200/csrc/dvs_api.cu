@@ -8,7 +8,7 @@ int& last_cuda_error() {
 }
 }  // namespace dvs
 
-extern "C" int dvs_version(void) { return 100; }   // 0.1.0
+extern "C" int dvs_version(void) { return 200; }   // 0.2.0: round-2 ABI (input formats, pose parameters, decoder kernels)
 
 extern "C" int dvs_last_cuda_error(void) { return dvs::last_cuda_error(); }
 
