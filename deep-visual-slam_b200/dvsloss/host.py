@@ -1,13 +1,14 @@
 """Host-resident entry point of the fused loss: inputs and results live in pinned host memory.
 
-``HostLossPipeline`` splits the batch into equal chunks and overlaps, on three CUDA streams, the host->device copies
+``HostLossPipeline`` splits the batch into chunks (tapered by default: 16 -> 6, 4, 3, 2, 1) and overlaps, on three CUDA streams, the host->device copies
 (all chunks are enqueued up-front into their own staging buffers -- a full batch is 0.2 GB of 180 -- so the copy engine
 never waits for the host), the fused loss forward+backward of chunk k as soon as its inputs have landed, and the
 device->host copy of the gradients of chunk k-1.
 Chunking is exact: every reduction of the loss is a batch mean (vo/learner_new.py:244, vo/learner_func.py:174), so
 the batch loss is the B_c/B-weighted sum of the chunk losses and the gradients of a chunk are B_c/B of its stand-alone
 gradients (tests/test_gpu_fused.py checks this decomposition).  PCIe is the bound of this path (203 MB in per step
-at the benchmark size against 1.8 ms of kernels), which is what the overlap is for.
+at the benchmark size against 1.6 ms of kernels), which is what the overlap is for.  The whole step is recorded as one CUDA graph
+the first time a set of pinned buffers is seen and replayed afterwards.
 """
 from __future__ import annotations
 
@@ -20,7 +21,7 @@ from .ops import images_u8_to_f32
 
 
 class HostLossPipeline:
-    def __init__(self, B: int, H: int, W: int, disp_sizes: Sequence[Sequence[int]], num_sources: int = 2, chunks=4,
+    def __init__(self, B: int, H: int, W: int, disp_sizes: Sequence[Sequence[int]], num_sources: int = 2, chunks="taper",
                  device=None, uint8_images: bool = False, u8_in_kernel: bool = False, graph: bool = True, **loss_kwargs):
         """``chunks``: a count (equal chunks), a sequence of chunk sizes summing to B, "taper" or "ramp".  Chunk losses and gradients are
         combined with the weights B_c / B, so unequal chunks are exact too; tapering the sizes (16 -> 6,4,3,2,1) shortens the part
