@@ -251,3 +251,31 @@ def test_disp_head_reads_a_ring_carrying_activation(dtype):
     assert torch.equal(outs[0][0], outs[1][0])
     for a, r in zip(outs[0][1], outs[1][1]):
         assert float((a.double() - r.double()).abs().max()) <= (1e-6 if dtype == torch.float32 else 2 ** -7) * float(r.double().abs().max())
+
+
+@pytest.mark.parametrize("cout", [16, 24, 6])
+def test_convblock_fused_and_fallback_paths_equal_the_stock_block(cout):
+    """ConvBlock = Conv3x3 + ELU (model/layers.py:106-117): 16 output channels take the fused bias + ELU kernel; 24 (6 four-channel
+    vectors: not a power of two, which the bias-gradient reduction wants) and 6 (not a multiple of 4) take the stock fall-backs;
+    all equal the stock block."""
+    from model.layers import ConvBlock
+    torch.manual_seed(cout)
+    dev = torch.device("cuda:0")
+    blk = ConvBlock(8, cout).to(dev)
+    x = torch.randn(2, 8, 13, 17, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    outs = []
+    try:
+        for fused in (True, False):
+            ConvBlock.fused_bias_elu = fused
+            blk.zero_grad()
+            y = blk(x)
+            g = torch.autograd.grad(y, [x] + list(blk.parameters()), torch.ones_like(y) * 0.1)
+            outs.append((y.detach().clone(), [t.clone() for t in g]))
+    finally:
+        ConvBlock.fused_bias_elu = True
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert float((outs[0][0] - outs[1][0]).abs().max()) <= 2e-6
+    for a, r in zip(outs[0][1], outs[1][1]):
+        assert float((a - r).abs().max()) <= 1e-5 * (float(r.abs().max()) + 1e-12)
