@@ -279,3 +279,32 @@ def test_convblock_fused_and_fallback_paths_equal_the_stock_block(cout):
     assert float((outs[0][0] - outs[1][0]).abs().max()) <= 2e-6
     for a, r in zip(outs[0][1], outs[1][1]):
         assert float((a - r).abs().max()) <= 1e-5 * (float(r.abs().max()) + 1e-12)
+
+
+def test_depthnet_resnet50_fused_decoder_equals_the_stock_sequence():
+    """BASELINE configs[3] uses the ResNet-50 encoder (skip channels 64 / 256 / 512 / 1024): the fused decoder path (glue kernels,
+    ring-carrying activations, fused heads) against the stock sequence, fp32, values and every parameter gradient."""
+    from model.depthnet import DepthNet
+    from model.layers import ConvBlock
+    torch.manual_seed(4)
+    dev = torch.device("cuda:0")
+    net = DepthNet(50, False).to(dev).eval().to(memory_format=torch.channels_last)
+    x = torch.rand(1, 3, 64, 96, device=dev).contiguous(memory_format=torch.channels_last)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    outs = {}
+    try:
+        for fused in (True, False):
+            DepthNet.fused_glue = DepthNet.fused_heads = DepthNet.padded_activations = ConvBlock.fused_bias_elu = fused
+            net.zero_grad()
+            o = net(x)
+            sum(v.mean() for v in o.values()).backward()
+            outs[fused] = ({k: v.detach().clone() for k, v in o.items()},
+                           {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None})
+    finally:
+        DepthNet.fused_glue = DepthNet.fused_heads = DepthNet.padded_activations = ConvBlock.fused_bias_elu = True
+        torch.backends.cudnn.allow_tf32 = tf32
+    for k in outs[False][0]:
+        assert torch.allclose(outs[True][0][k], outs[False][0][k], rtol=0, atol=1e-5), k
+    for n, gr in outs[False][1].items():
+        assert float((outs[True][1][n] - gr).abs().max()) <= 2e-3 * (float(gr.abs().max()) + 1e-12), n
