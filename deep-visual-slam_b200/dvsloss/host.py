@@ -74,6 +74,7 @@ class HostLossPipeline:
                 raw=[torch.empty(Bc, 3, H, W, dtype=torch.uint8, device=d) for _ in range(1 + num_sources)] if uint8_images else None))
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(d) for _ in range(3))
         self.graph_enabled = bool(graph)
+        self.max_graphs = 8                         # distinct sets of pinned buffers that get their own recorded graph
         self._graphs: Dict = {}
         self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
         self.ev_run = [torch.cuda.Event() for _ in range(chunks)]
@@ -91,6 +92,11 @@ class HostLossPipeline:
                [h_out["loss"]] + h_out["gd"] + h_out["gT"]
         key = tuple(t.data_ptr() for t in flat)
         g = self._graphs.get(key)
+        if g is None and len(self._graphs) >= self.max_graphs:
+            # a caller that hands over fresh pinned buffers every step would otherwise record (and keep alive) a graph per step
+            self._enqueue(h_in, h_out)
+            self.s_out.synchronize()
+            return
         if g is None:
             # two eager steps first (allocator warm-up, lazy module loading), then capture on a side stream
             for _ in range(2):

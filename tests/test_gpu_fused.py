@@ -597,6 +597,13 @@ def test_host_pipeline_graph_replay_matches_eager_enqueue():
     HostLossPipeline(B, H, W, sizes, 2, chunks=2, device=dev, noise=None, graph=False).run(h_in, eager)
     pipe.run(h_in, graphed)
     assert torch.equal(eager["loss"], graphed["loss"]) and torch.equal(eager["gd"][1], graphed["gd"][1])
+    # fresh output buffers every call: at most `max_graphs` graphs are recorded, later buffer sets run un-recorded, same results
+    pipe.max_graphs = 2
+    for _ in range(3):
+        fresh = mk_out()
+        pipe.run(h_in, fresh)
+        assert torch.equal(eager["loss"], fresh["loss"]) and torch.equal(eager["gd"][0], fresh["gd"][0])
+    assert len(pipe._graphs) == 2
     noisy = HostLossPipeline(B, H, W, sizes, 2, chunks=2, device=dev, noise="kernel", graph=True)
     noisy.run(h_in, graphed)                                      # capture (2 eager steps + capture do not replay)
     n0 = dvsloss.noise_state()
