@@ -9,15 +9,17 @@ Workload (BASELINE.json configs[1]): 640x480, batch 16 per GPU, 2 source frames,
 Redwood-shaped geometrically consistent triplets.  One step = one forward + backward of the loss
 for one batch.  Metric: warped pixels per second, B*S*N*H*W / t, whole job.  Prints ONE JSON line on rank 0.
 
-  value        device-timed (CUDA events), inputs resident in HBM, L2 flushed between steps
+  value        device-timed (CUDA events), inputs resident in HBM, L2 flushed between steps; the public call
+               (view_synthesis_loss + backward: four kernel launches) is recorded once as a CUDA graph and replayed
+               (config.launch; --eager-launch times the plain Python calls: +2 %)
   e2e          same step through the public host-resident API (dvsloss.HostLossPipeline) from pinned HOST buffers:
                H2D of every input, D2H of the losses and all gradients, inside the timed region (batch chunks
                overlap copy and compute on three streams; PCIe-bound)
-  roofline     dominant kernel (fused_tile_kernel) timed with events around its launch inside libdvsloss.so;
+  roofline     dominant kernel (fused_pair_kernel, the two-source tile kernel) timed with events around its launch inside libdvsloss.so;
                achieved = bytes_alg(B,H,W,N,S) / t   (SURVEY 8d figure, 303.9 B per full-res pixel at N=2,S=4)
-  cpu_baseline the oracle port (op-for-op restatement of the reference's PyTorch path) on the host cores, on a
-               bounded sample (batch 2 of the same workload); rank 0, N=1 only
-  eager_cuda_baseline   the same op sequence run eagerly on the GPU (the reference's own CUDA path), N=1 only
+  cpu_baseline the unmodified reference staged in baseline/_ref (kind "reference"; the oracle port only where the copy is
+               absent) on the host cores, on a bounded sample (batch 2 of the same workload); rank 0, N=1 only
+  eager_cuda_baseline   the same reference code run eagerly on the GPU (the reference's own CUDA path), N=1 only
   noise_torch  the same step with torch.randn noise tensors (the reference's RNG contract) instead of the in-kernel generator
   train_step_r50x4   BASELINE configs[3]: ResNet-50, 1280x960, sources +-1 and +-2, batch 8/GPU (5 steps)
   train_step   BASELINE configs[2]: full VO training step (stock ResNet-18 DepthNet + PoseNet in bf16 autocast, fused
@@ -402,6 +404,28 @@ def run_b200(args):
         flush.zero_()
         step()
     barrier()
+    # The timed step is the public call (view_synthesis_loss + backward) recorded once as a CUDA graph and replayed: four
+    # kernel launches per step either way, without the Python / autograd dispatch between them (--eager-launch times the plain calls)
+    launch_mode, run_step = "eager", step
+    if not args.eager_launch:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            for t in d_in["disps"] + d_in["Ts"]:
+                t.grad = None
+            g_step = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_step):
+                step()
+            for _ in range(2):
+                g_step.replay()
+            torch.cuda.synchronize()
+            launch_mode, run_step = "cuda_graph", g_step.replay
+        except Exception as exc:                                   # keep the bench line: fall back to plain calls
+            print(f"# graph capture of the loss step failed ({exc!r}); timing eager launches", file=sys.stderr)
+            torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -409,7 +433,7 @@ def run_b200(args):
     for e0, e1 in evs:
         flush.zero_()
         e0.record()
-        step()
+        run_step()
         e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -594,7 +618,7 @@ def run_b200(args):
                 "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_text(B), "noise": "automask noise from the in-kernel generator",
-                           "l2": "256 MB buffer written between timed steps (outside the event pairs)", "sharding": f"batch, {world} independent rank(s), no data-path collective"},
+                           "l2": "256 MB buffer written between timed steps (outside the event pairs)", "launch": launch_mode, "sharding": f"batch, {world} independent rank(s), no data-path collective"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "h2d_gbs_per_rank": rates, "h2d_raw_copy_gbs_per_rank": raw_rates, "host_affinity": affinity,
@@ -623,6 +647,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
     ap.add_argument("--e2e-chunks", default="taper", help="batch chunks of the host-resident pipeline (e2e leg): 'taper' (16 -> "
                     "6,4,3,2,1), a count, or comma-separated chunk sizes summing to --batch")
+    ap.add_argument("--eager-launch", action="store_true", help="time the device-resident step as plain Python calls instead of a "
+                    "CUDA-graph replay of the same calls")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-CUDA reference leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE configs[2])")
