@@ -136,8 +136,9 @@ __global__ void __launch_bounds__(NT, (NS <= 2 ? 2 : 1)) fused_tile_kernel(const
 
 // ------------------------------------------------------------------------------------------------ 3. post-pass
 // One launch after the tile kernel:
-//   blocks [0, B S)        per (image, scale): fixed-order reduction over the image's tiles (warp y reduces values v = y,
-//                          y+8, ...: lane-strided, then xor-shuffle -> deterministic); pose moments -> dL/dP -> dL/dT =
+//   blocks [0, B S)        per (image, scale): fixed-order reduction over the image's tiles (consecutive threads own
+//                          consecutive values, groups of threads stride the tiles, groups added in order -> deterministic);
+//                          pose moments -> dL/dP -> dL/dT =
 //                          K^T dL/dP (-> the six pose parameters when those were the inputs); smoothness mean-coupling
 //                          coefficient.  The block that finishes LAST (ticket counter) also forms loss/s and loss from
 //                          the per-image sums, again in a fixed order.
@@ -175,15 +176,34 @@ __global__ void __launch_bounds__(256) postpass_kernel(const __grid_constant__ F
   }
   const int b = blockIdx.x % f.B, s = blockIdx.x / f.B;
   const int nv = 3 + 12 * f.N;
-  const int lane = tid & 31, wy = tid >> 5;
   __shared__ float res[3 + 12 * kMaxN];
+  __shared__ float grp[8][64];
   __shared__ int last;
-  for (int v = wy; v < nv; v += 8) {
-    float a = 0.f;
-    for (int tl = lane; tl < f.tiles_per_img; tl += 32)
-      a += f.part[((size_t)(b * f.tiles_per_img + tl) * f.S + s) * nv + v];
-    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) res[v] = a;
+  {
+    // fixed-order sum over the image's tiles: consecutive threads own consecutive values (one coalesced line per tile), G groups
+    // of threads stride the tiles with four independent loads in flight, then the groups are added in order
+    const int VW = nv <= 32 ? 32 : 64, G = 256 / VW;
+    const int v = tid % VW, gq = tid / VW;
+    if (v < nv) {
+      const size_t stride = (size_t)f.S * nv;
+      const float* base = f.part + ((size_t)b * f.tiles_per_img * f.S + s) * nv + v;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int tl = gq;
+      for (; tl + 3 * G < f.tiles_per_img; tl += 4 * G) {
+        a0 += base[(size_t)tl * stride];
+        a1 += base[(size_t)(tl + G) * stride];
+        a2 += base[(size_t)(tl + 2 * G) * stride];
+        a3 += base[(size_t)(tl + 3 * G) * stride];
+      }
+      for (; tl < f.tiles_per_img; tl += G) a0 += base[(size_t)tl * stride];
+      grp[gq][v] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+    if (tid < nv) {
+      float a = 0.f;
+      for (int q = 0; q < G; ++q) a += grp[q][tid];
+      res[tid] = a;
+    }
   }
   __syncthreads();
   if (tid < 3) f.perimg[(s * f.B + b) * 3 + tid] = res[tid];
