@@ -20,6 +20,28 @@ from .functional import view_synthesis_loss
 from .ops import images_u8_to_f32
 
 
+def chunk_sizes(B: int, chunks) -> List[int]:
+    """Chunk sizes of a batch of B: ``chunks`` is a count (equal chunks), a sequence of sizes summing to B, "taper" (each chunk
+    ~3/8 of what is left: 16 -> 6, 4, 3, 2, 1 -- copy-bound steps want the short chunk LAST) or "ramp" (the taper reversed --
+    kernel-bound steps want the short chunk FIRST)."""
+    if isinstance(chunks, str):
+        if chunks not in ("taper", "ramp"):
+            raise ValueError("chunks: a count, a sequence of sizes, 'taper' or 'ramp'")
+        sizes, rem = [], B
+        while rem:
+            sizes.append(-(-rem * 3 // 8))
+            rem -= sizes[-1]
+        return sizes if chunks == "taper" else sizes[::-1]
+    if isinstance(chunks, int):
+        if chunks < 1 or B % chunks:
+            raise ValueError("the batch must split into equal chunks (or give the chunk sizes)")
+        return [B // chunks] * chunks
+    sizes = [int(v) for v in chunks]
+    if sum(sizes) != B or min(sizes) < 1:
+        raise ValueError("chunk sizes must be positive and sum to the batch size")
+    return sizes
+
+
 class HostLossPipeline:
     def __init__(self, B: int, H: int, W: int, disp_sizes: Sequence[Sequence[int]], num_sources: int = 2, chunks="taper",
                  device=None, uint8_images: bool = False, u8_in_kernel: bool = False, graph: bool = True, **loss_kwargs):
@@ -30,21 +52,7 @@ class HostLossPipeline:
         ``graph``: record the whole step -- every copy, kernel and cross-stream dependency -- as one CUDA graph the first time a
         given set of pinned buffers is seen and replay it afterwards: the step is then bound by the copy engines alone, not by
         ~150 host-side launches (the in-kernel noise counter is a device scalar, so replays keep drawing fresh noise)."""
-        if chunks in ("taper", "ramp"):                            # 16 -> 6, 4, 3, 2, 1: each chunk ~3/8 of what is left
-            sizes, rem = [], B
-            while rem:
-                sizes.append(-(-rem * 3 // 8))
-                rem -= sizes[-1]
-            # copy-bound steps (fp32 frames) want the short chunk LAST, kernel-bound ones (uint8 frames) want it FIRST
-            chunks = sizes if chunks == "taper" else sizes[::-1]
-        if isinstance(chunks, int):
-            if B % chunks:
-                raise ValueError("the batch must split into equal chunks (or give the chunk sizes)")
-            sizes = [B // chunks] * chunks
-        else:
-            sizes = [int(v) for v in chunks]
-            if sum(sizes) != B or min(sizes) < 1:
-                raise ValueError("chunk sizes must be positive and sum to the batch size")
+        sizes = chunk_sizes(B, chunks)
         self.sizes = sizes
         self.starts = [sum(sizes[:i]) for i in range(len(sizes))]
         chunks = len(sizes)

@@ -86,3 +86,18 @@ def test_two_rank_sharding_matches_global_batch(tmp_path):
     _standin_loss(joint, full).backward()
     g_ref = _grads(nets)
     assert torch.allclose(g_ddp, g_ref, rtol=1e-4, atol=1e-7), float((g_ddp - g_ref).abs().max())
+
+
+def test_host_pipeline_chunk_rules():
+    """dvsloss.host.chunk_sizes: the batch split of the host-resident pipeline (pure host logic)."""
+    from dvsloss.host import chunk_sizes
+    assert chunk_sizes(16, "taper") == [6, 4, 3, 2, 1] and chunk_sizes(16, "ramp") == [1, 2, 3, 4, 6]
+    assert chunk_sizes(16, 8) == [2] * 8 and chunk_sizes(16, [5, 4, 3, 2, 2]) == [5, 4, 3, 2, 2]
+    for B in range(1, 70):
+        for rule in ("taper", "ramp"):
+            s = chunk_sizes(B, rule)
+            assert sum(s) == B and min(s) >= 1
+            assert s == sorted(s, reverse=(rule == "taper"))            # tapering: the short chunk last; ramp: first
+    for bad in (3, [8, 7], [16, 0], "steps"):
+        with pytest.raises(ValueError):
+            chunk_sizes(16, bad)
