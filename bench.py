@@ -48,6 +48,15 @@ METRIC = "photometric_loss_fwd_bwd_warped_pixels_per_s"
 UNIT = "Gpix/s"
 
 
+_REAL_STDOUT = None
+
+
+def emit(text: str) -> None:
+    """The one JSON line: to the real stdout (see main)."""
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (text + "\n").encode())
+
+
 def workload_text(B):
     return (f"isolated photometric loss fwd+bwd, {W}x{H}, batch {B}/GPU, {NSRC} sources, {NSCALE} scales "
             f"(BASELINE configs[1]); consistent synthetic triplets")
@@ -258,7 +267,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------ eager CUDA leg
@@ -632,7 +641,7 @@ def run_b200(args):
                                 "note": "same step with the reference's RNG contract (torch.randn per scale handed to the kernel) instead of the in-kernel generator; this rank"}}
         if eager and "value" in eager:
             line["eager_cuda_baseline"]["speedup_device_timed"] = value / eager["value"]
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -658,6 +667,12 @@ def main():
     ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--no-train-big", action="store_true", help="skip the BASELINE configs[3] training-step leg (r50x4)")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout at N > 1), so the
+    # process's stdout is pointed at stderr for the run and the JSON line goes to the real stdout through a saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
