@@ -557,7 +557,8 @@ def bias_elu(x: torch.Tensor, bias=None, pad: bool = False) -> torch.Tensor:
 
 # ---------------------------------------------------------------------------------------------------- network inputs
 def pack_net_inputs_supported(target: torch.Tensor, sources) -> bool:
-    ok = lambda t: t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] == 3 and t.is_contiguous()
+    ok = lambda t: (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] == 3 and t.is_contiguous()
+                    and t.data_ptr() % 16 == 0)                 # 128-bit loads: a batch slice at an odd offset takes the stock path
     return (ok(target) and 1 <= len(sources) <= 4 and all(ok(s) and s.shape == target.shape for s in sources)
             and (target.shape[2] * target.shape[3]) % 8 == 0)
 
