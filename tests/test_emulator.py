@@ -73,3 +73,20 @@ def test_emulator_kink_free_every_element_strict(B, H, W, seed):
     prob = parity.kink_free_problem(B, H, W, seed)
     stats = parity.check_parity(emu_impl, prob, verbose=True, expect_kink_free=True)
     assert stats["grad_disp_relinf_max"] < 1e-3
+
+
+@pytest.mark.parametrize("B,H,W,N,dims,auto_mask", [
+    (1, 31, 61, 2, [(31, 61), (1, 1)], True),              # a 1x1 disparity map: every fine pixel reads the same coarse element
+    (2, 33, 40, 2, [(1, 40), (33, 1)], True),              # one-row and one-column disparity maps
+    (1, 3, 3, 2, [(3, 3), (1, 1)], True),                  # image smaller than the SSIM window's reach on every side
+    (1, 31, 31, 3, [(31, 31), (15, 15), (7, 7)], False),   # one pixel past the 30x30 tile in both directions
+    (1, 2, 200, 1, [(2, 200), (1, 100)], True),            # two rows, many tiles across
+    (1, 200, 2, 4, [(200, 2), (100, 1)], True),            # two columns, many tiles down
+])
+def test_emulator_degenerate_disparity_sizes_and_thin_images(B, H, W, N, dims, auto_mask):
+    """Edge geometry: reflection at both borders inside one pixel's window, coarse maps of extent 1, tile tails of one pixel."""
+    p = make_problem(B, H, W, N, len(dims), seed=H * 7 + W, consistent=False)
+    prob = parity.problem_from_synthetic(p, auto_mask)
+    rng = np.random.default_rng(H + W)
+    prob["disps"] = [rng.uniform(0.05, 0.9, (B, 1, h, w)).astype(np.float32) for h, w in dims]
+    parity.check_parity(emu_impl, prob, verbose=True)
