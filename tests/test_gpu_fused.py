@@ -71,6 +71,24 @@ def test_fused_non_pyramid_disparity_sizes():
     parity.check_parity(cuda_impl, prob, verbose=True)
 
 
+@pytest.mark.parametrize("B,H,W,N,dims,auto_mask", [
+    (1, 31, 61, 2, [(31, 61), (1, 1)], True),              # a 1x1 disparity map
+    (2, 33, 40, 2, [(1, 40), (33, 1)], True),              # one-row and one-column disparity maps
+    (1, 3, 3, 2, [(3, 3), (1, 1)], True),                  # image smaller than the SSIM window's reach on every side
+    (1, 31, 31, 3, [(31, 31), (15, 15), (7, 7)], False),   # one pixel past the 30x30 tile in both directions
+    (1, 2, 200, 1, [(2, 200), (1, 100)], True),            # two rows, many tiles across
+    (1, 200, 2, 4, [(200, 2), (100, 1)], True),            # two columns, many tiles down
+])
+def test_fused_degenerate_disparity_sizes_and_thin_images(B, H, W, N, dims, auto_mask):
+    """The real launch geometry on edge shapes (same cases as tests/test_emulator.py): grid tails of one pixel, coarse maps
+    of extent 1, reflection at both borders inside one window."""
+    p = make_problem(B, H, W, N, len(dims), seed=H * 7 + W, consistent=False)
+    prob = parity.problem_from_synthetic(p, auto_mask)
+    rng = np.random.default_rng(H + W)
+    prob["disps"] = [rng.uniform(0.05, 0.9, (B, 1, h, w)).astype(np.float32) for h, w in dims]
+    parity.check_parity(cuda_impl, prob, verbose=True)
+
+
 # Share of disparity elements with a kink pixel in their footprint on the 640x480 consistent problems (measured on the
 # float64 oracle: 5.5 % / 16.1 % / 45.4 % / 87.4 % at scales 0..3 -- a scale-3 element gathers 256 pixels).  Stored so
 # that a locator that silently starts excluding more shows up; those elements are still held to the footprint-scaled
