@@ -90,3 +90,11 @@ def test_emulator_degenerate_disparity_sizes_and_thin_images(B, H, W, N, dims, a
     rng = np.random.default_rng(H + W)
     prob["disps"] = [rng.uniform(0.05, 0.9, (B, 1, h, w)).astype(np.float32) for h, w in dims]
     parity.check_parity(emu_impl, prob, verbose=True)
+
+
+@pytest.mark.parametrize("i", range(0, 24, 3))
+def test_emulator_seeded_random_shapes(i):
+    """Every third case of tests/fuzz_cases.py on the block emulator (the GPU suite runs all of them through the C ABI)."""
+    import fuzz_cases
+    prob, gps = fuzz_cases.fuzz_case(i)
+    parity.check_parity(emu_impl, prob, grad_per_scale=gps, verbose=True)

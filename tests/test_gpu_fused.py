@@ -89,6 +89,15 @@ def test_fused_degenerate_disparity_sizes_and_thin_images(B, H, W, N, dims, auto
     parity.check_parity(cuda_impl, prob, verbose=True)
 
 
+@pytest.mark.parametrize("i", range(24))
+def test_fused_seeded_random_shapes(i):
+    """tests/fuzz_cases.py: random sizes (tile tails of every length), source / scale counts, disparity sizes, automask,
+    upstream gradients -- the real launches against the oracle."""
+    import fuzz_cases
+    prob, gps = fuzz_cases.fuzz_case(i)
+    parity.check_parity(cuda_impl, prob, grad_per_scale=gps, verbose=True)
+
+
 # Share of disparity elements with a kink pixel in their footprint on the 640x480 consistent problems (measured on the
 # float64 oracle: 5.5 % / 16.1 % / 45.4 % / 87.4 % at scales 0..3 -- a scale-3 element gathers 256 pixels).  Stored so
 # that a locator that silently starts excluding more shows up; those elements are still held to the footprint-scaled
