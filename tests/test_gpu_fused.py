@@ -483,12 +483,14 @@ def _problem_tensors(B, H, W, seed):
     return p, cut, Ts
 
 
-def test_fused_reads_bf16_disparities_and_uint8_images_in_kernel():
+@pytest.mark.parametrize("B,H,W", [(2, 96, 128), (2, 37, 53), (1, 61, 35), (3, 30, 31)])
+def test_fused_reads_bf16_disparities_and_uint8_images_in_kernel(B, H, W):
     """bf16 disparity maps (DepthNet under autocast) and uint8 frames (before ToTensor) go to the two-source
     kernel as they are; conversion on load is exact, so every result equals the call on the fp32-expanded tensors bit for bit
     (the bf16 gradients are the fp32 ones rounded to nearest even, i.e. what autograd's .to(bf16) backward would hand back)."""
     from dvsloss import view_synthesis_loss
-    p, cut, Ts = _problem_tensors(2, 96, 128, 41)
+    # odd sizes: byte / bf16 rows and images start at addresses that are not multiples of 4 (no packed loads may assume it)
+    p, cut, Ts = _problem_tensors(B, H, W, 41)
     q8 = lambda t: (t * 255).round().clamp(0, 255).to(torch.uint8)
     tgt8, src8 = cut(q8(p["target"])), [cut(q8(s)) for s in p["sources"]]
     # ToTensor runs on the host in the reference (vo/dataset/common.py:77): a true IEEE division.  (torch's CUDA kernel for
